@@ -1,0 +1,180 @@
+"""Synthetic checkpoints in the reference's state-dict layout.
+
+There are no pretrained weights on the build or GPU boxes and no network, so every
+test and benchmark runs on seeded random weights of the reference's architecture.
+Key names and shapes follow what ``Loader.get_gpt_weights`` / ``get_sovits_weights``
+hand to ``load_state_dict`` (reference gsv_tts/Loader.py:130-162, 80-95; SURVEY.md
+A.1, A.6).  Values are chosen so the network is *non-degenerate*: LayerNorm gamma/beta,
+the positional ``alpha`` scalars, weight-norm ``g`` and the zero-initialised coupling
+``post`` convolution (reference modules.py:479-480) are all randomised, otherwise a
+parity test against them would be vacuous.
+
+All draws come from a CPU ``torch.Generator`` so the same seed gives the same tensors
+on every machine with this torch build.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+GPT_CONFIG = {
+    "model": {
+        "hidden_dim": 512,
+        "embedding_dim": 512,
+        "head": 16,
+        "n_layer": 24,
+        "vocab_size": 1025,
+        "phoneme_vocab_size": 732,
+        "dropout": 0.0,
+        "EOS": 1024,
+    }
+}
+
+# a small config with the same head_dim (32) for fast CPU checks
+GPT_CONFIG_TINY = {
+    "model": {
+        "hidden_dim": 256,
+        "embedding_dim": 256,
+        "head": 8,
+        "n_layer": 3,
+        "vocab_size": 1025,
+        "phoneme_vocab_size": 732,
+        "dropout": 0.0,
+        "EOS": 1024,
+    }
+}
+
+_SOVITS_COMMON = dict(
+    inter_channels=192,
+    hidden_channels=192,
+    filter_channels=768,
+    n_heads=2,
+    n_layers=6,
+    kernel_size=3,
+    p_dropout=0.0,
+    resblock="1",
+    resblock_kernel_sizes=[3, 7, 11],
+    resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    upsample_rates=[10, 8, 2, 2, 2],
+    upsample_kernel_sizes=[16, 16, 8, 2, 2],
+)
+
+SOVITS_MODEL = {
+    "v2": dict(_SOVITS_COMMON, upsample_initial_channel=512, gin_channels=512, version="v2"),
+    "v2Pro": dict(_SOVITS_COMMON, upsample_initial_channel=512, gin_channels=1024, version="v2Pro"),
+    "v2ProPlus": dict(_SOVITS_COMMON, upsample_initial_channel=768, gin_channels=1024, version="v2ProPlus"),
+    # reduced widths, same topology: CPU-fast parity case
+    "tiny": dict(_SOVITS_COMMON, upsample_initial_channel=128, gin_channels=64, version="v2"),
+}
+
+
+def _randn(gen, *shape, std=1.0):
+    return torch.randn(*shape, generator=gen, dtype=torch.float32) * std
+
+
+def gpt_state_dict(config=GPT_CONFIG, seed: int = 0, eos_boost: float = 0.0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict with the key set of the reference ``Text2SemanticDecoder``.
+
+    ``eos_boost`` adds a constant to the EOS logit (through the last LayerNorm's beta and
+    the EOS row of ``ar_predict_layer``, which has no bias) so that sampled sequences
+    terminate in tests of the EOS handling.
+    """
+    m = config["model"]
+    d, L, V, P = m["hidden_dim"], m["n_layer"], m["vocab_size"], m["phoneme_vocab_size"]
+    F = 4 * d
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["bert_proj.weight"] = _randn(g, d, 1024, std=0.5 / math.sqrt(1024))
+    sd["bert_proj.bias"] = _randn(g, d, std=0.02)
+    sd["ar_text_embedding.word_embeddings.weight"] = _randn(g, P, d, std=0.7)
+    sd["ar_text_position.alpha"] = torch.tensor([1.15])
+    sd["ar_audio_embedding.word_embeddings.weight"] = _randn(g, V, d, std=0.7)
+    sd["ar_audio_position.alpha"] = torch.tensor([0.85])
+    sd["ar_predict_layer.weight"] = _randn(g, V, d, std=2.0 / math.sqrt(d))
+    for i in range(L):
+        p = f"t2s_transformer.blocks.{i}."
+        sd[p + "qkv.weight"] = _randn(g, 3 * d, d, std=1.0 / math.sqrt(d))
+        sd[p + "qkv.bias"] = _randn(g, 3 * d, std=0.05)
+        sd[p + "out_proj.weight"] = _randn(g, d, d, std=1.0 / math.sqrt(d))
+        sd[p + "out_proj.bias"] = _randn(g, d, std=0.05)
+        sd[p + "mlp.0.weight"] = _randn(g, F, d, std=1.0 / math.sqrt(d))
+        sd[p + "mlp.0.bias"] = _randn(g, F, std=0.05)
+        sd[p + "mlp.2.weight"] = _randn(g, d, F, std=1.0 / math.sqrt(F))
+        sd[p + "mlp.2.bias"] = _randn(g, d, std=0.05)
+        sd[p + "norm1.weight"] = 1.0 + _randn(g, d, std=0.1)
+        sd[p + "norm1.bias"] = _randn(g, d, std=0.05)
+        sd[p + "norm2.weight"] = 1.0 + _randn(g, d, std=0.1)
+        sd[p + "norm2.bias"] = _randn(g, d, std=0.05)
+    if eos_boost != 0.0:
+        u = _randn(g, d)
+        u = u / u.norm()
+        last = f"t2s_transformer.blocks.{L - 1}.norm2."
+        sd[last + "bias"] = sd[last + "bias"] + u
+        sd["ar_predict_layer.weight"][m["EOS"]] = eos_boost * u
+    return sd
+
+
+def _wn_pair(gen, cout, cin, k, gain):
+    """(weight_g, weight_v) for old-style weight norm over dims (1,2)."""
+    v = _randn(gen, cout, cin, k)
+    target = gain * torch.ones(cout) * (1.0 + 0.1 * torch.randn(cout, generator=gen))
+    return target.abs().view(cout, 1, 1), v
+
+
+def sovits_flow_dec_state_dict(model: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 state dict for the ``flow.*`` and ``dec.*`` sub-modules of ``SynthesizerTrn``.
+
+    ``flow`` keeps ``weight_g``/``weight_v`` (the reference never strips flow's weight norm,
+    Loader.py:73,95); ``dec`` uses plain ``weight`` as after ``dec.remove_weight_norm()``.
+    """
+    g = torch.Generator().manual_seed(seed + 1000)
+    C = model["inter_channels"]
+    Hc = model["hidden_channels"]
+    gin = model["gin_channels"]
+    half = C // 2
+    nl = 4
+    sd: Dict[str, torch.Tensor] = {}
+    for fi in (0, 2, 4, 6):
+        p = f"flow.flows.{fi}."
+        sd[p + "pre.weight"] = _randn(g, Hc, half, 1, std=1.0 / math.sqrt(half))
+        sd[p + "pre.bias"] = _randn(g, Hc, std=0.05)
+        for l in range(nl):
+            wg, wv = _wn_pair(g, 2 * Hc, Hc, 5, gain=1.0)
+            sd[p + f"enc.in_layers.{l}.weight_g"] = wg
+            sd[p + f"enc.in_layers.{l}.weight_v"] = wv
+            sd[p + f"enc.in_layers.{l}.bias"] = _randn(g, 2 * Hc, std=0.05)
+            rs = 2 * Hc if l < nl - 1 else Hc
+            wg, wv = _wn_pair(g, rs, Hc, 1, gain=0.7)
+            sd[p + f"enc.res_skip_layers.{l}.weight_g"] = wg
+            sd[p + f"enc.res_skip_layers.{l}.weight_v"] = wv
+            sd[p + f"enc.res_skip_layers.{l}.bias"] = _randn(g, rs, std=0.05)
+        wg, wv = _wn_pair(g, 2 * Hc * nl, gin, 1, gain=0.5)
+        sd[p + "enc.cond_layer.weight_g"] = wg
+        sd[p + "enc.cond_layer.weight_v"] = wv
+        sd[p + "enc.cond_layer.bias"] = _randn(g, 2 * Hc * nl, std=0.05)
+        sd[p + "post.weight"] = _randn(g, half, Hc, 1, std=0.3 / math.sqrt(Hc))
+        sd[p + "post.bias"] = _randn(g, half, std=0.02)
+
+    C0 = model["upsample_initial_channel"]
+    sd["dec.conv_pre.weight"] = _randn(g, C0, C, 7, std=1.0 / math.sqrt(C * 7))
+    sd["dec.conv_pre.bias"] = _randn(g, C0, std=0.05)
+    sd["dec.cond.weight"] = _randn(g, C0, gin, 1, std=0.5 / math.sqrt(gin))
+    sd["dec.cond.bias"] = _randn(g, C0, std=0.05)
+    ch = C0
+    for i, (u, k) in enumerate(zip(model["upsample_rates"], model["upsample_kernel_sizes"])):
+        cin, cout = ch, ch // 2
+        taps = max(1.0, k / u)
+        sd[f"dec.ups.{i}.weight"] = _randn(g, cin, cout, k, std=1.2 / math.sqrt(cin * taps))
+        sd[f"dec.ups.{i}.bias"] = _randn(g, cout, std=0.05)
+        ch = cout
+        for j, kk in enumerate(model["resblock_kernel_sizes"]):
+            rp = f"dec.resblocks.{i * len(model['resblock_kernel_sizes']) + j}."
+            for c in range(3):
+                sd[rp + f"convs1.{c}.weight"] = _randn(g, ch, ch, kk, std=0.8 / math.sqrt(ch * kk))
+                sd[rp + f"convs1.{c}.bias"] = _randn(g, ch, std=0.05)
+                sd[rp + f"convs2.{c}.weight"] = _randn(g, ch, ch, kk, std=0.5 / math.sqrt(ch * kk))
+                sd[rp + f"convs2.{c}.bias"] = _randn(g, ch, std=0.05)
+    sd["dec.conv_post.weight"] = _randn(g, 1, ch, 7, std=0.6 / math.sqrt(ch * 7))
+    return sd

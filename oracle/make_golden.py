@@ -1,0 +1,171 @@
+"""ORACLE support (test infrastructure): generate ``tests/golden/*.npz`` by running the
+REFERENCE's own modules (imported from /root/reference through ``ref_shim``) on seeded
+synthetic weights and inputs.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+The reference cannot travel to the GPU box, so these small fixtures are what pins both
+the oracle restatement (CPU tests) and the CUDA path (GPU tests).  Weights are not stored:
+they are regenerated from the seed by ``gsv_tts._synthetic`` (same torch build everywhere).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gsv-tts-lite_b200"))
+
+from gsv_tts import _synthetic as syn  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_grad_enabled(False)
+
+
+def _inputs(seed, nx, ny):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 732, (nx,), generator=g)
+    y = torch.randint(0, 1024, (ny,), generator=g)
+    bert = torch.randn(nx, 1024, generator=g)
+    return x, y, bert
+
+
+def gpt_teacher_forced(ref, x, y, bert, forced, max_seq):
+    """Reference prefill + decode steps with the input token of every step forced, so a
+    difference in one step's logits cannot cascade.  Returns logits [1+n, V] (row 0 =
+    after prefill) and the hidden states."""
+    xy_pos, mask = ref.process_single_data(x[None], y[None], bert[None])
+    bucket = ref.cuda_graph_buckets[1][-1]
+    bucket.kv_cache_len.fill_(0)
+    # the reference allocates its cache with torch.empty (t2s_model.py:245-246); the SDPA path
+    # multiplies masked garbage by zero weights, which is NaN if the garbage is NaN/Inf
+    bucket.k_cache.zero_()
+    bucket.v_cache.zero_()
+    h = ref.t2s_transformer.process_prompt(xy_pos, bucket.k_cache, bucket.v_cache, bucket.kv_cache_len, mask)
+    rows = [ref.ar_predict_layer(h[:, -1]).float()[0].clone()]
+    hid = [h[0, -1].float().clone()]
+    pe = (ref.ar_audio_position.alpha * ref.ar_audio_position.pe).transpose(0, 1)
+    sdpa = hasattr(bucket, "decode_attn_mask") and bucket.decode_attn_mask is not None
+    if sdpa:
+        bucket.decode_attn_mask.fill_(False)
+        bucket.decode_attn_mask[:, :, :, : int(bucket.kv_cache_len)] = True
+    for t in forced.tolist():
+        tok = torch.tensor([[t]])
+        xin = ref.ar_audio_embedding(tok) * ref.ar_audio_position.x_scale + pe[bucket.kv_cache_len - x.shape[0]]
+        if sdpa:
+            bucket.decode_attn_mask[:, :, :, int(bucket.kv_cache_len)] = True
+            hd = ref.t2s_transformer.decode_next_token(xin, bucket.k_cache, bucket.v_cache, bucket.kv_cache_len,
+                                                       bucket.decode_attn_mask, bucket.batch_indices)
+        else:
+            hd = ref.t2s_transformer.decode_next_token(xin, bucket.k_cache, bucket.v_cache, bucket.kv_cache_len)
+        rows.append(ref.ar_predict_layer(hd[:, -1]).float()[0].clone())
+        hid.append(hd[0, -1].float().clone())
+    return torch.stack(rows), torch.stack(hid)
+
+
+def make_gpt(name, cfg, nx, ny, n_forced, max_seq, eos_boost, infer_seed, with_bf16):
+    sd = syn.gpt_state_dict(cfg, seed=0, eos_boost=eos_boost)
+    x, y, bert = _inputs(1234, nx, ny)
+    forced = torch.randint(0, 1024, (n_forced,), generator=torch.Generator().manual_seed(99))
+    ref = ref_shim.build_reference_gpt(sd, cfg, torch.float32, "cpu", [(1, max_seq)])
+    logits, hidden = gpt_teacher_forced(ref, x, y, bert, forced, max_seq)
+    out = dict(x=x.numpy(), y=y.numpy(), bert=bert.numpy(), forced=forced.numpy(),
+               tf_logits=logits.numpy(), tf_hidden=hidden.numpy(),
+               eos_boost=np.float32(eos_boost), max_seq=np.int64(max_seq), infer_seed=np.int64(infer_seed))
+    # seeded free-running decode through the reference's own entry points
+    torch.manual_seed(infer_seed)
+    out["infer_tokens"] = ref.infer(x[None], y[None], bert[None])[0, 0].numpy()
+    torch.manual_seed(infer_seed)
+    chunks = [(c[0, 0].numpy().copy(), f) for c, f in
+              ref.infer_stream(x[None], y[None], bert[None], stream_chunk=10, debug=False)]
+    out["stream_lens"] = np.array([len(c) for c, _ in chunks])
+    out["stream_final"] = chunks[-1][0]
+    out["stream_first"] = chunks[0][0]
+    if with_bf16:
+        # the reference's own 16-bit CPU path, to calibrate tolerances (SURVEY.md 7 "rounding order")
+        for dt, tag in ((torch.bfloat16, "bf16"), (torch.float16, "fp16")):
+            r16 = ref_shim.build_reference_gpt(sd, cfg, dt, "cpu", [(1, max_seq)])
+            lg16, _ = gpt_teacher_forced(r16, x, y, bert.to(dt), forced, max_seq)
+            out[f"tf_logits_{tag}"] = lg16.numpy()
+    np.savez_compressed(os.path.join(OUT, f"gpt_{name}.npz"), **out)
+    print(name, "logits", logits.shape, "std", float(logits.std()), "infer n", len(out["infer_tokens"]),
+          "stream", out["stream_lens"])
+
+
+def make_gpt_batched(name, cfg, n_req, slots, max_seq, eos_boost):
+    """Reference ``infer_batched`` end to end (continuous batching through ``slots`` slots).
+    Only the token *lengths* depend on its 5-step check schedule; stored for the contract
+    checks (s0 excluded, cut at first EOS, every request returned exactly once)."""
+    sd = syn.gpt_state_dict(cfg, seed=0, eos_boost=eos_boost)
+    ref = ref_shim.build_reference_gpt(sd, cfg, torch.float32, "cpu", [(slots, max_seq)])
+    g = torch.Generator().manual_seed(4321)
+    xs, ys, bs = [], [], []
+    for r in range(n_req):
+        nx = int(torch.randint(20, 50, (1,), generator=g))
+        ny = int(torch.randint(20, 60, (1,), generator=g))
+        xs.append(torch.randint(0, 732, (nx,), generator=g))
+        ys.append(torch.randint(0, 1024, (ny,), generator=g))
+        bs.append(torch.randn(nx, 1024, generator=g))
+    torch.manual_seed(5)
+    toks, order = ref.infer_batched(xs, ys, bs)
+    out = dict(n_req=np.int64(n_req), slots=np.int64(slots), max_seq=np.int64(max_seq), eos_boost=np.float32(eos_boost),
+               order=order.numpy(), lens=np.array([len(t) for t in toks]))
+    for i, t in enumerate(toks):
+        out[f"tok{i}"] = t.numpy()
+    for r in range(n_req):
+        out[f"x{r}"], out[f"y{r}"], out[f"b{r}"] = xs[r].numpy(), ys[r].numpy(), bs[r].numpy().astype(np.float16)
+    np.savez_compressed(os.path.join(OUT, f"gpt_{name}.npz"), **out)
+    print(name, "order", order.tolist(), "lens", out["lens"].tolist())
+
+
+def make_vocoder(name, key, B, T, masked_tail, ge_per_frame=False, with16=True):
+    model = syn.SOVITS_MODEL[key]
+    sd = syn.sovits_flow_dec_state_dict(model, seed=0)
+    flow, dec = ref_shim.build_reference_flow_dec(sd, model, torch.float32, "cpu")
+    g = torch.Generator().manual_seed(777)
+    z_p = torch.randn(B, 192, T, generator=g)
+    mask = torch.ones(B, 1, T)
+    if masked_tail and B > 1:
+        mask[1, :, T - masked_tail:] = 0
+    ge = torch.randn(B, model["gin_channels"], T if ge_per_frame else 1, generator=g)
+    z = flow(z_p, mask, ge)
+    o = dec(z * mask, g=ge)
+    out = dict(z_p=z_p.numpy(), mask=mask.numpy(), ge=ge.numpy(), z=z.numpy(), audio=o.numpy())
+    if with16:
+        for dt, tag in ((torch.bfloat16, "bf16"), (torch.float16, "fp16")):
+            f16, d16 = ref_shim.build_reference_flow_dec(sd, model, dt, "cpu")
+            z16 = f16(z_p.to(dt), mask.to(dt), ge.to(dt))
+            out[f"audio_{tag}"] = d16(z16 * mask.to(dt), g=ge.to(dt)).float().numpy()
+            out[f"z_{tag}"] = z16.float().numpy()
+    np.savez_compressed(os.path.join(OUT, f"vocoder_{name}.npz"), **out)
+    msg = f"{name}: z std {float(z.std()):.3f} audio std {float(o.std()):.3f} max {float(o.abs().max()):.3f}"
+    if with16:
+        msg += f" | ref16-vs-32 audio err bf16 {np.abs(out['audio_bf16'] - out['audio']).max():.2e} fp16 {np.abs(out['audio_fp16'] - out['audio']).max():.2e}"
+    print(msg)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["gpt", "batched", "voc"]
+    if "gpt" in which:
+        make_gpt("tiny", syn.GPT_CONFIG_TINY, nx=40, ny=30, n_forced=12, max_seq=256, eos_boost=6.0, infer_seed=7, with_bf16=True)
+        make_gpt("full", syn.GPT_CONFIG, nx=48, ny=60, n_forced=8, max_seq=512, eos_boost=6.0, infer_seed=11, with_bf16=True)
+    if "batched" in which:
+        make_gpt_batched("tiny_batched", syn.GPT_CONFIG_TINY, n_req=7, slots=4, max_seq=256, eos_boost=6.0)
+    if "voc" in which:
+        make_vocoder("tiny", "tiny", B=2, T=20, masked_tail=5)
+        make_vocoder("tiny_ge_t", "tiny", B=1, T=16, masked_tail=0, ge_per_frame=True, with16=False)
+        make_vocoder("v2pro", "v2Pro", B=1, T=12, masked_tail=0)
+        make_vocoder("v2proplus", "v2ProPlus", B=1, T=8, masked_tail=0, with16=False)
+        make_vocoder("v2", "v2", B=1, T=8, masked_tail=0, with16=False)
+
+
+if __name__ == "__main__":
+    # the reference's static buffers are inference tensors
+    with torch.inference_mode():
+        main()
