@@ -1,0 +1,178 @@
+// capi_gpt.cu -- extern "C" entry points of the GPT half of libgsv_b200 (see include/gsv_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "gpt_internal.cuh"
+
+static thread_local char g_err[512] = "";
+void gsv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* gsv_last_error(void) { return g_err; }
+extern "C" int gsv_version(void) { return 100; }
+
+extern "C" int gsv_device_check(int device) {
+  cudaDeviceProp prop;
+  GSV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    gsv_set_error("device %d is sm_%d%d; libgsv_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    return GSV_ERR_NODEVICE;
+  }
+  return GSV_OK;
+}
+
+template <typename P>
+static int dev_alloc(gsv_gpt_ctx* ctx, P** out, size_t bytes, bool zero) {
+  void* ptr = nullptr;
+  GSV_CUDA(cudaMalloc(&ptr, bytes));
+  if (zero) GSV_CUDA(cudaMemset(ptr, 0, bytes));
+  ctx->all_allocs[ctx->n_allocs++] = ptr;
+  *out = reinterpret_cast<P*>(ptr);
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w, gsv_gpt_ctx** out) {
+  GSV_ARG(dims && w && out);
+  GSV_ARG(dims->n_head > 0 && dims->d_model == dims->n_head * GSV_HEAD_DIM);
+  GSV_ARG(dims->d_model % 256 == 0 && dims->d_model <= 1024 && dims->d_ff == 4 * dims->d_model);
+  GSV_ARG(dims->vocab > 1 && dims->vocab <= GSV_VOCAB_MAX && dims->eos >= 0 && dims->eos < dims->vocab);
+  GSV_ARG(dims->max_slots >= 1 && dims->max_slots <= GSV_MAX_SLOTS);
+  GSV_ARG(dims->max_seq >= 8 && dims->max_seq <= dims->n_pos);
+  GSV_ARG(dims->dtype == GSV_F16 || dims->dtype == GSV_BF16);
+  GSV_ARG(dims->d_bert % 32 == 0);
+  int dev = 0;
+  GSV_CUDA(cudaGetDevice(&dev));
+  int rc = gsv_device_check(dev);
+  if (rc) return rc;
+  gsv_gpt_ctx* ctx = new (std::nothrow) gsv_gpt_ctx();
+  GSV_ARG(ctx != nullptr);
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->dims = *dims;
+  ctx->device = dev;
+  GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  GptParams& p = ctx->p;
+  p.d = dims->d_model; p.H = dims->n_head; p.L = dims->n_layer; p.F = dims->d_ff; p.V = dims->vocab;
+  p.eos = dims->eos; p.S = dims->max_seq; p.slots = dims->max_slots; p.n_pos = dims->n_pos;
+  p.d_bert = dims->d_bert; p.n_phoneme = dims->n_phoneme;
+  p.w_qkv = w->w_qkv; p.b_qkv = w->b_qkv; p.w_o = w->w_o; p.b_o = w->b_o; p.w_1 = w->w_1; p.b_1 = w->b_1;
+  p.w_2 = w->w_2; p.b_2 = w->b_2; p.ln1_g = w->ln1_g; p.ln1_b = w->ln1_b; p.ln2_g = w->ln2_g; p.ln2_b = w->ln2_b;
+  p.w_head = w->w_head; p.emb_audio = w->emb_audio; p.pe_audio = w->pe_audio; p.emb_text = w->emb_text;
+  p.pe_text = w->pe_text; p.w_bert = w->w_bert; p.b_bert = w->b_bert;
+  const size_t S = p.S, B = p.slots, d = p.d, F = p.F;
+  const size_t kv_bytes = (size_t)p.L * B * S * d * 2;
+#define A(field, bytes, zero) if ((rc = dev_alloc(ctx, &field, (bytes), (zero)))) { gsv_gpt_destroy(ctx); return rc; }
+  A(p.kc, kv_bytes, true);
+  A(p.vc, kv_bytes, true);
+  A(p.kv_len, B * sizeof(int), true);
+  A(p.x_len, B * sizeof(int), true);
+  A(p.tokens, B * S * sizeof(int), true);
+  A(p.n_gen, B * sizeof(int), true);
+  A(p.active, B * sizeof(int), true);
+  A(p.seen, B * (GSV_VOCAB_MAX / 32) * sizeof(unsigned), true);
+  A(p.samp, B * sizeof(gsv_gpt_sampling), true);
+  A(p.samp_count, B * sizeof(unsigned long long), true);
+  A(p.xin, B * d * sizeof(float), true);
+  A(p.xres, B * d * sizeof(float), true);
+  A(p.q, B * d * sizeof(float), true);
+  A(p.part, B * p.H * GSV_NSPLIT_MAX * GSV_PART_STRIDE * sizeof(float), true);
+  A(p.y1, B * d * sizeof(float), true);
+  A(p.xres1, B * d * sizeof(float), true);
+  A(p.hbuf, B * F * sizeof(float), true);
+  A(p.y2, B * d * sizeof(float), true);
+  A(p.logits, B * GSV_VOCAB_MAX * sizeof(float), true);
+  A(p.barrier, 64, true);
+  A(p.forced_pos, 64, true);
+  A(p.trace_pos, 64, true);
+  A(ctx->pf_x, S * d * 2, false);
+  A(ctx->pf_qkv, S * 3 * d * 2, false);
+  A(ctx->pf_attn, S * d * 2, false);
+  A(ctx->pf_h, S * F * 2, false);
+  A(ctx->pf_tmp, S * d * 2, false);
+#undef A
+  if ((rc = gsv_gpt_decode_configure(ctx))) { gsv_gpt_destroy(ctx); return rc; }
+  *out = ctx;
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_destroy(gsv_gpt_ctx* ctx) {
+  if (!ctx) return GSV_OK;
+  for (int i = 0; i < ctx->n_allocs; ++i) cudaFree(ctx->all_allocs[i]);
+  delete ctx;
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
+                               const void* dev_bert, const gsv_gpt_sampling* samp, void* stream) {
+  GSV_ARG(ctx && dev_x && dev_y && dev_bert && samp);
+  GSV_ARG(slot >= 0 && slot < ctx->p.slots);
+  GSV_ARG(nx >= 1 && ny >= 1);
+  if (nx + ny >= ctx->p.S) {
+    // the reference does not validate this and fails with a shape error inside process_prompt
+    // (t2s_model.py:49; SURVEY.md 8b "Errors"); here it is an argument error
+    gsv_set_error("prompt length %d+%d does not fit the KV cache (max_seq %d)", nx, ny, ctx->p.S);
+    return GSV_ERR_ARG;
+  }
+  return gsv_gpt_prefill_impl(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, samp, (cudaStream_t)stream);
+}
+
+extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
+  GSV_ARG(ctx && n_steps >= 1);
+  return gsv_gpt_decode_launch(ctx, n_steps, (cudaStream_t)stream);
+}
+
+extern "C" int gsv_gpt_read(gsv_gpt_ctx* ctx, int32_t* host_n_gen, int32_t* host_active, int32_t* host_tokens, int first_slot,
+                            int n_slots, void* stream) {
+  GSV_ARG(ctx && first_slot >= 0 && n_slots >= 1 && first_slot + n_slots <= ctx->p.slots);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (host_n_gen)
+    GSV_CUDA(cudaMemcpyAsync(host_n_gen, ctx->p.n_gen + first_slot, n_slots * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (host_active)
+    GSV_CUDA(cudaMemcpyAsync(host_active, ctx->p.active + first_slot, n_slots * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (host_tokens)
+    GSV_CUDA(cudaMemcpyAsync(host_tokens, ctx->p.tokens + (size_t)first_slot * ctx->p.S,
+                             (size_t)n_slots * ctx->p.S * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_state_ptrs(gsv_gpt_ctx* ctx, int32_t** dev_tokens, int32_t** dev_n_gen, int32_t** dev_active) {
+  GSV_ARG(ctx);
+  if (dev_tokens) *dev_tokens = ctx->p.tokens;
+  if (dev_n_gen) *dev_n_gen = ctx->p.n_gen;
+  if (dev_active) *dev_active = ctx->p.active;
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream) {
+  GSV_ARG(ctx && slot >= 0 && slot < ctx->p.slots);
+  GSV_CUDA(cudaMemsetAsync(ctx->p.active + slot, 0, sizeof(int), (cudaStream_t)stream));
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows) {
+  GSV_ARG(ctx);
+  ctx->p.noise = dev_noise;
+  ctx->p.noise_rows = dev_noise ? n_rows : 0;
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n) {
+  GSV_ARG(ctx);
+  ctx->p.forced = dev_forced;
+  ctx->p.n_forced = dev_forced ? n : 0;
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows) {
+  GSV_ARG(ctx);
+  ctx->p.trace = dev_rows;
+  ctx->p.trace_max = dev_rows ? max_rows : 0;
+  return GSV_OK;
+}
+
+extern "C" int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,66 @@
+// gpt_internal.cuh -- parameter block shared by the GPT prefill and decode kernels.
+#pragma once
+#include "common.cuh"
+
+#define GSV_MAX_SLOTS 32
+#define GSV_SLOT_TILE 8          // slots whose activations are staged in shared memory together
+#define GSV_NSPLIT_MAX 16        // split-KV factor upper bound
+#define GSV_PART_STRIDE 36       // floats per attention partial: m, l, pad, pad, o[32]
+#define GSV_HEAD_DIM 32
+#define GSV_DECODE_THREADS 512
+#define GSV_VOCAB_MAX 2048       // sampling scratch is sized for this
+
+struct GptParams {
+  int d, H, L, F, V, eos, S, slots, n_pos, d_bert, n_phoneme;
+  // weights (element type T)
+  const void *w_qkv, *b_qkv, *w_o, *b_o, *w_1, *b_1, *w_2, *b_2;
+  const void *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void *w_head, *emb_audio, *pe_audio, *emb_text, *pe_text, *w_bert, *b_bert;
+  // KV cache, layout [L][slots][H][S][32] (T): one (layer, slot, head) stream is contiguous
+  void *kc, *vc;
+  // per-slot state
+  int* kv_len;      // [slots] live positions in the cache
+  int* x_len;       // [slots] Nx (phoneme count): PE index of the next token is kv_len - x_len
+  int* tokens;      // [slots][S] sampled tokens, index 0 = first token after prefill (s0)
+  int* n_gen;       // [slots]
+  int* active;      // [slots]
+  unsigned* seen;   // [slots][GSV_VOCAB_MAX/32] bitmap of prompt + sampled tokens (repetition penalty)
+  gsv_gpt_sampling* samp;           // [slots]
+  unsigned long long* samp_count;   // [slots] sample() calls so far (Philox counter / noise row)
+  // step buffers exchanged between CTAs (fp32, read with ld.cg)
+  float* xin;     // [slots][d] input of layer 0 for the next step (embedding + PE)
+  float* xres;    // [slots][d] post-LN layer input, residual for the attention half
+  float* q;       // [slots][d]
+  float* part;    // [slots][H][GSV_NSPLIT_MAX][GSV_PART_STRIDE]
+  float* y1;      // [slots][d] x + out_proj(attn) (pre-LN1)
+  float* xres1;   // [slots][d] LN1 output, residual for the MLP half
+  float* hbuf;    // [slots][F]
+  float* y2;      // [slots][d] pre-LN2
+  float* logits;  // [slots][GSV_VOCAB_MAX]
+  unsigned* barrier;
+  // parity hooks
+  const float* noise; int noise_rows;
+  const int* forced; int n_forced; int* forced_pos;
+  float* trace; int trace_max; int* trace_pos;
+};
+
+struct gsv_gpt_ctx {
+  gsv_gpt_dims dims;
+  GptParams p;
+  int device;
+  int num_sms;
+  int decode_grid;
+  size_t decode_smem;
+  long long launches;
+  // prefill scratch (T unless noted), sized for max_seq rows
+  void *pf_x, *pf_qkv, *pf_attn, *pf_h, *pf_tmp;
+  float* pf_f32;
+  void* all_allocs[64];
+  int n_allocs;
+};
+
+// kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
+int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
+int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny,
+                         const void* bert, const gsv_gpt_sampling* samp, cudaStream_t st);
+int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);

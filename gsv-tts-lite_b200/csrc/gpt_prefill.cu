@@ -1,0 +1,326 @@
+// gpt_prefill.cu -- prompt prefill of one request into one KV-cache slot, and its first token.
+//
+// Replaces process_single_data + T2STransformer.process_prompt + the first sample()
+// (reference gsv_tts/GPT_SoVITS/GPT/t2s_model.py:351-383, 31-65, 114-127, 414-420; the same
+// sequence is the slot-refill path of infer_batched, :696-722).
+//
+// Round-1 implementation: straightforward tiled kernels (fp32 accumulate, T activations rounded
+// where the reference rounds them).  The GEMMs are the tcgen05 candidate for the next round; the
+// structure (what is fused into which epilogue) is already the final one.
+#include "gpt_sample.cuh"
+
+namespace {
+
+// ---- embeddings (A.2) ------------------------------------------------------------------------
+// text rows:  round(round(emb_text[x] + bert_proj) + alpha_t*pe[i]);  audio rows: round(emb_audio[y] + alpha_a*pe[m])
+template <typename T>
+__global__ void embed_kernel(const GptParams p, const int64_t* __restrict__ x, int nx, const int64_t* __restrict__ y, int ny,
+                             const T* __restrict__ bert_proj /*[nx][d]*/, T* __restrict__ out /*[nx+ny][d]*/) {
+  const int row = blockIdx.x, d = p.d;
+  const T* pe;
+  const T* emb;
+  if (row < nx) {
+    long long id = x[row];
+    id = id < 0 ? 0 : (id >= p.n_phoneme ? p.n_phoneme - 1 : id);
+    emb = reinterpret_cast<const T*>(p.emb_text) + (size_t)id * d;
+    pe = reinterpret_cast<const T*>(p.pe_text) + (size_t)row * d;
+  } else {
+    long long id = y[row - nx];
+    id = id < 0 ? 0 : (id >= p.V ? p.V - 1 : id);
+    emb = reinterpret_cast<const T*>(p.emb_audio) + (size_t)id * d;
+    pe = reinterpret_cast<const T*>(p.pe_audio) + (size_t)(row - nx) * d;
+  }
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float e = Elem<T>::to_f(emb[c]);
+    if (row < nx) e = Elem<T>::to_f(Elem<T>::from_f(e + Elem<T>::to_f(bert_proj[(size_t)row * d + c])));
+    out[(size_t)row * d + c] = Elem<T>::from_f(e + Elem<T>::to_f(pe[c]));
+  }
+}
+
+// ---- C[M][N] = A[M][K] W[N][K]^T + bias  (nn.Linear), optional ReLU --------------------------------
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W,
+                                                      const T* __restrict__ bias, T* __restrict__ C, int ldc, int M, int N,
+                                                      int K) {
+  constexpr int BM = 64, BN = 64, BK = 32;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lr = tid >> 2, lk = (tid & 3) * 8;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    float a8[8], w8[8];
+    if (m0 + lr < M) unpack8<T>(*reinterpret_cast<const uint4*>(A + (size_t)(m0 + lr) * lda + k0 + lk), a8);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+    }
+    if (n0 + lr < N) unpack8<T>(ld_weight(W + (size_t)(n0 + lr) * K + k0 + lk), w8);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w8[j] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { As[lk + j][lr] = a8[j]; Ws[lk + j][lr] = w8[j]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? Elem<T>::to_f(bias[n]) : 0.f);
+      if (RELU) v = fmaxf(v, 0.f);
+      C[(size_t)m * ldc + n] = Elem<T>::from_f(v);
+    }
+  }
+}
+
+// ---- K,V of the prompt into the cache slot: kc[l][slot][h][t][32] ----------------------------------------
+template <typename T>
+__global__ void kv_scatter_kernel(const GptParams p, int layer, int slot, const T* __restrict__ qkv, int n) {
+  const int t = blockIdx.x, d = p.d;
+  T* kc = reinterpret_cast<T*>(p.kc);
+  T* vc = reinterpret_cast<T*>(p.vc);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const size_t a = (((size_t)(layer * p.slots + slot) * p.H + (c >> 5)) * p.S + t) * GSV_HEAD_DIM + (c & 31);
+    kc[a] = qkv[(size_t)t * 3 * d + d + c];
+    vc[a] = qkv[(size_t)t * 3 * d + 2 * d + c];
+  }
+}
+
+// ---- masked prompt attention (A.2 mask): text row -> all text; audio row i -> keys 0..i -----------------
+// one warp per (query row, head); 4 lanes x 8 dims per key, 8 keys per pass
+template <typename T>
+__global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int nx, int d,
+                                                           int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= n * H) return;
+  const int i = item / H, h = item - i * H;
+  const int lim = i < nx ? nx : i + 1;
+  const int sub = lane & 3, pg = lane >> 2;
+  const float qscale = rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f;
+  float q[8];
+  unpack8<T>(*reinterpret_cast<const uint4*>(qkv + (size_t)i * 3 * d + h * GSV_HEAD_DIM + sub * 8), q);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] *= qscale;
+  float m = GSV_NEG_INF, l = 0.f, o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  for (int tt = 0; tt < lim; tt += 8) {
+    const int t = tt + pg;
+    const bool ok = t < lim;
+    float s = GSV_NEG_INF, vf[8];
+    if (ok) {
+      float kf[8];
+      const T* row = qkv + (size_t)t * 3 * d + h * GSV_HEAD_DIM + sub * 8;
+      unpack8<T>(*reinterpret_cast<const uint4*>(row + d), kf);
+      unpack8<T>(*reinterpret_cast<const uint4*>(row + 2 * d), vf);
+      s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(q[j], kf[j], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float sc = exp2f(m - mn), pr = exp2f(s - mn);
+      l = l * sc + pr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, vf[j], o[j] * sc);
+      m = mn;
+    }
+  }
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, m2);
+    const float a = mn > GSV_NEG_INF ? exp2f(m - mn) : 0.f;
+    const float b = mn > GSV_NEG_INF ? exp2f(m2 - mn) : 0.f;
+    l = l * a + l2 * b;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = o[j] * a + __shfl_xor_sync(0xffffffffu, o[j], off) * b;
+    m = mn;
+  }
+  if (pg == 0) {
+    float r[8];
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = o[j] * inv;
+    *reinterpret_cast<uint4*>(out + (size_t)i * d + h * GSV_HEAD_DIM + sub * 8) = pack8<T>(r);
+  }
+}
+
+// ---- x = LayerNorm(round(res + y)) (post-LN, t2s_model.py:57-58, 62-63); warp per row, in place on x ---------------
+template <typename T>
+__global__ void __launch_bounds__(128) add_ln_kernel(T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ g,
+                                                     const T* __restrict__ b, int n, int d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= n) return;
+  float v[32];
+  const int per = d >> 5;     // d <= 1024
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) {
+      const int c = i * 32 + lane;
+      v[i] = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(x[(size_t)row * d + c]) + Elem<T>::to_f(y[(size_t)row * d + c])));
+      sum += v[i];
+    }
+  const float mean = warp_sum(sum) / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) sq += (v[i] - mean) * (v[i] - mean);
+  const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) {
+      const int c = i * 32 + lane;
+      x[(size_t)row * d + c] = Elem<T>::from_f((v[i] - mean) * rstd * Elem<T>::to_f(g[c]) + Elem<T>::to_f(b[c]));
+    }
+}
+
+// ---- logits of the last prompt row (fp32) + slot state reset ----------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_row_kernel(const GptParams p, int slot, const T* __restrict__ xrow) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.V) return;
+  const T* w = reinterpret_cast<const T*>(p.w_head) + (size_t)row * p.d;
+  float acc = 0.f;
+  for (int c = lane * 8; c < p.d; c += 256) {
+    float wf[8], xf[8];
+    unpack8<T>(ld_weight(w + c), wf);
+    unpack8<T>(*reinterpret_cast<const uint4*>(xrow + c), xf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(wf[j], xf[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) p.logits[(size_t)slot * GSV_VOCAB_MAX + row] = acc;
+}
+
+__global__ void slot_reset_kernel(const GptParams p, int slot, int nx, int n, const int64_t* __restrict__ y, int ny,
+                                  gsv_gpt_sampling samp) {
+  unsigned* seen = p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32);
+  for (int i = threadIdx.x; i < GSV_VOCAB_MAX / 32; i += blockDim.x) seen[i] = 0u;
+  __syncthreads();
+  // previous_tokens starts as the prompt tokens y (t2s_model.py:412)
+  for (int i = threadIdx.x; i < ny; i += blockDim.x) {
+    long long t = y[i];
+    if (t >= 0 && t < GSV_VOCAB_MAX) atomicOr(seen + (t >> 5), 1u << (t & 31));
+  }
+  if (threadIdx.x == 0) {
+    p.kv_len[slot] = n;
+    p.x_len[slot] = nx;
+    p.n_gen[slot] = 0;
+    p.samp_count[slot] = 0ull;
+    p.active[slot] = 1;
+    p.samp[slot] = samp;
+    if (slot == 0) {
+      if (p.forced_pos) *p.forced_pos = 0;
+      if (p.trace_pos) *p.trace_pos = 0;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GSV_DECODE_THREADS, 1) first_token_kernel(const GptParams p, int slot) {
+  extern __shared__ __align__(16) float sm[];
+  sample_slot<T>(p, slot, sm);
+}
+
+template <typename T>
+int gemm(const T* A, int lda, const T* W, const T* bias, T* C, int ldc, int M, int N, int K, bool relu, cudaStream_t st,
+         long long& launches) {
+  if (K % 32 != 0) { gsv_set_error("gemm: K=%d must be a multiple of 32", K); return GSV_ERR_ARG; }
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (relu) gemm_tn_kernel<T, true><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K);
+  else gemm_tn_kernel<T, false><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K);
+  launches += 1;
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
+template <typename T>
+int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert,
+                 const gsv_gpt_sampling& samp, cudaStream_t st) {
+  const GptParams& p = ctx->p;
+  const int d = p.d, F = p.F, L = p.L, n = nx + ny;
+  T* X = reinterpret_cast<T*>(ctx->pf_x);        // [n][d]
+  T* QKV = reinterpret_cast<T*>(ctx->pf_qkv);    // [n][3d]
+  T* ATT = reinterpret_cast<T*>(ctx->pf_attn);   // [n][d]
+  T* Hh = reinterpret_cast<T*>(ctx->pf_h);       // [n][F]
+  T* TMP = reinterpret_cast<T*>(ctx->pf_tmp);    // [n][d]
+  int rc;
+  // bert_proj (nn.Linear(1024, d), t2s_model.py:172, 354)
+  if ((rc = gemm<T>(reinterpret_cast<const T*>(bert), p.d_bert, reinterpret_cast<const T*>(p.w_bert),
+                    reinterpret_cast<const T*>(p.b_bert), TMP, d, nx, d, p.d_bert, false, st, ctx->launches)))
+    return rc;
+  embed_kernel<T><<<n, 128, 0, st>>>(p, x, nx, y, ny, TMP, X);
+  ctx->launches += 1;
+  GSV_CHECK_LAUNCH();
+  for (int l = 0; l < L; ++l) {
+    const T* wqkv = reinterpret_cast<const T*>(p.w_qkv) + (size_t)l * 3 * d * d;
+    const T* bqkv = reinterpret_cast<const T*>(p.b_qkv) + (size_t)l * 3 * d;
+    if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches))) return rc;
+    kv_scatter_kernel<T><<<n, 128, 0, st>>>(p, l, slot, QKV, n);
+    prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(QKV, ATT, n, nx, d, p.H);
+    ctx->launches += 2;
+    GSV_CHECK_LAUNCH();
+    if ((rc = gemm<T>(ATT, d, reinterpret_cast<const T*>(p.w_o) + (size_t)l * d * d,
+                      reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, n, d, d, false, st, ctx->launches)))
+      return rc;
+    add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln1_g) + (size_t)l * d,
+                                                 reinterpret_cast<const T*>(p.ln1_b) + (size_t)l * d, n, d);
+    ctx->launches += 1;
+    GSV_CHECK_LAUNCH();
+    if ((rc = gemm<T>(X, d, reinterpret_cast<const T*>(p.w_1) + (size_t)l * F * d,
+                      reinterpret_cast<const T*>(p.b_1) + (size_t)l * F, Hh, F, n, F, d, true, st, ctx->launches)))
+      return rc;
+    if ((rc = gemm<T>(Hh, F, reinterpret_cast<const T*>(p.w_2) + (size_t)l * d * F,
+                      reinterpret_cast<const T*>(p.b_2) + (size_t)l * d, TMP, d, n, d, F, false, st, ctx->launches)))
+      return rc;
+    add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln2_g) + (size_t)l * d,
+                                                 reinterpret_cast<const T*>(p.ln2_b) + (size_t)l * d, n, d);
+    ctx->launches += 1;
+    GSV_CHECK_LAUNCH();
+  }
+  slot_reset_kernel<<<1, 256, 0, st>>>(p, slot, nx, n, y, ny, samp);
+  head_row_kernel<T><<<(p.V + 7) / 8, 256, 0, st>>>(p, slot, X + (size_t)(n - 1) * d);
+  const size_t smem = GSV_SAMPLE_SMEM_FLOATS * sizeof(float);
+  first_token_kernel<T><<<1, GSV_DECODE_THREADS, smem, st>>>(p, slot);
+  ctx->launches += 3;
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
+}  // namespace
+
+int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert,
+                         const gsv_gpt_sampling* samp, cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return prefill_impl<__half>(ctx, slot, x, nx, y, ny, bert, *samp, st);
+  return prefill_impl<__nv_bfloat16>(ctx, slot, x, nx, y, ny, bert, *samp, st);
+}

@@ -1,0 +1,270 @@
+// gpt_sample.cuh -- one CTA samples the next token of one slot and prepares the slot's next
+// input vector.  Restates sample()/logits_to_probs() (reference GPT/utils.py:12-59) and the
+// bookkeeping around it (t2s_model.py:415-420, 442-456, 649-653, 727-728) as device code.
+#pragma once
+#include "gpt_internal.cuh"
+
+#define GSV_NEG_INF (-__int_as_float(0x7f800000))
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax amax2(ArgMax a, ArgMax b) {
+  // larger value wins; ties -> smaller index (torch.argmax returns the first maximum)
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax a, float* red_v, int* red_i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = amax2(a, b);
+  }
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red_v[w] = a.v; red_i[w] = a.i; }
+  __syncthreads();
+  ArgMax r;
+  r.v = red_v[0]; r.i = red_i[0];
+  for (int k = 1; k < nw; ++k) { ArgMax b; b.v = red_v[k]; b.i = red_i[k]; r = amax2(r, b); }
+  return r;
+}
+__device__ __forceinline__ float block_sum(float a, float* red_v) {
+  a = warp_sum(a);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red_v[w] = a;
+  __syncthreads();
+  float r = 0.f;
+  for (int k = 0; k < nw; ++k) r += red_v[k];
+  return r;
+}
+
+// Shared memory (in floats) needed by sample_slot; carved up at the top of the function.
+#define GSV_SAMPLE_SMEM_FLOATS (3 * GSV_VOCAB_MAX + 64)
+
+template <typename T>
+__device__ void sample_slot(const GptParams& p, int slot, float* sm) {
+  float* lg = sm;                                         // [GSV_VOCAB_MAX] working logits
+  int* sidx = reinterpret_cast<int*>(sm + GSV_VOCAB_MAX); // [GSV_VOCAB_MAX] sort indices (top-p only)
+  float* kbuf = sm + 2 * GSV_VOCAB_MAX;                   // [GSV_VOCAB_MAX] exp() in sorted order (top-p only)
+  float* red_v = sm + 3 * GSV_VOCAB_MAX;                  // [32]
+  int* red_i = reinterpret_cast<int*>(red_v + 32);        // [32]
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const gsv_gpt_sampling sp = p.samp[slot];
+  const int ngen = ld_cg(p.n_gen + slot);
+  const bool first = ngen == 0;
+  const int Vv = first ? p.V - 1 : p.V;                   // first sample: EOS column sliced off (:417)
+  const unsigned long long cnt = __ldcg(p.samp_count + slot);
+  __syncthreads();
+
+  // raw logits (+ optional trace of slot 0 for the teacher-forced parity test)
+  int trow = -1;
+  if (slot == 0 && p.trace != nullptr) {
+    trow = ld_cg(p.trace_pos);
+    if (trow >= p.trace_max) trow = -1;
+  }
+  for (int v = tid; v < GSV_VOCAB_MAX; v += NT) {
+    float l = GSV_NEG_INF;
+    if (v < p.V) {
+      l = ld_cg(p.logits + (size_t)slot * GSV_VOCAB_MAX + v);
+      if (trow >= 0) p.trace[(size_t)trow * p.V + v] = l;
+      if (v >= Vv) l = GSV_NEG_INF;
+    }
+    lg[v] = l;
+  }
+  __syncthreads();
+  const bool suppress = first ? (sp.suppress_steps > 0) : (ngen < sp.suppress_steps);
+  if (tid == 0) {
+    if (trow >= 0) st_cg(p.trace_pos, trow + 1);
+    if (suppress) {                                       // suppressed_tokens = [280, 486, EOS] (:170)
+      if (280 < Vv) lg[280] = GSV_NEG_INF;
+      if (486 < Vv) lg[486] = GSV_NEG_INF;
+      if (p.eos < Vv) lg[p.eos] = GSV_NEG_INF;
+    }
+    if (sp.mask_eos && p.eos < Vv) lg[p.eos] = GSV_NEG_INF;
+  }
+  __syncthreads();
+
+  // (1) repetition penalty over the set of previous tokens (utils.py:20-27; duplicates in
+  //     previous_tokens gather the same original score, so a set is equivalent)
+  const float rp = sp.repetition_penalty;
+  if (rp != 1.0f) {
+    const unsigned* seen = p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32);
+    for (int v = tid; v < Vv; v += NT) {
+      if ((__ldcg(seen + (v >> 5)) >> (v & 31)) & 1u) {
+        float l = lg[v];
+        lg[v] = l < 0.f ? l * rp : l / rp;
+      }
+    }
+    __syncthreads();
+  }
+
+  // (2) top-p (utils.py:29-39): sort descending, drop sorted entries whose inclusive cumulative
+  //     probability exceeds top_p, except rank 0
+  if (sp.top_p < 1.0f) {
+    for (int v = tid; v < GSV_VOCAB_MAX; v += NT) sidx[v] = v;
+    __syncthreads();
+    // bitonic sort of the index array, keys looked up through lg[]; descending, ties by index
+    for (int k = 2; k <= GSV_VOCAB_MAX; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < GSV_VOCAB_MAX; t += NT) {
+          int u = t ^ j;
+          if (u > t) {
+            int ia = sidx[t], ib = sidx[u];
+            float a = lg[ia], b = lg[ib];
+            bool desc = (t & k) == 0;
+            bool a_before_b = (a > b) || (a == b && ia < ib);
+            if (desc ? !a_before_b : a_before_b) { sidx[t] = ib; sidx[u] = ia; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const float top = lg[sidx[0]];
+    float part = 0.f;
+    for (int t = tid; t < GSV_VOCAB_MAX; t += NT) {
+      float e = __expf(lg[sidx[t]] - top);
+      kbuf[t] = e;
+      part += e;
+    }
+    const float total = block_sum(part, red_v);
+    __syncthreads();
+    // inclusive scan in sorted order: each thread owns a contiguous run of `per` entries
+    const int per = GSV_VOCAB_MAX / NT;
+    float run = 0.f;
+    for (int i = 0; i < per; ++i) run += kbuf[tid * per + i];
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float n = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += n;
+    }
+    __syncthreads();
+    if ((tid & 31) == 31) red_v[tid >> 5] = incl;
+    __syncthreads();
+    float base = 0.f;
+    for (int w = 0; w < (tid >> 5); ++w) base += red_v[w];
+    float cum = base + incl - run;
+    for (int i = 0; i < per; ++i) {
+      int t = tid * per + i;
+      cum += kbuf[t];
+      if (t > 0 && cum / total > sp.top_p) lg[sidx[t]] = GSV_NEG_INF;   // distinct targets: no race
+    }
+    __syncthreads();
+  }
+
+  // (3) temperature (utils.py:41)
+  {
+    const float t = fmaxf(sp.temperature, 1e-5f);
+    if (t != 1.0f)
+      for (int v = tid; v < Vv; v += NT) lg[v] = lg[v] / t;
+    __syncthreads();
+  }
+
+  // (4) top-k pivot = k-th largest value with multiplicity (utils.py:43-46); ties with the pivot survive
+  if (sp.top_k > 0) {
+    const int k = min(sp.top_k, Vv);
+    constexpr int PER = GSV_VOCAB_MAX / GSV_DECODE_THREADS;   // blockDim.x == GSV_DECODE_THREADS
+    float cur[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      int v = tid + i * NT;
+      cur[i] = v < Vv ? lg[v] : GSV_NEG_INF;
+    }
+    float pivot = GSV_NEG_INF;
+    for (int r = 0; r < k; ++r) {
+      ArgMax a;
+      a.v = GSV_NEG_INF; a.i = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        ArgMax b; b.v = cur[i]; b.i = tid + i * NT;
+        a = amax2(a, b);
+      }
+      a = block_argmax(a, red_v, red_i);
+      pivot = a.v;
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        if (tid + i * NT == a.i) cur[i] = GSV_NEG_INF;    // remove exactly one instance
+    }
+    for (int v = tid; v < Vv; v += NT)
+      if (lg[v] < pivot) lg[v] = GSV_NEG_INF;
+    __syncthreads();
+  }
+
+  // (5) softmax (utils.py:48)
+  float mx = GSV_NEG_INF;
+  for (int v = tid; v < Vv; v += NT) mx = fmaxf(mx, lg[v]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((tid & 31) == 0) red_v[tid >> 5] = mx;
+  __syncthreads();
+  mx = red_v[0];
+  for (int w = 1; w < (NT >> 5); ++w) mx = fmaxf(mx, red_v[w]);
+  float part = 0.f;
+  for (int v = tid; v < Vv; v += NT) {
+    float e = __expf(lg[v] - mx);
+    lg[v] = e;
+    part += e;
+  }
+  const float total = block_sum(part, red_v);
+  const float inv_total = 1.0f / total;
+
+  // (6) token = argmax(p / q), q ~ Exp(1) i.i.d. per column (utils.py:5-9)
+  ArgMax best;
+  best.v = -1.0f; best.i = 0x7fffffff;
+  const bool ext = p.noise != nullptr && slot == 0 && cnt < (unsigned long long)p.noise_rows;
+  const uint2 key = make_uint2((uint32_t)sp.seed, (uint32_t)(sp.seed >> 32));
+  for (int v = tid; v < Vv; v += NT) {
+    float q;
+    if (ext) {
+      q = p.noise[(size_t)cnt * p.V + v];
+    } else {
+      uint4 r = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)(v >> 2), 0u), key);   // slot-independent: the seed names the request
+      uint32_t bits = (v & 3) == 0 ? r.x : (v & 3) == 1 ? r.y : (v & 3) == 2 ? r.z : r.w;
+      q = exp1_from_bits(bits);
+    }
+    ArgMax b;
+    b.v = (lg[v] * inv_total) / q;
+    b.i = v;
+    best = amax2(best, b);
+  }
+  best = block_argmax(best, red_v, red_i);
+  int tok = best.i;
+
+  // bookkeeping by one thread; every value other CTAs read later goes through st.cg
+  const int kvl = ld_cg(p.kv_len + slot);
+  if (sp.max_new_tokens > 0 && ngen > sp.max_new_tokens) tok = p.eos;    // ngen counts s0 too
+  if (slot == 0 && p.forced != nullptr) {
+    int fp = ld_cg(p.forced_pos);
+    if (fp < p.n_forced) {
+      tok = p.forced[fp];
+      if (tid == 0) st_cg(p.forced_pos, fp + 1);
+    }
+  }
+  const int kv_cap = (sp.max_kv > 0 && sp.max_kv < p.S) ? sp.max_kv : p.S;
+  const bool stop = (tok == p.eos) || (kvl >= kv_cap);
+  if (tid == 0) {
+    st_cg(p.tokens + (size_t)slot * p.S + ngen, tok);
+    st_cg(p.n_gen + slot, ngen + 1);
+    __stcg(p.samp_count + slot, cnt + 1);
+    if (tok < GSV_VOCAB_MAX) atomicOr(p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32) + (tok >> 5), 1u << (tok & 31));
+    if (stop) st_cg(p.active + slot, 0);
+  }
+  // next input: emb_audio[tok] * x_scale(=1) + (alpha*pe)[kv_len - Nx]  (:455-456, :727-728)
+  if (!stop) {
+    const T* emb = reinterpret_cast<const T*>(p.emb_audio) + (size_t)tok * p.d;
+    int pos = kvl - ld_cg(p.x_len + slot);
+    pos = max(0, min(pos, p.n_pos - 1));
+    const T* pe = reinterpret_cast<const T*>(p.pe_audio) + (size_t)pos * p.d;
+    for (int c = tid; c < p.d; c += NT) {
+      // the reference adds two T values and rounds to T
+      float s = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(emb[c]) + Elem<T>::to_f(pe[c])));
+      st_cg(p.xin + (size_t)slot * p.d + c, s);
+    }
+  }
+  __syncthreads();
+}

@@ -1,0 +1,671 @@
+// vocoder.cu -- SoVITS reverse flow (4 x WaveNet residual coupling) + HiFi-GAN generator.
+//
+// Replaces SynthesizerTrn.flow_dec / the CUDA-graph bucket path of decode()
+// (reference gsv_tts/GPT_SoVITS/SoVITS/models.py:380-383, 406-425): ResidualCouplingBlock
+// (models.py:23-65, modules.py:447-511), WN (modules.py:30-104, commons.py:14-21), Generator
+// (models.py:68-132) and ResBlock1 (modules.py:115-203) -- ~504 library launches per call there.
+//
+// Data layout: every activation is time-major / channels-last, [B][T][C], so channels are the
+// contiguous (reduction) axis of every convolution tap: coalesced 16-byte loads now, and the
+// K-major operand layout an implicit-GEMM tensor-core kernel needs next.  Each convolution
+// consumes a 16-bit, already-activated copy of its input and carries residual streams in fp32;
+// every elementwise op of the reference (bias, conditioning add, mask, leaky-ReLU, residual add,
+// MRF average, channel flip) is folded into a convolution epilogue or an index map:
+//   * Flip (modules.py:504-511) never moves data: flows at odd flip parity read/write the
+//     physical channels through a reversed index.
+//   * weight-norm is folded once at load by the host (the reference re-evaluates g*v/||v|| on
+//     every call because flow's weight-norm is never removed, Loader.py:73,95).
+//   * xs/3 (models.py:127) and the following leaky-ReLU are applied in the epilogue of the last
+//     convolution of the third ResBlock.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+enum { ACT_NONE = 0, ACT_LRELU_01 = 1, ACT_LRELU_001 = 2 };
+
+template <typename T>
+struct ConvArgs {
+  // input: [B][Tin][in_ld] T, channels [in_off, in_off+Cin); in_rev reads them in reversed order
+  const T* in;
+  int in_ld, in_off, in_rev;
+  int B, Tin, Tout, Cin, Cout, KW, dil, stride;   // stride > 1: transposed convolution (upsampling)
+  // weights [KW][rows][Cin] T: pointer already at the first output row, w_tap = rows_total*Cin
+  const T* w;
+  long long w_tap;
+  const T* bias;
+  // v = conv + bias (+ add[b][tg][co])
+  const float* add;
+  int add_ld, add_tg;
+  // if res32: v = res32 + res_sign * v          (fp32 residual stream)
+  const float* res32;
+  float res_sign;
+  // if acc32: v = (acc_init ? v : acc32 + v); acc32 = v; v *= acc_scale
+  float* acc32;
+  int acc_init;
+  float acc_scale;
+  // if mask: v *= mask[b][t]
+  const T* mask;
+  // if out32: out32 = v ; if outT: outT = T(act(v))
+  float* out32;
+  T* outT;
+  int act;
+  // res32/acc32/out32/outT share one channel geometry: row stride o_ld, first channel o_off,
+  // o_rev writes channel (Cout-1-co)
+  int o_ld, o_off, o_rev;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_LRELU_01) return v > 0.f ? v : 0.1f * v;
+  if (act == ACT_LRELU_001) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void conv_epilogue(const ConvArgs<T>& a, int b, int t, int co, float v) {
+  v += Elem<T>::to_f(a.bias[co]);
+  if (a.add) v += a.add[((size_t)b * a.add_tg + (a.add_tg > 1 ? t : 0)) * a.add_ld + co];
+  const size_t o = ((size_t)b * a.Tout + t) * a.o_ld + a.o_off + (a.o_rev ? a.Cout - 1 - co : co);
+  if (a.res32) v = a.res32[o] + a.res_sign * v;
+  if (a.acc32) {
+    if (!a.acc_init) v += a.acc32[o];
+    a.acc32[o] = v;
+    v *= a.acc_scale;
+  }
+  if (a.mask) v *= Elem<T>::to_f(a.mask[(size_t)b * a.Tout + t]);
+  if (a.out32) a.out32[o] = v;
+  if (a.outT) a.outT[o] = Elem<T>::from_f(act_apply(v, a.act));
+}
+
+// load 8 consecutive logical input channels [c, c+8) of row (b, t) as floats (zero outside [0,Tin))
+template <typename T>
+__device__ __forceinline__ void load_in8(const ConvArgs<T>& a, int b, int t, int c, float* f) {
+  if (t < 0 || t >= a.Tin) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    return;
+  }
+  const T* row = a.in + ((size_t)b * a.Tin + t) * a.in_ld + a.in_off;
+  if (!a.in_rev) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(row + c), f);
+  } else {
+    float r[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(row + (a.Cin - 8 - c)), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = r[7 - j];
+  }
+}
+
+// ---- "same" dilated Conv1d, channels-last, CUDA cores --------------------------------------------------
+// CTA tile: TT = 4096/CO_T time steps x CO_T output channels; 256 threads, 4x4 outputs each.
+template <typename T, int CO_T>
+__global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs<T> a) {
+  constexpr int NTX = CO_T / 4;
+  constexpr int TT = (256 / NTX) * 4;
+  constexpr int HALO_MAX = 64;
+  __shared__ float xs[8][TT + HALO_MAX];
+  __shared__ __align__(16) float ws[8][CO_T];
+  const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
+  const int b = blockIdx.z, t0 = blockIdx.x * TT, co0 = blockIdx.y * CO_T;
+  const int halo = (a.KW - 1) * a.dil, pad = halo / 2;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < a.Cin; c0 += 8) {
+    __syncthreads();
+    for (int r = tid; r < TT + halo; r += 256) {
+      float f[8];
+      load_in8<T>(a, b, t0 - pad + r, c0, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xs[j][r] = f[j];
+    }
+    for (int k = 0; k < a.KW; ++k) {
+      __syncthreads();
+      if (tid < CO_T) {
+        float f[8];
+        if (co0 + tid < a.Cout) unpack8<T>(ld_weight(a.w + k * a.w_tap + (size_t)(co0 + tid) * a.Cin + c0), f);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ws[j][tid] = f[j];
+      }
+      __syncthreads();
+      const int off = ty * 4 + k * a.dil;
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[ci][tx * 4]);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = xs[ci][off + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= a.Tout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < a.Cout) conv_epilogue<T>(a, b, t, co, acc[i][j]);
+    }
+  }
+}
+
+// ---- ConvTranspose1d(stride s, kernel KW, padding (KW-s)/2), polyphase gather form -------------------------
+//   out[t][co] = sum_ci sum_{j == (t+pad) mod s, j < KW, step s} x[(t+pad-j)/s][ci] * w[j][co][ci]
+template <typename T, int CO_T>
+__global__ void __launch_bounds__(256) convt1d_kernel(const ConvArgs<T> a) {
+  constexpr int NTX = CO_T / 4;
+  constexpr int TT = (256 / NTX) * 4;     // output samples per CTA
+  constexpr int NIN_MAX = TT / 2 + 24;    // input frames needed (stride >= 2, KW <= 16)
+  __shared__ float xs[8][NIN_MAX];
+  __shared__ __align__(16) float ws[16][8][CO_T];
+  const int tid = threadIdx.x, tx = tid % NTX, ty = tid / NTX;
+  const int b = blockIdx.z, t0 = blockIdx.x * TT, co0 = blockIdx.y * CO_T;
+  const int s = a.stride, pad = (a.KW - s) / 2;
+  // input frame range touched by outputs [t0, t0+TT)
+  int tin0 = (t0 + pad - (a.KW - 1));
+  tin0 = tin0 >= 0 ? tin0 / s : -((-tin0 + s - 1) / s);
+  const int tin1 = (t0 + TT - 1 + pad) / s;
+  const int nin = tin1 - tin0 + 1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < a.Cin; c0 += 8) {
+    __syncthreads();
+    for (int r = tid; r < nin; r += 256) {
+      float f[8];
+      load_in8<T>(a, b, tin0 + r, c0, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xs[j][r] = f[j];
+    }
+    for (int i = tid; i < a.KW * CO_T; i += 256) {
+      const int k = i / CO_T, co = i - k * CO_T;
+      float f[8];
+      if (co0 + co < a.Cout) unpack8<T>(ld_weight(a.w + k * a.w_tap + (size_t)(co0 + co) * a.Cin + c0), f);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ws[k][j][co] = f[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + ty * 4 + i;
+      const int r = (t + pad) % s;
+      for (int k = r; k < a.KW; k += s) {
+        const int ti = (t + pad - k) / s - tin0;     // exact division; frames outside [0,Tin) were zero-filled
+        if (ti < 0 || ti >= nin) continue;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const float x = xs[ci][ti];
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][ci][tx * 4]);
+          acc[i][0] = fmaf(x, w4.x, acc[i][0]);
+          acc[i][1] = fmaf(x, w4.y, acc[i][1]);
+          acc[i][2] = fmaf(x, w4.z, acc[i][2]);
+          acc[i][3] = fmaf(x, w4.w, acc[i][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= a.Tout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co < a.Cout) conv_epilogue<T>(a, b, t, co, acc[i][j]);
+    }
+  }
+}
+
+// ---- conv_post (C -> 1, k7, no bias) + tanh (models.py:128-130); input already leaky-ReLU(0.01)'d -------------
+template <typename T>
+__global__ void __launch_bounds__(256) conv_post_kernel(const T* __restrict__ in, const T* __restrict__ w, T* __restrict__ out,
+                                                        int B, int Tn, int C) {
+  extern __shared__ float wsm[];   // [7][C]
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) wsm[i] = Elem<T>::to_f(w[i]);
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * Tn) return;
+  const int b = (int)(idx / Tn), t = (int)(idx - (long long)b * Tn);
+  float acc = 0.f;
+  for (int k = 0; k < 7; ++k) {
+    const int ti = t + k - 3;
+    if (ti < 0 || ti >= Tn) continue;
+    const T* row = in + ((size_t)b * Tn + ti) * C;
+    for (int c = 0; c < C; c += 8) {
+      float f[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wsm[k * C + c + j], acc);
+    }
+  }
+  out[idx] = Elem<T>::from_f(tanhf(acc));
+}
+
+// ---- WaveNet gate: u = tanh(a[:H]) * sigmoid(a[H:]) (commons.py:14-21) --------------------------------------------
+template <typename T>
+__global__ void gate_kernel(const float* __restrict__ a32, T* __restrict__ u, long long rows, int Hc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Hc) return;
+  const long long r = i / Hc;
+  const int c = (int)(i - r * Hc);
+  const float ta = a32[r * 2 * Hc + c], sa = a32[r * 2 * Hc + Hc + c];
+  u[i] = Elem<T>::from_f(tanhf(ta) * (1.f / (1.f + __expf(-sa))));
+}
+
+// ---- layout changes at the boundary: torch [B][C][T] <-> time-major [B][T][C] ------------------------------------------
+template <typename T>
+__global__ void to_time_major_kernel(const T* __restrict__ in, float* __restrict__ out32, T* __restrict__ outT, int C, int Tn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < Tn) ? Elem<T>::to_f(in[((size_t)b * C + c) * Tn + t]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < Tn && c < C) {
+      const float v = tile[threadIdx.x][i];
+      const size_t o = ((size_t)b * Tn + t) * C + c;
+      if (out32) out32[o] = v;
+      if (outT) outT[o] = Elem<T>::from_f(v);
+    }
+  }
+}
+template <typename T>
+__global__ void to_channel_major_kernel(const float* __restrict__ in32, T* __restrict__ out, int C, int Tn) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < Tn) ? in32[((size_t)b * Tn + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < Tn && c < C) out[((size_t)b * C + c) * Tn + t] = Elem<T>::from_f(tile[threadIdx.x][i]);
+  }
+}
+
+struct Weight {
+  const void* w;
+  const void* b;
+};
+
+}  // namespace
+
+struct gsv_voc_ctx {
+  gsv_voc_dims dims;
+  std::map<std::string, Weight> weights;
+  void* scratch;
+  size_t scratch_bytes;
+  void* zero_bias;       // conv layers without bias
+  void* debug_z;
+  long long launches;
+};
+
+namespace {
+
+template <typename T>
+int launch_conv(gsv_voc_ctx* ctx, const ConvArgs<T>& a, cudaStream_t st) {
+  if (a.Cin % 8 != 0 || a.in_off % 8 != 0 || a.in_ld % 8 != 0) {
+    gsv_set_error("conv: channel counts must be multiples of 8 (Cin=%d off=%d ld=%d)", a.Cin, a.in_off, a.in_ld);
+    return GSV_ERR_ARG;
+  }
+  if (a.stride == 1) {
+    if ((a.KW - 1) * a.dil > 64) { gsv_set_error("conv: halo too large"); return GSV_ERR_ARG; }
+    if (a.Cout > 32) {
+      dim3 g((a.Tout + 63) / 64, (a.Cout + 63) / 64, a.B);
+      conv1d_kernel<T, 64><<<g, 256, 0, st>>>(a);
+    } else if (a.Cout > 16) {
+      dim3 g((a.Tout + 127) / 128, 1, a.B);
+      conv1d_kernel<T, 32><<<g, 256, 0, st>>>(a);
+    } else {
+      dim3 g((a.Tout + 255) / 256, 1, a.B);
+      conv1d_kernel<T, 16><<<g, 256, 0, st>>>(a);
+    }
+  } else {
+    if (a.KW > 16 || a.stride < 2) { gsv_set_error("convT: kernel %d stride %d unsupported", a.KW, a.stride); return GSV_ERR_ARG; }
+    if (a.Cout > 32) {
+      dim3 g((a.Tout + 63) / 64, (a.Cout + 63) / 64, a.B);
+      convt1d_kernel<T, 64><<<g, 256, 0, st>>>(a);
+    } else if (a.Cout > 16) {
+      dim3 g((a.Tout + 127) / 128, 1, a.B);
+      convt1d_kernel<T, 32><<<g, 256, 0, st>>>(a);
+    } else {
+      dim3 g((a.Tout + 255) / 256, 1, a.B);
+      convt1d_kernel<T, 16><<<g, 256, 0, st>>>(a);
+    }
+  }
+  ctx->launches += 1;
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
+struct Arena {
+  char* base;
+  size_t off, cap;
+  template <typename P> P* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    P* p = reinterpret_cast<P*>(base + off);
+    off += n * sizeof(P);
+    return p;
+  }
+};
+
+template <typename T>
+int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const void* ge_, int B, int Tn, int Tg, void* out_,
+                  cudaStream_t st) {
+  const gsv_voc_dims& D = ctx->dims;
+  const int C = D.inter_channels, Hc = D.hidden_channels, half = C / 2, gin = D.gin_channels, C0 = D.upsample_initial_channel;
+  const int NL = D.wn_layers, NF = D.n_flows, NK = D.n_resblock_kernels;
+  const T* z_p = reinterpret_cast<const T*>(z_p_);
+  const T* mask = reinterpret_cast<const T*>(mask_);
+  const T* ge = reinterpret_cast<const T*>(ge_);
+  T* out = reinterpret_cast<T*>(out_);
+  auto W = [&](const std::string& name, Weight& w) -> int {
+    auto it = ctx->weights.find(name);
+    if (it == ctx->weights.end()) { gsv_set_error("vocoder weight '%s' was never set", name.c_str()); return GSV_ERR_STATE; }
+    w = it->second;
+    if (!w.b) w.b = ctx->zero_bias;
+    return GSV_OK;
+  };
+
+  // ---- scratch carve-up -----------------------------------------------------------------------------
+  size_t maxn = 0;   // max over generator stages of (samples per frame * channels)
+  {
+    size_t spf = 1; int ch = C0;
+    for (int i = 0; i < D.n_ups; ++i) { spf *= D.upsample_rates[i]; ch /= 2; maxn = spf * ch > maxn ? spf * ch : maxn; }
+  }
+  const size_t BT = (size_t)B * Tn;
+  float *z32, *h32, *a32, *o32, *condF, *condD, *X0, *XJ, *ACC;
+  T *zT, *hT, *uT, *oT, *geT, *preT, *XA0, *XAJ, *TA, *NEXT;
+  auto carve = [&](Arena& ar) {
+    z32 = ar.take<float>(BT * C);
+    zT = ar.take<T>(BT * C);
+    h32 = ar.take<float>(BT * Hc);
+    hT = ar.take<T>(BT * Hc);
+    a32 = ar.take<float>(BT * 2 * Hc);
+    uT = ar.take<T>(BT * Hc);
+    o32 = ar.take<float>(BT * Hc);
+    oT = ar.take<T>(BT * Hc);
+    geT = ar.take<T>((size_t)B * Tg * gin);
+    condF = ar.take<float>((size_t)NF * B * Tg * 2 * Hc * NL);
+    condD = ar.take<float>((size_t)B * Tg * C0);
+    preT = ar.take<T>(BT * C0);
+    X0 = ar.take<float>(BT * maxn);
+    XA0 = ar.take<T>(BT * maxn);
+    XJ = ar.take<float>(BT * maxn);
+    XAJ = ar.take<T>(BT * maxn);
+    TA = ar.take<T>(BT * maxn);
+    ACC = ar.take<float>(BT * maxn);
+    NEXT = ar.take<T>(BT * maxn);
+  };
+  Arena dry{nullptr, 0, 0};
+  carve(dry);
+  const size_t need = dry.off + 256;
+  if (need > ctx->scratch_bytes) {
+    GSV_CUDA(cudaStreamSynchronize(st));
+    if (ctx->scratch) GSV_CUDA(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+    GSV_CUDA(cudaMalloc(&ctx->scratch, need));
+    ctx->scratch_bytes = need;
+  }
+  Arena ar{reinterpret_cast<char*>(ctx->scratch), 0, ctx->scratch_bytes};
+  carve(ar);
+
+  int rc;
+  const dim3 tb(32, 8);
+  // ---- boundary transposes ------------------------------------------------------------------------------
+  to_time_major_kernel<T><<<dim3((Tn + 31) / 32, (C + 31) / 32, B), tb, 0, st>>>(z_p, z32, zT, C, Tn);
+  to_time_major_kernel<T><<<dim3((Tg + 31) / 32, (gin + 31) / 32, B), tb, 0, st>>>(ge, nullptr, geT, gin, Tg);
+  ctx->launches += 2;
+  GSV_CHECK_LAUNCH();
+
+  auto base_args = [&]() {
+    ConvArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.dil = 1; a.stride = 1; a.KW = 1; a.res_sign = 1.f; a.acc_scale = 1.f;
+    return a;
+  };
+
+  // ---- conditioning: cond_layer of each flow and dec.cond are 1x1 convs of ge (modules.py:83-84, models.py:116)
+  for (int f = 0; f <= NF; ++f) {
+    Weight w;
+    const bool dec = f == NF;
+    if ((rc = W(dec ? std::string("dec.cond") : "flow.flows." + std::to_string(2 * f) + ".enc.cond_layer", w))) return rc;
+    ConvArgs<T> a = base_args();
+    a.in = geT; a.in_ld = gin; a.Tin = a.Tout = Tg; a.Cin = gin;
+    a.Cout = dec ? C0 : 2 * Hc * NL;
+    a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)a.Cout * gin; a.bias = reinterpret_cast<const T*>(w.b);
+    a.out32 = dec ? condD : condF + (size_t)f * B * Tg * 2 * Hc * NL;
+    a.o_ld = a.Cout;
+    if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+  }
+
+  // ---- reverse flow: for fi = 3,2,1,0: Flip, then coupling.reverse (models.py:63-64) --------------------------------
+  for (int n = 0; n < NF; ++n) {
+    const int f = NF - 1 - n;
+    const bool odd = ((n + 1) & 1) != 0;          // flips applied so far
+    // logical x0 = first half after the flips, logical x1 = second half
+    const int x0_off = odd ? half : 0, x1_off = odd ? 0 : half;
+    const std::string P = "flow.flows." + std::to_string(2 * f) + ".";
+    Weight w;
+    // pre: h = (Wpre x0 + b) * mask (modules.py:484)
+    if ((rc = W(P + "pre", w))) return rc;
+    {
+      ConvArgs<T> a = base_args();
+      a.in = zT; a.in_ld = C; a.in_off = x0_off; a.in_rev = odd; a.Tin = a.Tout = Tn; a.Cin = half; a.Cout = Hc;
+      a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)Hc * half; a.bias = reinterpret_cast<const T*>(w.b);
+      a.mask = mask; a.out32 = h32; a.outT = hT; a.o_ld = Hc;
+      if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+    }
+    const float* cond = condF + (size_t)f * B * Tg * 2 * Hc * NL;
+    for (int l = 0; l < NL; ++l) {
+      // in_layer conv5 + cond slice -> gate (modules.py:87-94)
+      if ((rc = W(P + "enc.in_layers." + std::to_string(l), w))) return rc;
+      {
+        ConvArgs<T> a = base_args();
+        a.in = hT; a.in_ld = Hc; a.Tin = a.Tout = Tn; a.Cin = Hc; a.Cout = 2 * Hc; a.KW = D.wn_kernel;
+        a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)2 * Hc * Hc; a.bias = reinterpret_cast<const T*>(w.b);
+        a.add = cond + (size_t)l * 2 * Hc; a.add_ld = 2 * Hc * NL; a.add_tg = Tg;
+        a.out32 = a32; a.o_ld = 2 * Hc;
+        if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+      }
+      {
+        const long long n_el = (long long)BT * Hc;
+        gate_kernel<T><<<(unsigned)((n_el + 255) / 256), 256, 0, st>>>(a32, uT, (long long)BT, Hc);
+        ctx->launches += 1;
+        GSV_CHECK_LAUNCH();
+      }
+      // res_skip (modules.py:97-103)
+      if ((rc = W(P + "enc.res_skip_layers." + std::to_string(l), w))) return rc;
+      const bool last = l == NL - 1;
+      const int rows = last ? Hc : 2 * Hc;
+      if (!last) {   // residual half: h = (h + r[:H]) * mask
+        ConvArgs<T> a = base_args();
+        a.in = uT; a.in_ld = Hc; a.Tin = a.Tout = Tn; a.Cin = Hc; a.Cout = Hc;
+        a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)rows * Hc; a.bias = reinterpret_cast<const T*>(w.b);
+        a.res32 = h32; a.mask = mask; a.out32 = h32; a.outT = hT; a.o_ld = Hc;
+        if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+      }
+      {              // skip half: out += r[H:] (or all of r for the last layer); out*mask feeds post
+        ConvArgs<T> a = base_args();
+        a.in = uT; a.in_ld = Hc; a.Tin = a.Tout = Tn; a.Cin = Hc; a.Cout = Hc;
+        a.w = reinterpret_cast<const T*>(w.w) + (last ? 0 : (size_t)Hc * Hc); a.w_tap = (long long)rows * Hc;
+        a.bias = reinterpret_cast<const T*>(w.b) + (last ? 0 : Hc);
+        a.acc32 = o32; a.acc_init = l == 0; a.o_ld = Hc;
+        if (last) { a.mask = mask; a.outT = oT; }
+        if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+      }
+    }
+    // post + coupling: x1 = (x1 - (Wpost out + b) * mask) * mask (modules.py:486, 499); mask is 0/1
+    if ((rc = W(P + "post", w))) return rc;
+    {
+      ConvArgs<T> a = base_args();
+      a.in = oT; a.in_ld = Hc; a.Tin = a.Tout = Tn; a.Cin = Hc; a.Cout = half;
+      a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)half * Hc; a.bias = reinterpret_cast<const T*>(w.b);
+      a.res32 = z32; a.res_sign = -1.f; a.mask = mask; a.out32 = z32; a.outT = zT;
+      a.o_ld = C; a.o_off = x1_off; a.o_rev = odd;
+      if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+    }
+  }
+  if (ctx->debug_z) {
+    to_channel_major_kernel<T><<<dim3((Tn + 31) / 32, (C + 31) / 32, B), tb, 0, st>>>(z32, reinterpret_cast<T*>(ctx->debug_z), C, Tn);
+    ctx->launches += 1;
+    GSV_CHECK_LAUNCH();
+  }
+
+  // ---- generator (models.py:113-132) ----------------------------------------------------------------------
+  Weight w;
+  if ((rc = W("dec.conv_pre", w))) return rc;
+  {
+    // dec(z * mask): re-mask z on the way in (a no-op after >= 2 flows, kept for n_flows < 2)
+    ConvArgs<T> a = base_args();
+    a.in = zT; a.in_ld = C; a.Tin = a.Tout = Tn; a.Cin = C; a.Cout = C0; a.KW = 7;
+    a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)C0 * C; a.bias = reinterpret_cast<const T*>(w.b);
+    a.add = condD; a.add_ld = C0; a.add_tg = Tg;
+    a.outT = preT; a.act = ACT_LRELU_01; a.o_ld = C0;
+    if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+  }
+  const T* stage_in = preT;
+  int ch = C0, Tcur = Tn;
+  for (int i = 0; i < D.n_ups; ++i) {
+    const int u = D.upsample_rates[i], ku = D.upsample_kernel_sizes[i];
+    const int cin = ch, cout = ch / 2, Tnext = Tcur * u;
+    if ((rc = W("dec.ups." + std::to_string(i), w))) return rc;
+    {
+      ConvArgs<T> a = base_args();
+      a.in = stage_in; a.in_ld = cin; a.Tin = Tcur; a.Tout = Tnext; a.Cin = cin; a.Cout = cout; a.KW = ku; a.stride = u;
+      a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)cout * cin; a.bias = reinterpret_cast<const T*>(w.b);
+      a.out32 = X0; a.outT = XA0; a.act = ACT_LRELU_01; a.o_ld = cout;
+      if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+    }
+    ch = cout; Tcur = Tnext;
+    for (int j = 0; j < NK; ++j) {
+      const int k = D.resblock_kernel_sizes[j];
+      const std::string R = "dec.resblocks." + std::to_string(i * NK + j) + ".";
+      for (int c = 0; c < 3; ++c) {
+        const int dl = D.resblock_dilations[j][c];
+        Weight w1, w2;
+        if ((rc = W(R + "convs1." + std::to_string(c), w1))) return rc;
+        if ((rc = W(R + "convs2." + std::to_string(c), w2))) return rc;
+        {   // xt = lrelu(conv_d(lrelu(x)))
+          ConvArgs<T> a = base_args();
+          a.in = c == 0 ? XA0 : XAJ; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k; a.dil = dl;
+          a.w = reinterpret_cast<const T*>(w1.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w1.b);
+          a.outT = TA; a.act = ACT_LRELU_01; a.o_ld = ch;
+          if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+        }
+        {   // x = conv_1(xt) + x
+          ConvArgs<T> a = base_args();
+          a.in = TA; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k;
+          a.w = reinterpret_cast<const T*>(w2.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w2.b);
+          a.res32 = c == 0 ? X0 : XJ; a.o_ld = ch;
+          if (c < 2) {
+            a.out32 = XJ; a.outT = XAJ; a.act = ACT_LRELU_01;
+          } else {
+            // xs += resblock(x); after the third block x = xs / 3 (models.py:121-127), then the next
+            // stage's leaky-ReLU (0.1) or the final one (default slope 0.01, models.py:128)
+            a.acc32 = ACC; a.acc_init = j == 0;
+            if (j == NK - 1) {
+              a.acc_scale = 1.f / (float)NK;
+              a.outT = NEXT; a.act = (i == D.n_ups - 1) ? ACT_LRELU_001 : ACT_LRELU_01;
+            }
+          }
+          if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+        }
+      }
+    }
+    stage_in = NEXT;
+    // NEXT is consumed by the next stage's upsampling before it is written again (same stream)
+  }
+  if ((rc = W("dec.conv_post", w))) return rc;
+  {
+    const long long n_out = (long long)B * Tcur;
+    conv_post_kernel<T><<<(unsigned)((n_out + 255) / 256), 256, 7 * ch * sizeof(float), st>>>(
+        stage_in, reinterpret_cast<const T*>(w.w), out, B, Tcur, ch);
+    ctx->launches += 1;
+    GSV_CHECK_LAUNCH();
+  }
+  return GSV_OK;
+}
+
+}  // namespace
+
+extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
+  GSV_ARG(dims && out);
+  GSV_ARG(dims->inter_channels % 16 == 0 && dims->hidden_channels % 8 == 0 && dims->gin_channels % 8 == 0);
+  GSV_ARG(dims->n_ups >= 1 && dims->n_ups <= 8 && dims->n_resblock_kernels >= 1 && dims->n_resblock_kernels <= 4);
+  GSV_ARG(dims->upsample_initial_channel % (8 << dims->n_ups) == 0);
+  GSV_ARG(dims->dtype == GSV_F16 || dims->dtype == GSV_BF16);
+  for (int i = 0; i < dims->n_ups; ++i) {
+    GSV_ARG(dims->upsample_rates[i] >= 2 && dims->upsample_kernel_sizes[i] <= 16);
+    GSV_ARG((dims->upsample_kernel_sizes[i] - dims->upsample_rates[i]) % 2 == 0);
+  }
+  int dev = 0;
+  GSV_CUDA(cudaGetDevice(&dev));
+  int rc = gsv_device_check(dev);
+  if (rc) return rc;
+  gsv_voc_ctx* ctx = new (std::nothrow) gsv_voc_ctx();
+  GSV_ARG(ctx != nullptr);
+  ctx->dims = *dims;
+  ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->debug_z = nullptr; ctx->launches = 0;
+  GSV_CUDA(cudaMalloc(&ctx->zero_bias, 8192));
+  GSV_CUDA(cudaMemset(ctx->zero_bias, 0, 8192));
+  *out = ctx;
+  return GSV_OK;
+}
+
+extern "C" int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias) {
+  GSV_ARG(ctx && name && dev_weight);
+  ctx->weights[std::string(name)] = Weight{dev_weight, dev_bias};
+  return GSV_OK;
+}
+
+extern "C" int gsv_voc_destroy(gsv_voc_ctx* ctx) {
+  if (!ctx) return GSV_OK;
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->zero_bias) cudaFree(ctx->zero_bias);
+  delete ctx;
+  return GSV_OK;
+}
+
+extern "C" int gsv_voc_set_debug_z(gsv_voc_ctx* ctx, void* dev_z) {
+  GSV_ARG(ctx);
+  ctx->debug_z = dev_z;
+  return GSV_OK;
+}
+
+extern "C" int64_t gsv_voc_launch_count(gsv_voc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const void* dev_mask, const void* dev_ge, int B, int T,
+                                int Tg, void* dev_out, void* stream) {
+  GSV_ARG(ctx && dev_z_p && dev_mask && dev_ge && dev_out);
+  GSV_ARG(B >= 1 && T >= 1 && (Tg == 1 || Tg == T));
+  if (ctx->dims.dtype == GSV_F16)
+    return flow_dec_impl<__half>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
+  return flow_dec_impl<__nv_bfloat16>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
+}

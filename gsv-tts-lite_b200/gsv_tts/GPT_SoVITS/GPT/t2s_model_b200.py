@@ -1,0 +1,336 @@
+"""B200 backend of the text-to-semantic decoder.
+
+Third backend next to the reference's SDPA and FlashAttention ones (reference
+gsv_tts/GPT_SoVITS/GPT/t2s_model.py and t2s_model_flash_attn.py, selected in
+gsv_tts/Loader.py:117-121, 156-160).  Same constructor, same state-dict keys, same
+``initialize_runtime`` / ``infer`` / ``infer_stream`` / ``infer_batched`` signatures and return
+shapes; the arithmetic runs in ``libgsv_b200.so`` (prefill kernels + one persistent decode
+kernel per launch).  This class only owns parameters, packs them for the kernels and drives
+the slot life cycle.
+
+Differences a caller can observe (documented):
+  * decode stops at the first EOS on the device; the reference tests EOS every 5th step and cuts
+    the overshoot afterwards (t2s_model.py:451-464) -- same returned tokens.
+  * the noise for ``argmax(p / Exp(1))`` comes from a per-slot Philox stream seeded from torch's
+    global generator, not from ``Tensor.exponential_``; tests inject identical noise instead.
+  * idle slots are skipped instead of stepped with kv_len reset to 0 (t2s_model.py:684-695).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterator, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from ... import _native as N
+
+
+class _TokenEmbedding(nn.Module):
+    """Parameter holder with the reference's key ``word_embeddings.weight`` (embedding.py:7-32)."""
+
+    def __init__(self, dim: int, vocab: int):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(vocab, dim)
+
+
+class _SinePositionalEmbedding(nn.Module):
+    """Holds ``alpha`` (embedding.py:35-50); the table itself is built in initialize_runtime."""
+
+    def __init__(self):
+        super().__init__()
+        self.alpha = nn.Parameter(torch.ones(1))
+
+
+class _Block(nn.Module):
+    def __init__(self, d: int):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(d)
+        self.qkv = nn.Linear(d, 3 * d)
+        self.out_proj = nn.Linear(d, d)
+        self.norm2 = nn.LayerNorm(d)
+        self.mlp = nn.Sequential(nn.Linear(d, 4 * d), nn.ReLU(inplace=True), nn.Linear(4 * d, d))
+
+
+class _Transformer(nn.Module):
+    def __init__(self, n: int, d: int):
+        super().__init__()
+        self.blocks = nn.ModuleList([_Block(d) for _ in range(n)])
+
+
+def sine_table(n_pos: int, dim: int) -> torch.Tensor:
+    """pe[p,2j]=sin(p w_j), pe[p,2j+1]=cos(p w_j), w_j=exp(-2j ln(1e4)/dim), fp32 (embedding.py:52-69)."""
+    pos = torch.arange(n_pos, dtype=torch.float32).unsqueeze(1)
+    w = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * -(math.log(10000.0) / dim))
+    pe = torch.zeros(n_pos, dim, dtype=torch.float32)
+    pe[:, 0::2] = torch.sin(pos * w)
+    pe[:, 1::2] = torch.cos(pos * w)
+    return pe
+
+
+class Text2SemanticDecoder(nn.Module):
+    N_POS = 4000                      # t2s_model.py:212-213
+    DECODE_CHUNK = 32                 # decode steps per persistent launch in infer()
+    BATCH_INTERVAL = 8                # decode steps between harvest/refill points in infer_batched()
+
+    def __init__(self, config):
+        super().__init__()
+        m = config["model"]
+        self.model_dim = m["hidden_dim"]
+        self.embedding_dim = m["embedding_dim"]
+        self.num_head = m["head"]
+        self.num_layers = m["n_layer"]
+        self.vocab_size = m["vocab_size"]
+        self.phoneme_vocab_size = m["phoneme_vocab_size"]
+        self.p_dropout = m["dropout"]
+        self.EOS = m["EOS"]
+        if self.model_dim != self.embedding_dim:
+            raise ValueError("hidden_dim must equal embedding_dim")
+        self.bert_proj = nn.Linear(1024, self.embedding_dim)
+        self.ar_text_embedding = _TokenEmbedding(self.embedding_dim, self.phoneme_vocab_size)
+        self.ar_text_position = _SinePositionalEmbedding()
+        self.ar_audio_embedding = _TokenEmbedding(self.embedding_dim, self.vocab_size)
+        self.ar_audio_position = _SinePositionalEmbedding()
+        self.ar_predict_layer = nn.Linear(self.model_dim, self.vocab_size, bias=False)
+        self.t2s_transformer = _Transformer(self.num_layers, self.model_dim)
+        self._ctx = None
+        self._packed = {}
+        self._buckets = {}            # batch size -> sorted list of lengths (gpt_cache)
+        self._parity_noise = None     # test hook: [rows][V] fp32 Exp(1) noise for slot 0
+        self.debug_seed: Optional[int] = None
+
+    # ------------------------------------------------------------------ runtime set-up
+    @torch.inference_mode()
+    def initialize_runtime(self, dtype, device, gpt_cache):
+        """Counterpart of t2s_model.py:210-298: size the KV cache for the largest (B, S) bucket and
+        hand packed weights to the native context.  Nested buckets collapse to "attend over the
+        live kv_len" (SURVEY.md A.5); only the per-batch-size length cap is kept."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise N.NativeError("the B200 backend needs a CUDA device; there is no CPU path here")
+        self._device, self._dtype = device, dtype
+        for b, s in gpt_cache:
+            self._buckets.setdefault(int(b), []).append(int(s))
+        for b in self._buckets:
+            self._buckets[b].sort()
+        max_slots = max(self._buckets)
+        max_seq = max(max(v) for v in self._buckets.values())
+        d, L = self.model_dim, self.num_layers
+        blk = self.t2s_transformer.blocks
+
+        def stack(get):
+            return torch.stack([get(b).detach() for b in blk]).to(device=device, dtype=dtype).contiguous()
+
+        pe = sine_table(self.N_POS, d).to(device=device, dtype=dtype)
+        pk = {
+            "w_qkv": stack(lambda b: b.qkv.weight), "b_qkv": stack(lambda b: b.qkv.bias),
+            "w_o": stack(lambda b: b.out_proj.weight), "b_o": stack(lambda b: b.out_proj.bias),
+            "w_1": stack(lambda b: b.mlp[0].weight), "b_1": stack(lambda b: b.mlp[0].bias),
+            "w_2": stack(lambda b: b.mlp[2].weight), "b_2": stack(lambda b: b.mlp[2].bias),
+            "ln1_g": stack(lambda b: b.norm1.weight), "ln1_b": stack(lambda b: b.norm1.bias),
+            "ln2_g": stack(lambda b: b.norm2.weight), "ln2_b": stack(lambda b: b.norm2.bias),
+        }
+
+        def one(t):
+            return t.detach().to(device=device, dtype=dtype).contiguous()
+
+        pk["w_head"] = one(self.ar_predict_layer.weight)
+        pk["emb_audio"] = one(self.ar_audio_embedding.word_embeddings.weight)
+        pk["emb_text"] = one(self.ar_text_embedding.word_embeddings.weight)
+        # alpha * pe in the storage dtype, as the reference computes pe_cache (t2s_model.py:409)
+        pk["pe_audio"] = (one(self.ar_audio_position.alpha) * pe).contiguous()
+        pk["pe_text"] = (one(self.ar_text_position.alpha) * pe).contiguous()
+        pk["w_bert"] = one(self.bert_proj.weight)
+        pk["b_bert"] = one(self.bert_proj.bias)
+        self._packed = pk
+        dims = N.GptDims(d_model=d, n_head=self.num_head, n_layer=L, d_ff=4 * d, vocab=self.vocab_size,
+                         eos=self.EOS, n_phoneme=self.phoneme_vocab_size, d_bert=1024, n_pos=self.N_POS,
+                         dtype=N.dtype_code(dtype), max_slots=max_slots, max_seq=max_seq)
+        w = N.GptWeights(**{k: v.data_ptr() for k, v in pk.items()})
+        ctx = C.c_void_p()
+        with torch.cuda.device(device):
+            N.check(N.lib().gsv_gpt_create(C.byref(dims), C.byref(w), C.byref(ctx)))
+        self._ctx = ctx
+        self._max_slots, self._max_seq = max_slots, max_seq
+        # pinned read-back buffers
+        self._h_ngen = torch.zeros(max_slots, dtype=torch.int32).pin_memory()
+        self._h_active = torch.zeros(max_slots, dtype=torch.int32).pin_memory()
+        self._h_tokens = torch.zeros(max_slots, max_seq, dtype=torch.int32).pin_memory()
+
+    def __del__(self):
+        try:
+            if self._ctx is not None:
+                N.lib().gsv_gpt_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _next_seed(self) -> int:
+        if self.debug_seed is not None:
+            return self.debug_seed
+        return int(torch.randint(0, 2 ** 62, (1,)).item())      # follows torch.manual_seed
+
+    def _prefill(self, slot, x, y, bert, samp: N.GptSampling):
+        x = x.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+        y = y.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+        bert = bert.to(device=self._device, dtype=self._dtype).contiguous().view(x.numel(), -1)
+        N.check(N.lib().gsv_gpt_prefill(self._ctx, slot, x.data_ptr(), x.numel(), y.data_ptr(), y.numel(),
+                                        bert.data_ptr(), C.byref(samp), self._stream()))
+
+    def _decode(self, n_steps: int):
+        N.check(N.lib().gsv_gpt_decode(self._ctx, n_steps, self._stream()))
+
+    def _read(self, n_slots: int, tokens: bool = True):
+        N.check(N.lib().gsv_gpt_read(self._ctx, self._h_ngen.data_ptr(), self._h_active.data_ptr(),
+                                     self._h_tokens.data_ptr() if tokens else None, 0, n_slots, self._stream()))
+        torch.cuda.current_stream(self._device).synchronize()
+
+    def _release_all(self):
+        for s in range(self._max_slots):
+            N.check(N.lib().gsv_gpt_release_slot(self._ctx, s, self._stream()))
+
+    def _single_setup(self, x, y, bert, top_k, top_p, temperature, repetition_penalty, suppress_steps,
+                      force_steps: Optional[int]):
+        if 1 not in self._buckets:
+            raise KeyError("gpt_cache has no batch-size-1 bucket")        # same failure as t2s_model.py:400
+        self._release_all()
+        samp = N.GptSampling(top_k=top_k if top_k is not None else 0, top_p=top_p if top_p is not None else 1.0,
+                             temperature=temperature, repetition_penalty=repetition_penalty,
+                             suppress_steps=suppress_steps, max_new_tokens=0,
+                             mask_eos=1 if force_steps is not None else 0, max_kv=self._buckets[1][-1],
+                             seed=self._next_seed())
+        if self._parity_noise is not None:
+            N.check(N.lib().gsv_gpt_set_noise(self._ctx, self._parity_noise.data_ptr(), self._parity_noise.shape[0]))
+        else:
+            N.check(N.lib().gsv_gpt_set_noise(self._ctx, None, 0))
+        self._prefill(0, x, y, bert, samp)
+
+    # ------------------------------------------------------------------ reference entry points
+    @torch.inference_mode()
+    def infer(self, x, y, bert_feature, top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0,
+              repetition_penalty: float = 1.35, initial_suppression_steps: int = 10, check_interval: int = 5,
+              force_steps: Optional[int] = None):
+        """t2s_model.py:385-464.  x [1,Nx] int64, y [1,Ny] int64, bert [1,Nx,1024] -> int64 [1,1,N]."""
+        self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
+                           initial_suppression_steps, force_steps)
+        done_steps = 0
+        while True:
+            n = self.DECODE_CHUNK
+            if force_steps is not None:
+                n = min(n, force_steps - done_steps)
+                if n <= 0:
+                    break
+            self._decode(n)
+            done_steps += n
+            self._read(1, tokens=False)
+            if not int(self._h_active[0]):
+                break
+        self._read(1)
+        n_gen = int(self._h_ngen[0])
+        toks = self._h_tokens[0, :n_gen].to(torch.int64)
+        # tokens[0] is the first sampled token, which the reference never returns (:458); cut at EOS (:459-464)
+        out = toks[1:]
+        if out.numel() and int(out[-1]) == self.EOS:
+            out = out[:-1]
+        return out.to(self._device).view(1, 1, -1)
+
+    @torch.inference_mode()
+    def infer_stream(self, x, y, bert_feature, top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0,
+                     repetition_penalty: float = 1.35, initial_suppression_steps: int = 10, stream_chunk: int = 25,
+                     boost_first_chunk: bool = True, debug: bool = True,
+                     force_steps: Optional[int] = None) -> Iterator[Tuple[torch.Tensor, bool]]:
+        """t2s_model.py:466-553: yields (tokens so far [1,1,n], is_final) every ``stream_chunk`` tokens,
+        one chunk late unless ``boost_first_chunk``; the final yield after an EOS break carries the
+        first sampled token (the reference slices ``[-idx:]`` with idx one past the appended count)."""
+        self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
+                           initial_suppression_steps, force_steps)
+        first, pre_chunk, idx = True, None, 0
+        while True:
+            n = stream_chunk
+            if force_steps is not None:
+                n = min(n, force_steps - idx)
+                if n <= 0:
+                    break
+            self._decode(n)
+            self._read(1)
+            n_gen = int(self._h_ngen[0])            # s0 + decode steps so far
+            active = int(self._h_active[0])
+            toks = self._h_tokens[0, :n_gen].to(torch.int64)
+            steps = n_gen - 1
+            if not active and int(toks[-1]) == self.EOS:
+                # EOS sampled at decode step `steps`: loop broke before the append (:534-535)
+                final = toks[0:steps]
+                yield final.to(self._device).view(1, 1, -1), True
+                return
+            idx = steps
+            if idx % stream_chunk == 0 and idx > 0:
+                if pre_chunk is not None:
+                    yield pre_chunk, False
+                pre_chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
+                if boost_first_chunk and first:
+                    first = False
+                    yield pre_chunk, False
+                    pre_chunk = None
+            if not active:
+                break
+        self._read(1)
+        n_gen = int(self._h_ngen[0])
+        toks = self._h_tokens[0, :n_gen].to(torch.int64)
+        yield toks[1:].to(self._device).view(1, 1, -1), True
+
+    @torch.inference_mode()
+    def infer_batched(self, x: List[torch.Tensor], y: List[torch.Tensor], bert_feature: List[torch.Tensor],
+                      top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35,
+                      check_interval: int = 5, max_new: Optional[List[int]] = None):
+        """t2s_model.py:555-734: continuous batching.  Slot count = smallest configured batch >= B,
+        else the largest (:569-574); no repetition penalty, no token suppression (:613, :651);
+        finished rows are harvested and their slot refilled from the queue (:672-722).
+        Returns (list of int64 [n_i] in completion order, int64 [B] original indices)."""
+        B = len(x)
+        slots = None
+        for b in sorted(self._buckets):
+            slots = b
+            if b >= B:
+                break
+        max_kv = self._buckets[slots][-1]
+        self._release_all()
+        N.check(N.lib().gsv_gpt_set_noise(self._ctx, None, 0))
+        base_seed = self._next_seed()
+
+        def start(slot, r):
+            samp = N.GptSampling(top_k=top_k if top_k is not None else 0, top_p=top_p if top_p is not None else 1.0,
+                                 temperature=temperature, repetition_penalty=1.0, suppress_steps=0,
+                                 max_new_tokens=(max_new[r] if max_new is not None else 0), mask_eos=0,
+                                 max_kv=max_kv, seed=(base_seed + 0x9E3779B97F4A7C15 * (r + 1)) & (2 ** 64 - 1))
+            self._prefill(slot, x[r], y[r], bert_feature[r], samp)
+
+        owner = [-1] * slots
+        nxt = 0
+        for s in range(min(slots, B)):
+            start(s, nxt)
+            owner[s] = nxt
+            nxt += 1
+        results, order = [], []
+        interval = max(int(check_interval), self.BATCH_INTERVAL)
+        while any(o >= 0 for o in owner):
+            self._decode(interval)
+            self._read(slots)
+            for s in range(slots):
+                if owner[s] >= 0 and not int(self._h_active[s]):
+                    n_gen = int(self._h_ngen[s])
+                    toks = self._h_tokens[s, 1:n_gen].to(torch.int64)
+                    if toks.numel() and int(toks[-1]) == self.EOS:
+                        toks = toks[:-1]
+                    results.append(toks.to(self._device))
+                    order.append(owner[s])
+                    owner[s] = -1
+                    if nxt < B:
+                        start(s, nxt)
+                        owner[s] = nxt
+                        nxt += 1
+        return results, torch.tensor(order, device=self._device)

@@ -66,7 +66,7 @@ SOVITS_MODEL = {
     "v2Pro": dict(_SOVITS_COMMON, upsample_initial_channel=512, gin_channels=1024, version="v2Pro"),
     "v2ProPlus": dict(_SOVITS_COMMON, upsample_initial_channel=768, gin_channels=1024, version="v2ProPlus"),
     # reduced widths, same topology: CPU-fast parity case
-    "tiny": dict(_SOVITS_COMMON, upsample_initial_channel=128, gin_channels=64, version="v2"),
+    "tiny": dict(_SOVITS_COMMON, upsample_initial_channel=256, gin_channels=64, version="v2"),
 }
 
 

@@ -1,0 +1,190 @@
+/* gsv_b200.h -- C ABI of libgsv_b200.so: the two hot paths of GSV-TTS-Lite on B200 (sm_100a).
+ *
+ * The reference (chinokikiss/GSV-TTS-Lite, /root/reference) has no native layer: its seam is
+ * Python duck typing at two objects built by gsv_tts/Loader.py.  Each entry point below cites
+ * the reference code whose work it takes over.  Signatures use plain pointers and sizes only:
+ * no torch types cross this boundary.  All pointers named dev_* are device pointers owned by
+ * the caller; `stream` is a cudaStream_t passed as void*.  Every function returns GSV_OK (0)
+ * or a negative gsv_status and never throws; gsv_last_error() gives the message.
+ *
+ * Element type of every "T" array is dims.dtype (fp16 or bf16); accumulation is fp32.
+ */
+#ifndef GSV_B200_H
+#define GSV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GSV_OK = 0,
+  GSV_ERR_ARG = -1,      /* bad argument / unsupported shape */
+  GSV_ERR_CUDA = -2,     /* CUDA runtime error (message in gsv_last_error) */
+  GSV_ERR_STATE = -3,    /* call sequence error (e.g. decode on an empty slot set) */
+  GSV_ERR_NODEVICE = -4  /* not an sm_100 device */
+} gsv_status;
+
+typedef enum { GSV_F16 = 0, GSV_BF16 = 1 } gsv_dtype;
+
+const char* gsv_last_error(void);
+int gsv_version(void);
+/* Device check: GSV_OK only on compute capability 10.x. */
+int gsv_device_check(int device);
+
+/* ======================================================================================
+ * GPT semantic-token decoder
+ * replaces Text2SemanticDecoder (reference gsv_tts/GPT_SoVITS/GPT/t2s_model.py:158-734 and
+ * t2s_model_flash_attn.py) and what it calls in torch / flash-attn.
+ * ====================================================================================== */
+
+typedef struct {
+  int32_t d_model;     /* config["model"]["hidden_dim"]   (t2s_model.py:161) */
+  int32_t n_head;      /* config["model"]["head"]; head_dim must be 32       */
+  int32_t n_layer;
+  int32_t d_ff;        /* 4*d_model (t2s_model.py:14 mlp_ratio)             */
+  int32_t vocab;       /* 1025, EOS included                                 */
+  int32_t eos;
+  int32_t n_phoneme;
+  int32_t d_bert;      /* 1024 (t2s_model.py:172)                            */
+  int32_t n_pos;       /* rows of the positional tables (4000, :212-213)     */
+  int32_t dtype;       /* gsv_dtype                                          */
+  int32_t max_slots;   /* max batch size over gpt_cache   (<= 32)            */
+  int32_t max_seq;     /* max sequence length over gpt_cache                 */
+} gsv_gpt_dims;
+
+/* Device pointers to weights in the reference's own row-major layouts (nn.Linear: [out][in]).
+ * Per-layer tensors are stacked on a leading layer axis.  All of type T. */
+typedef struct {
+  const void* w_qkv;   /* [L][3d][d]   blocks.{i}.qkv.weight      */
+  const void* b_qkv;   /* [L][3d]                                 */
+  const void* w_o;     /* [L][d][d]    out_proj.weight            */
+  const void* b_o;     /* [L][d]                                  */
+  const void* w_1;     /* [L][F][d]    mlp.0.weight               */
+  const void* b_1;     /* [L][F]                                  */
+  const void* w_2;     /* [L][d][F]    mlp.2.weight               */
+  const void* b_2;     /* [L][d]                                  */
+  const void* ln1_g;   /* [L][d] norm1.weight                     */
+  const void* ln1_b;   /* [L][d] norm1.bias                       */
+  const void* ln2_g;   /* [L][d] norm2.weight                     */
+  const void* ln2_b;   /* [L][d] norm2.bias                       */
+  const void* w_head;  /* [V][d]  ar_predict_layer.weight (no bias) */
+  const void* emb_audio; /* [V][d] ar_audio_embedding              */
+  const void* pe_audio;  /* [n_pos][d] alpha_audio * pe ("pe_cache", t2s_model.py:409) */
+  const void* emb_text;  /* [P][d] ar_text_embedding               */
+  const void* pe_text;   /* [n_pos][d] alpha_text * pe             */
+  const void* w_bert;    /* [d][d_bert] bert_proj.weight           */
+  const void* b_bert;    /* [d]                                    */
+} gsv_gpt_weights;
+
+/* Per-slot sampling controls = keyword arguments of infer / infer_stream / infer_batched
+ * (t2s_model.py:386-397, 556-566) and of sample() (GPT/utils.py:12-59). */
+typedef struct {
+  int32_t top_k;              /* <=0: disabled                                   */
+  float top_p;                /* >=1: disabled                                   */
+  float temperature;
+  float repetition_penalty;   /* 1.0: disabled (batched mode, t2s_model.py:651)  */
+  int32_t suppress_steps;     /* tokens {280,486,EOS} masked while idx < this (10 single, 0 batched) */
+  int32_t max_new_tokens;     /* <=0: until the cache is full; else EOS is forced after this many   */
+  int32_t mask_eos;           /* bench hook: never sample EOS              */
+  int32_t max_kv;             /* <=0: dims.max_seq; else the slot stops when kv_len reaches this (the
+                                 largest bucket length of its batch size, t2s_model.py:425, :656)     */
+  uint64_t seed;              /* Philox key for the slot's Exp(1) noise          */
+} gsv_gpt_sampling;
+
+typedef struct gsv_gpt_ctx gsv_gpt_ctx;
+
+/* Allocates KV cache [L][slots][H][S][32] x2 and all step buffers (initialize_runtime,
+ * t2s_model.py:210-298: one K root, one V root, static step I/O).  No graph capture is needed
+ * here: the decode kernel is one persistent launch per call. */
+int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w, gsv_gpt_ctx** out);
+int gsv_gpt_destroy(gsv_gpt_ctx* ctx);
+
+/* Prefill one request into a cache slot and sample its first token:
+ * process_single_data + T2STransformer.process_prompt + first sample() (t2s_model.py:351-383,
+ * 114-127, 414-420; refill path :696-722).  dev_x [nx] int64 phoneme ids, dev_y [ny] int64
+ * prompt tokens, dev_bert [nx][d_bert] T.  The slot becomes active. */
+int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
+                    const void* dev_bert, const gsv_gpt_sampling* samp, void* stream);
+
+/* Run up to n_steps decode steps over every active slot in ONE persistent kernel launch:
+ * T2STransformer.decode_next_token x n (t2s_model.py:129-143) + ar_predict_layer + sample +
+ * next-token embedding (:430-456, :637-653, :727-728), with per-slot stop at EOS / full cache
+ * evaluated on the device (no host sync per token, cf. :426, :451-453). */
+int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream);
+
+/* Copy slot state to host memory (asynchronously on `stream`; caller synchronises):
+ * n_gen[slot] = tokens sampled so far INCLUDING the first one (s0), active[slot] = still decoding,
+ * tokens[slot*max_seq + i].  Any pointer may be NULL. */
+int gsv_gpt_read(gsv_gpt_ctx* ctx, int32_t* host_n_gen, int32_t* host_active, int32_t* host_tokens,
+                 int first_slot, int n_slots, void* stream);
+/* Device pointers to the same state (for zero-copy consumers on the GPU). */
+int gsv_gpt_state_ptrs(gsv_gpt_ctx* ctx, int32_t** dev_tokens, int32_t** dev_n_gen, int32_t** dev_active);
+int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream);
+
+/* ---- parity hooks (used by tests/; they do not change the arithmetic) ------------------- */
+/* Exp(1) noise rows [n_rows][vocab] fp32 consumed one row per sample() call of slot 0, in call
+ * order, instead of the in-kernel Philox stream (SURVEY.md 7 "sampling parity under a seed"). */
+int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows);
+/* Teacher forcing for slot 0: its i-th sample() call (i = 0 is the first token after prefill)
+ * returns forced[i] instead of its own draw, so decode step i+1 is fed forced[i]. */
+int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n);
+/* Raw logits of slot 0 are appended as rows [vocab] fp32 (row 0 = prefill). */
+int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows);
+/* Number of kernel launches issued by this context so far (bench "gpu_launches"). */
+int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx);
+
+/* ======================================================================================
+ * SoVITS reverse flow + HiFi-GAN generator
+ * replaces SynthesizerTrn.flow_dec and the graph path of decode()
+ * (reference gsv_tts/GPT_SoVITS/SoVITS/models.py:380-383, 406-425, 23-138;
+ *  module/modules.py:80-104, 190-203, 482-511).
+ * ====================================================================================== */
+
+typedef struct {
+  int32_t inter_channels;   /* 192 */
+  int32_t hidden_channels;  /* 192 */
+  int32_t gin_channels;     /* 512 (v2) / 1024 (v2Pro, v2ProPlus) */
+  int32_t n_flows;          /* 4 coupling layers (models.py:31)    */
+  int32_t wn_layers;        /* 4 (models.py:303)                    */
+  int32_t wn_kernel;        /* 5                                    */
+  int32_t upsample_initial_channel; /* 512 / 768                   */
+  int32_t n_ups;            /* 5                                    */
+  int32_t upsample_rates[8];
+  int32_t upsample_kernel_sizes[8];
+  int32_t n_resblock_kernels;       /* 3 */
+  int32_t resblock_kernel_sizes[4]; /* 3,7,11 */
+  int32_t resblock_dilations[4][3]; /* 1,3,5  */
+  int32_t dtype;
+} gsv_voc_dims;
+
+/* Weights are passed by name, one tensor at a time, already weight-norm-folded (w = g*v/||v||,
+ * SURVEY.md A.6) and converted to T by the host loader.  Layouts expected (time-major, so that
+ * channels are the contiguous axis of every activation and weight tap):
+ *   Conv1d           : [k][Cout][Cin]
+ *   ConvTranspose1d  : [k][Cout][Cin]   (from torch's [Cin][Cout][k])
+ *   bias             : [Cout]
+ * Names are the reference state-dict names without the ".weight"/".bias" suffix, e.g.
+ * "flow.flows.0.enc.in_layers.2", "dec.ups.3", "dec.resblocks.7.convs1.0", "dec.conv_post". */
+typedef struct gsv_voc_ctx gsv_voc_ctx;
+
+int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out);
+int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias);
+int gsv_voc_destroy(gsv_voc_ctx* ctx);
+
+/* o = dec(flow(z_p, mask, ge, reverse) * mask, g=ge).
+ * dev_z_p [B][192][T] T (torch layout, as handed to flow_dec), dev_mask [B][T] T,
+ * dev_ge [B][gin][Tg] T with Tg == 1 or Tg == T (batched path, reference TTS.py:740-744),
+ * dev_out [B][T*samples_per_frame] T.  Scratch is grown on demand and cached in ctx. */
+int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const void* dev_mask, const void* dev_ge,
+                     int B, int T, int Tg, void* dev_out, void* stream);
+/* Test hook: also return the flow output z [B][192][T] T (NULL to skip). */
+int gsv_voc_set_debug_z(gsv_voc_ctx* ctx, void* dev_z);
+int64_t gsv_voc_launch_count(gsv_voc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSV_B200_H */
