@@ -1,0 +1,11 @@
+#!/bin/bash
+# One GPU round: bench line, ncu launch list of the same command, ncu --set full of the top kernel.
+mkdir -p gpurun_out
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+ncu --set full --clock-control none --import-source on -k regex:gpt_decode_kernel -s 2 -c 2 -o gpurun_out/prof_decode -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-300
+ls -la gpurun_out
