@@ -1,6 +1,7 @@
 // capi_gpt.cu -- extern "C" entry points of the GPT half of libgsv_b200 (see include/gsv_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -94,7 +95,12 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(ctx->pf_attn, S * d * 2, false);
   A(ctx->pf_h, S * F * 2, false);
   A(ctx->pf_tmp, S * d * 2, false);
+  A(ctx->ll_buf, gsv_gpt_ll_buffer_bytes(ctx), true);
 #undef A
+  {
+    const char* e = getenv("GSV_DECODE_IMPL");
+    ctx->force_barrier_kernel = (e && strcmp(e, "barrier") == 0) ? 1 : 0;
+  }
   if ((rc = gsv_gpt_decode_configure(ctx))) { gsv_gpt_destroy(ctx); return rc; }
   *out = ctx;
   return GSV_OK;
@@ -118,11 +124,18 @@ extern "C" int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x,
     gsv_set_error("prompt length %d+%d does not fit the KV cache (max_seq %d)", nx, ny, ctx->p.S);
     return GSV_ERR_ARG;
   }
+  ctx->slot_live[slot] = 1;
   return gsv_gpt_prefill_impl(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, samp, (cudaStream_t)stream);
 }
 
 extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   GSV_ARG(ctx && n_steps >= 1);
+  int live = 0;
+  for (int i = 0; i < ctx->p.slots; ++i) live += ctx->slot_live[i];
+  if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
+  // 1..4 live sequences: latency-optimised flag-in-data kernel; otherwise the barrier kernel
+  if (!ctx->force_barrier_kernel && gsv_gpt_ll_supported(ctx, live, n_steps))
+    return gsv_gpt_decode_ll_launch(ctx, live, n_steps, (cudaStream_t)stream);
   return gsv_gpt_decode_launch(ctx, n_steps, (cudaStream_t)stream);
 }
 
@@ -151,6 +164,7 @@ extern "C" int gsv_gpt_state_ptrs(gsv_gpt_ctx* ctx, int32_t** dev_tokens, int32_
 extern "C" int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream) {
   GSV_ARG(ctx && slot >= 0 && slot < ctx->p.slots);
   GSV_CUDA(cudaMemsetAsync(ctx->p.active + slot, 0, sizeof(int), (cudaStream_t)stream));
+  ctx->slot_live[slot] = 0;
   return GSV_OK;
 }
 
@@ -176,3 +190,11 @@ extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int m
 }
 
 extern "C" int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta) {
+  GSV_ARG(ctx);
+  ctx->p.prof = reinterpret_cast<long long*>(dev_records);
+  ctx->p.prof_max = dev_records ? max_records : 0;
+  ctx->p.prof_cta = cta;
+  return GSV_OK;
+}

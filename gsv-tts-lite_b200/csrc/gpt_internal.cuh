@@ -42,6 +42,8 @@ struct GptParams {
   const float* noise; int noise_rows;
   const int* forced; int n_forced; int* forced_pos;
   float* trace; int trace_max; int* trace_pos;
+  // in-kernel timeline (tools/decode_timeline.py): {id, clock64} records written by one CTA
+  long long* prof; int prof_max; int prof_cta;
 };
 
 struct gsv_gpt_ctx {
@@ -57,6 +59,11 @@ struct gsv_gpt_ctx {
   float* pf_f32;
   void* all_allocs[64];
   int n_allocs;
+  // small-batch LL decode kernel (gpt_decode_ll.cu)
+  void* ll_buf;
+  unsigned long long ll_seq;
+  int slot_live[GSV_MAX_SLOTS];   // host-side view: prefilled and not yet released
+  int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
 };
 
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
@@ -64,3 +71,6 @@ int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
 int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny,
                          const void* bert, const gsv_gpt_sampling* samp, cudaStream_t st);
 int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);
+size_t gsv_gpt_ll_buffer_bytes(const gsv_gpt_ctx* ctx);
+bool gsv_gpt_ll_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
+int gsv_gpt_decode_ll_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);

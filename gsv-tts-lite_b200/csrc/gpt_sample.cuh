@@ -46,8 +46,32 @@ __device__ __forceinline__ float block_sum(float a, float* red_v) {
 // Shared memory (in floats) needed by sample_slot; carved up at the top of the function.
 #define GSV_SAMPLE_SMEM_FLOATS (3 * GSV_VOCAB_MAX + 64)
 
+// Optional flag-in-data ("LL") plumbing used by the small-batch decode kernel (gpt_decode_ll.cu):
+// logits were already polled into sm[0..V), the next input and the slot status are published as
+// {value, tag} words, and kv_len comes from the caller instead of global memory.
+struct SampleLL {
+  bool preloaded;
+  uint2* xin_ll;
+  uint2* status_ll;
+  unsigned tag;
+  int kv_len;
+};
+__device__ __forceinline__ void ll_store(uint2* p, float val, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint2 ll_peek(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ll_wait(const uint2* p, unsigned tag) {
+  uint2 v;
+  do { v = ll_peek(p); } while (v.y != tag);
+  return __uint_as_float(v.x);
+}
+
 template <typename T>
-__device__ void sample_slot(const GptParams& p, int slot, float* sm) {
+__device__ void sample_slot(const GptParams& p, int slot, float* sm, const SampleLL* ll = nullptr) {
   float* lg = sm;                                         // [GSV_VOCAB_MAX] working logits
   int* sidx = reinterpret_cast<int*>(sm + GSV_VOCAB_MAX); // [GSV_VOCAB_MAX] sort indices (top-p only)
   float* kbuf = sm + 2 * GSV_VOCAB_MAX;                   // [GSV_VOCAB_MAX] exp() in sorted order (top-p only)
@@ -67,10 +91,11 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm) {
     trow = ld_cg(p.trace_pos);
     if (trow >= p.trace_max) trow = -1;
   }
+  const bool preloaded = ll != nullptr && ll->preloaded;
   for (int v = tid; v < GSV_VOCAB_MAX; v += NT) {
     float l = GSV_NEG_INF;
     if (v < p.V) {
-      l = ld_cg(p.logits + (size_t)slot * GSV_VOCAB_MAX + v);
+      l = preloaded ? lg[v] : ld_cg(p.logits + (size_t)slot * GSV_VOCAB_MAX + v);
       if (trow >= 0) p.trace[(size_t)trow * p.V + v] = l;
       if (v >= Vv) l = GSV_NEG_INF;
     }
@@ -236,7 +261,7 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm) {
   int tok = best.i;
 
   // bookkeeping by one thread; every value other CTAs read later goes through st.cg
-  const int kvl = ld_cg(p.kv_len + slot);
+  const int kvl = ll ? ll->kv_len : ld_cg(p.kv_len + slot);
   if (sp.max_new_tokens > 0 && ngen > sp.max_new_tokens) tok = p.eos;    // ngen counts s0 too
   if (slot == 0 && p.forced != nullptr) {
     int fp = ld_cg(p.forced_pos);
@@ -253,6 +278,10 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm) {
     __stcg(p.samp_count + slot, cnt + 1);
     if (tok < GSV_VOCAB_MAX) atomicOr(p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32) + (tok >> 5), 1u << (tok & 31));
     if (stop) st_cg(p.active + slot, 0);
+    if (ll) {
+      st_cg(p.kv_len + slot, kvl);
+      ll_store(ll->status_ll, stop ? 0.f : 1.f, ll->tag);
+    }
   }
   // next input: emb_audio[tok] * x_scale(=1) + (alpha*pe)[kv_len - Nx]  (:455-456, :727-728)
   if (!stop) {
@@ -264,6 +293,7 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm) {
       // the reference adds two T values and rounds to T
       float s = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(emb[c]) + Elem<T>::to_f(pe[c])));
       st_cg(p.xin + (size_t)slot * p.d + c, s);
+      if (ll) ll_store(ll->xin_ll + c, s, ll->tag);
     }
   }
   __syncthreads();

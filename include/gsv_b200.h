@@ -135,6 +135,9 @@ int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n);
 int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows);
 /* Number of kernel launches issued by this context so far (bench "gpu_launches"). */
 int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx);
+/* Tuning hook: CTA `cta` of the decode kernel appends {marker id, SM clock} pairs (2 x int64 per
+ * record, record 0 holds the count) to dev_records; NULL disables. */
+int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta);
 
 /* ======================================================================================
  * SoVITS reverse flow + HiFi-GAN generator
