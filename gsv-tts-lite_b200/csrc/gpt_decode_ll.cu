@@ -135,6 +135,7 @@ struct LLShared {
   float qkv[3][GSV_HEAD_DIM];              // q (pre-scaled), k_new, v_new of this CTA's head
   float wpart[NWARP][GSV_HEAD_DIM + 2];    // per-warp attention partials
   float wscale[NWARP];
+  float outv[MAXB][NWARP];                 // this trip's outputs, gathered for one coalesced LL store
   GemvDesc desc[5];        // 0 QKV, 1 out-proj, 2 MLP up, 3 MLP down, 4 head
 };
 
@@ -266,9 +267,11 @@ __device__ __forceinline__ void stage_input(const GemvDesc& d, const uint2* in, 
 }
 
 // ---- the one GEMV phase routine -----------------------------------------------------------------------------
-// unit of work = (output row r, K-quarter qd): a D-wide dot product per live slot.  kq == 1: warp w of CTA c
-// owns row c + G w (+ G*16 j).  kq == 4: warp w owns quarter (w & 3) of row c + G (w >> 2) (+ 4 G j), so the
-// four quarters of a row meet in one CTA and are summed through shared memory.
+// unit of work = (output row r, K-quarter qd): a D-wide dot product per live slot.  CTA c owns the
+// CONTIGUOUS rows [c*rpc, c*rpc + rpc), rpc = ceil(N / G): its outputs are adjacent words of the LL buffer,
+// gathered in shared memory and published by one warp with one coalesced store, so every 128-byte line of
+// an exchange buffer has a single writer.  kq == 1: warp w computes row c*rpc + w (+16 j).  kq == 4: warp w
+// computes quarter (w & 3) of row c*rpc + (w >> 2) (+4 j); the quarters are summed through shared memory.
 template <typename T, int NCH_D, int NB>
 __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, int ln_layer, const uint2* in_override,
                                         unsigned in_tag, unsigned out_tag, float* xs, const uint2* ll_part, int n_layers,
@@ -278,8 +281,11 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, nb = sh.nb;
   const int kq = d.kq;
-  const int r0 = kq == 4 ? blockIdx.x + G * (warp >> 2) : blockIdx.x + G * warp;
-  const int rstep = kq == 4 ? 4 * G : G * NWARP;
+  const int rpc = (d.N + G - 1) / G;
+  const int row_begin = blockIdx.x * rpc, row_end = min(d.N, row_begin + rpc);
+  const int rsub = kq == 4 ? (warp >> 2) : warp;             // row of this warp within a trip
+  const int rstep = kq == 4 ? 4 : NWARP;                      // rows per trip
+  const int r0 = row_begin + rsub;
   const int qd = kq == 4 ? (warp & 3) : 0;
   const T* W = reinterpret_cast<const T*>(d.W) + (size_t)layer * d.w_lstride + (size_t)qd * D;
   const T* B = d.B ? reinterpret_cast<const T*>(d.B) + (size_t)layer * d.b_lstride : nullptr;
@@ -290,13 +296,19 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
   uint4* slot = ring + ((size_t)((gl % RING_LAYERS) * RING_UNITS + (use_ring ? di : 0)) * NWARP + warp) * (D / 8);
   uint4 w[NCH_D];
   unsigned short braw = 0, g_raw = 0, b_raw = 0;
-  if (r0 < d.N) {
+  if (r0 < row_end) {
     if (!use_ring) {
       const uint4* src = reinterpret_cast<const uint4*>(W + (size_t)r0 * d.w_ld);
 #pragma unroll
       for (int c = 0; c < NCH_D; ++c) w[c] = ld_weight(src + c * 32 + lane);
     }
     if (B) braw = ld_raw16(B + r0);
+  }
+  if (row_begin >= d.N) {
+    // this CTA owns no row of this phase: it neither consumes the input nor produces output (nobody waits
+    // on it); it only keeps the ring's commit-group count in step
+    if (use_ring) cp_async_commit();
+    return;
   }
   const bool ln = d.gamma != nullptr && ln_layer >= 0;
   if (ln && tid < D) {
@@ -318,24 +330,19 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
   mark(p, 40 + di);
   if (use_ring) {
     cp_async_wait<RING_LAYERS * RING_UNITS - 1>();       // this unit's group has landed (each lane reads back its own chunks)
-    if (r0 < d.N) {
+    if (r0 < row_end) {
 #pragma unroll
       for (int c = 0; c < NCH_D; ++c) w[c] = slot[c * 32 + lane];
     }
   }
   // ---- dot products, epilogue, publish
   const int F = 4 * D;
-  // kq == 4: the trip count is CTA-uniform (shared-memory sync inside); kq == 1: per warp, no sync inside
-  const int trips = kq == 4 ? (d.N - (int)blockIdx.x + 4 * G - 1) / (4 * G) : (r0 < d.N ? (d.N - r0 + rstep - 1) / rstep : 0);
+  const int trips = (rpc + rstep - 1) / rstep;            // CTA-uniform (shared-memory syncs inside)
 #pragma unroll 1
   for (int j = 0; j < trips; ++j) {
     const int r = r0 + j * rstep;
-    const bool valid = r < d.N;
-#ifdef GSV_LATE_W
-    if (valid) {
-#else
+    const bool valid = r < row_end;
     if (j > 0 && valid) {
-#endif
       const uint4* src = reinterpret_cast<const uint4*>(W + (size_t)r * d.w_ld);
 #pragma unroll
       for (int c = 0; c < NCH_D; ++c) w[c] = ld_weight(src + c * 32 + lane);
@@ -372,15 +379,25 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
           float v = acc[s] + bias;
           if (d.res_add) v += d.res_add[s * D + r];
           if (d.relu) v = fmaxf(v, 0.f);
-          ll_store(d.out + (size_t)sh.sl[s] * d.out_ld + r, v, out_tag);
+          sh.outv[s][rsub] = v;
         }
       }
     }
+    __syncthreads();
+    if (warp == 0) {
+      const int rr = row_begin + j * rstep + lane;            // one coalesced store of this trip's rows per slot
+      if (lane < rstep && rr < row_end) {
+#pragma unroll
+        for (int s = 0; s < NB; ++s)
+          if (s < nb) ll_store(d.out + (size_t)sh.sl[s] * d.out_ld + rr, sh.outv[s][lane], out_tag);
+      }
+    }
+    if (j + 1 < trips) __syncthreads();
   }
   if (use_ring) {
     // same unit, RING_LAYERS layers later, into the slot just consumed (every thread commits a group,
     // valid row or not, so that wait_group counts line up)
-    if (r0 < d.N) {
+    if (r0 < row_end) {
       const int nl = (layer + RING_LAYERS) % n_layers;
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(d.W) + (size_t)nl * d.w_lstride +
                                                         (size_t)qd * D + (size_t)r0 * d.w_ld);
@@ -576,9 +593,10 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll_kernel(const GptParams p,
     for (int gl0 = 0; gl0 < RING_LAYERS; ++gl0) {
       for (int u = 0; u < RING_UNITS; ++u) {
         const GemvDesc& d = sh.desc[u];
-        const int r0 = d.kq == 4 ? cta + G * (warp >> 2) : cta + G * warp;
+        const int rpc = (d.N + G - 1) / G;
+        const int r0 = cta * rpc + (d.kq == 4 ? (warp >> 2) : warp);
         const int qd = d.kq == 4 ? (warp & 3) : 0;
-        if (r0 < d.N) {
+        if (r0 < min(d.N, cta * rpc + rpc)) {
           const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(d.W) + (size_t)(gl0 % L) * d.w_lstride +
                                                             (size_t)qd * D + (size_t)r0 * d.w_ld);
           uint4* slot = ring + ((size_t)(gl0 * RING_UNITS + u) * NWARP + warp) * (D / 8);

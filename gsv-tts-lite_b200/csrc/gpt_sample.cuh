@@ -56,13 +56,18 @@ struct SampleLL {
   unsigned tag;
   int kv_len;
 };
+// One naturally aligned 64-bit SCALAR access per word: {value (low 32 bits), tag (high 32 bits)}.  A
+// vector access (st.v2.u32 / ld.v2.u32) is modelled by the PTX memory model as two scalar accesses in
+// unspecified order, so a reader could see the new tag with the old value; a scalar b64 access is
+// single-copy atomic.
 __device__ __forceinline__ void ll_store(uint2* p, float val, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(tag) : "memory");
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(val);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ uint2 ll_peek(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return make_uint2((unsigned)(w & 0xffffffffull), (unsigned)(w >> 32));
 }
 __device__ __forceinline__ float ll_wait(const uint2* p, unsigned tag) {
   uint2 v;
