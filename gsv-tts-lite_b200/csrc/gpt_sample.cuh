@@ -268,8 +268,9 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   // bookkeeping by one thread; every value other CTAs read later goes through st.cg
   const int kvl = ll ? ll->kv_len : ld_cg(p.kv_len + slot);
   if (sp.max_new_tokens > 0 && ngen > sp.max_new_tokens) tok = p.eos;    // ngen counts s0 too
-  if (slot == 0 && p.forced != nullptr) {
+  if (slot == 0 && p.forced != nullptr) {        // CTA-uniform branch
     int fp = ld_cg(p.forced_pos);
+    __syncthreads();                              // every thread has read the cursor before thread 0 moves it
     if (fp < p.n_forced) {
       tok = p.forced[fp];
       if (tid == 0) st_cg(p.forced_pos, fp + 1);
