@@ -1,0 +1,236 @@
+// conv_umma.cuh -- Conv1d / ConvTranspose1d as an implicit GEMM on the 5th-generation tensor cores.
+//
+// (included by vocoder.cu after ConvArgs / conv_epilogue_row8)
+//
+// GEMM view of  out[t][co] = sum_k sum_ci x[t + k*dil - pad][ci] * w[k][co][ci]  (reference F.conv1d call
+// sites: models.py:114-130, modules.py:84-103, 190-203):
+//     M = 128 consecutive time steps of one batch element        (TMEM lanes)
+//     N = BN output channels                                     (TMEM columns, fp32 accumulators)
+//     K = 64 input channels of one tap per pipeline stage        (4 x tcgen05.mma M128 N(BN) K16)
+// Activations are channels-last [B][T][C], so a tap is just a ROW SHIFT of the same matrix: the A tile of tap
+// k is a TMA box at row t0 + k*dil - pad of the 3-D tensor map (C, T, B); rows outside [0, T) are zero-filled
+// by TMA, which is exactly the convolution's zero padding (and never crosses into the next batch element).
+// Weights are tap-major [k][Cout][Cin], i.e. K-major N x K tiles: B tile = TMA box (64, BN) of tap k.
+// ConvTranspose1d (models.py:120) runs in polyphase form: output phase r = (t + pad) mod s only sees the taps
+// k = r + j*s, and frame index q = (t + pad) div s, so phase r is an ordinary convolution over input frames
+// with row shift -j whose results land on the strided rows t = q*s + r - pad.  One CTA = one (M tile, N tile,
+// batch element, phase).
+//
+// Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM allocator + (lane 0) MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused conv epilogue -> global).  kStages-deep mbarrier ring.
+#pragma once
+#include <cuda.h>
+
+namespace umma {
+
+constexpr int BM = 128;          // time steps per tile
+constexpr int BK = 64;           // channels per stage: 128 bytes of 16-bit elements = one SWIZZLE_128B row
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const uint32_t a = smem_u32(bar);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], both K-major, 16-bit inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address
+// and offsets in 16-byte units, LBO unused (1), SBO = 1024 B between 8-row groups, version 1, layout type 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+template <typename T> struct UmmaFmt;
+template <> struct UmmaFmt<__half> { static constexpr uint32_t v = 0; };
+template <> struct UmmaFmt<__nv_bfloat16> { static constexpr uint32_t v = 1; };
+
+template <typename T>
+struct Params {
+  CUtensorMap tm_a;      // activations (C, Tin, B), box (64, 128, 1), SWIZZLE_128B
+  CUtensorMap tm_w;      // weights (Cin, Cout, KW), box (64, BN, 1), SWIZZLE_128B
+  int kchunks;           // ceil(Cin / 64)
+  int in_off;            // first input channel
+  int KW, n_phase;       // taps; output phases (1: convolution, s: transposed convolution with stride s)
+  int dil, pad;          // convolution: row shift of tap k is k*dil - pad
+  int t_pad;             // transposed convolution: t = q*s + r - t_pad
+  int m_ext;             // rows q in [0, m_ext) are computed
+  ConvArgs<T> ep;
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ Params<T> P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  // carve: [stages][A | B] (1024-byte aligned), then barriers
+  const uint32_t base_u = smem_u32(smem_raw);
+  uint8_t* tiles = smem_raw + ((1024u - (base_u & 1023u)) & 1023u);
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int b = blockIdx.z / P.n_phase, r = blockIdx.z - b * P.n_phase;
+  const bool transposed = P.n_phase > 1;
+  const int n_taps = transposed ? (P.KW - r + P.n_phase - 1) / P.n_phase : P.KW;
+  const int n_kb = n_taps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ----
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(&empty_bar[s], ((kb / kStages) - 1) & 1);
+        const int j = kb / P.kchunks, c = kb - j * P.kchunks;
+        const int wtap = transposed ? r + j * P.n_phase : j;
+        const int shift = transposed ? -j : j * P.dil - P.pad;
+        uint8_t* sa = tiles + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_3d(sa, &P.tm_a, &full_bar[s], P.in_off + c * BK, q0 + shift, b);
+        tma_load_3d(sa + A_BYTES, &P.tm_w, &full_bar[s], c * BK, n0, wtap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&full_bar[s], (kb / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
+        const uint64_t ad = smem_desc_sw128(sa), bd = smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+      }
+      tc_commit(&acc_bar);                 // accumulator complete
+    }
+  } else {
+    // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = rows q0 + 32*(w%4) + lane ----
+    const int quarter = warp & 3;
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const int q = q0 + quarter * 32 + lane;
+    const int t = transposed ? q * P.n_phase + r - P.t_pad : q;
+    const bool row_ok = q < P.m_ext && t >= 0 && t < P.ep.Tout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      tc_ld_wait();
+      if (row_ok) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        conv_epilogue_row8<T>(P.ep, b, t, n0 + c0, f);
+        conv_epilogue_row8<T>(P.ep, b, t, n0 + c0 + 8, f + 8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+  }
+}
+
+template <int BN> constexpr size_t smem_bytes() { return (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024; }
+
+// ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 3-D map over 16-bit elements: dims (d0, d1, d2) with byte strides (s1, s2) for dims 1 and 2; box (b0, b1, 1)
+inline int make_map(CUtensorMap* m, bool bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                    uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { gsv_set_error("cuTensorMapEncodeTiled entry point not available"); return GSV_ERR_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult rc = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
+                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    gsv_set_error("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u", (int)rc,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1,
+                  (unsigned long long)s2, b0, b1);
+    return GSV_ERR_CUDA;
+  }
+  return GSV_OK;
+}
+
+}  // namespace umma

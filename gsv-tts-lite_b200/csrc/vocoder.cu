@@ -17,11 +17,16 @@
 //     every call because flow's weight-norm is never removed, Loader.py:73,95).
 //   * xs/3 (models.py:127) and the following leaky-ReLU are applied in the epilogue of the last
 //     convolution of the third ResBlock.
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
+#include <vector>
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -80,6 +85,57 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs<T>& a, int b, int t
   if (a.mask) v *= Elem<T>::to_f(a.mask[(size_t)b * a.Tout + t]);
   if (a.out32) a.out32[o] = v;
   if (a.outT) a.outT[o] = Elem<T>::from_f(act_apply(v, a.act));
+}
+
+// the same epilogue for 8 consecutive output channels [co, co+8) of one row, vectorised when the output
+// channel map is not reversed (co multiple of 8; every pointer 16-byte aligned at such a channel)
+template <typename T>
+__device__ __forceinline__ void conv_epilogue_row8(const ConvArgs<T>& a, int b, int t, int co, const float* acc) {
+  if (a.o_rev) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) conv_epilogue<T>(a, b, t, co + j, acc[j]);
+    return;
+  }
+  float v[8], tmp[8];
+  unpack8<T>(*reinterpret_cast<const uint4*>(a.bias + co), tmp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = acc[j] + tmp[j];
+  if (a.add) {
+    const float* ap = a.add + ((size_t)b * a.add_tg + (a.add_tg > 1 ? t : 0)) * a.add_ld + co;
+    const float4 x = *reinterpret_cast<const float4*>(ap), y = *reinterpret_cast<const float4*>(ap + 4);
+    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+  }
+  const size_t o = ((size_t)b * a.Tout + t) * a.o_ld + a.o_off + co;
+  if (a.res32) {
+    const float4 x = *reinterpret_cast<const float4*>(a.res32 + o), y = *reinterpret_cast<const float4*>(a.res32 + o + 4);
+    const float rr[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = rr[j] + a.res_sign * v[j];
+  }
+  if (a.acc32) {
+    if (!a.acc_init) {
+      const float4 x = *reinterpret_cast<const float4*>(a.acc32 + o), y = *reinterpret_cast<const float4*>(a.acc32 + o + 4);
+      v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+    }
+    *reinterpret_cast<float4*>(a.acc32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(a.acc32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= a.acc_scale;
+  }
+  if (a.mask) {
+    const float m = Elem<T>::to_f(a.mask[(size_t)b * a.Tout + t]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= m;
+  }
+  if (a.out32) {
+    *reinterpret_cast<float4*>(a.out32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(a.out32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (a.outT) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
+    *reinterpret_cast<uint4*>(a.outT + o) = pack8<T>(v);
+  }
 }
 
 // load 8 consecutive logical input channels [c, c+8) of row (b, t) as floats (zero outside [0,Tin))
@@ -309,9 +365,20 @@ __global__ void to_channel_major_kernel(const float* __restrict__ in32, T* __res
   }
 }
 
+#include "conv_umma.cuh"
+
 struct Weight {
   const void* w;
   const void* b;
+};
+
+// one cached pair of tensor maps per convolution call site of a flow_dec pass (re-encoded when the signature changes)
+struct MapCacheEntry {
+  const void *in, *w;
+  int in_ld, Tin, B, Cin, Cout, KW, bn;
+  long long w_tap;
+  alignas(64) CUtensorMap tm_a;
+  alignas(64) CUtensorMap tm_w;
 };
 
 }  // namespace
@@ -324,15 +391,85 @@ struct gsv_voc_ctx {
   void* zero_bias;       // conv layers without bias
   void* debug_z;
   long long launches;
+  std::vector<MapCacheEntry> map_cache;   // indexed by call site order within one flow_dec pass
+  size_t op_index;
+  int use_umma;                           // GSV_VOC_IMPL=cuda disables the tensor-core path (A/B checks)
+  int num_sms;
 };
 
 namespace {
+
+// ---- tensor-core path (conv_umma.cuh) ---------------------------------------------------------------------
+template <typename T>
+bool umma_eligible(const ConvArgs<T>& a) {
+  return !a.in_rev && a.Cin >= 64 && a.Cin % 8 == 0 && a.in_ld % 8 == 0 && a.Cout % 32 == 0 && a.KW <= 16 &&
+         (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && (a.w_tap % 8) == 0;
+}
+
+template <typename T, int BN>
+int launch_umma_bn(const umma::Params<T>& P, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)umma::smem_bytes<BN>()));
+    attr_set = true;
+  }
+  umma::conv_umma_kernel<T, BN><<<grid, umma::kThreads, umma::smem_bytes<BN>(), st>>>(P);
+  return GSV_OK;
+}
+
+template <typename T>
+int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStream_t st) {
+  const bool transposed = a.stride > 1;
+  const int n_phase = transposed ? a.stride : 1;
+  const int m_ext = transposed ? a.Tin + (a.KW - 1) / a.stride + 1 : a.Tout;
+  const int mt = (m_ext + umma::BM - 1) / umma::BM;
+  // N tile: as wide as divides Cout, narrowed while the grid would leave most SMs idle
+  int bn = a.Cout % 128 == 0 ? 128 : (a.Cout % 64 == 0 ? 64 : 32);
+  while (bn > 32 && (long long)mt * (a.Cout / bn) * a.B * n_phase < ctx->num_sms) bn >>= 1;
+  if (op >= ctx->map_cache.size()) ctx->map_cache.resize(op + 1);
+  MapCacheEntry& e = ctx->map_cache[op];
+  if (e.in != a.in || e.w != a.w || e.in_ld != a.in_ld || e.Tin != a.Tin || e.B != a.B || e.Cin != a.Cin || e.Cout != a.Cout ||
+      e.KW != a.KW || e.bn != bn || e.w_tap != a.w_tap) {
+    const bool bf16 = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value;
+    int rc = umma::make_map(&e.tm_a, bf16, a.in, (uint64_t)a.in_ld, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.in_ld * 2,
+                            (uint64_t)a.Tin * a.in_ld * 2, umma::BK, umma::BM);
+    if (rc) return rc;
+    rc = umma::make_map(&e.tm_w, bf16, a.w, (uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)a.KW, (uint64_t)a.Cin * 2,
+                        (uint64_t)a.w_tap * 2, umma::BK, (uint32_t)bn);
+    if (rc) return rc;
+    e.in = a.in; e.w = a.w; e.in_ld = a.in_ld; e.Tin = a.Tin; e.B = a.B; e.Cin = a.Cin; e.Cout = a.Cout; e.KW = a.KW;
+    e.bn = bn; e.w_tap = a.w_tap;
+  }
+  umma::Params<T> P;
+  P.tm_a = e.tm_a; P.tm_w = e.tm_w;
+  P.kchunks = (a.Cin + umma::BK - 1) / umma::BK;
+  P.in_off = a.in_off;
+  P.KW = a.KW; P.n_phase = n_phase;
+  P.dil = a.dil; P.pad = (a.KW - 1) * a.dil / 2;
+  P.t_pad = transposed ? (a.KW - a.stride) / 2 : 0;
+  P.m_ext = m_ext;
+  P.ep = a;
+  const dim3 grid(mt, a.Cout / bn, a.B * n_phase);
+  int rc;
+  if (bn == 128) rc = launch_umma_bn<T, 128>(P, grid, st);
+  else if (bn == 64) rc = launch_umma_bn<T, 64>(P, grid, st);
+  else rc = launch_umma_bn<T, 32>(P, grid, st);
+  if (rc) return rc;
+  ctx->launches += 1;
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
 
 template <typename T>
 int launch_conv(gsv_voc_ctx* ctx, const ConvArgs<T>& a, cudaStream_t st) {
   if (a.Cin % 8 != 0 || a.in_off % 8 != 0 || a.in_ld % 8 != 0) {
     gsv_set_error("conv: channel counts must be multiples of 8 (Cin=%d off=%d ld=%d)", a.Cin, a.in_off, a.in_ld);
     return GSV_ERR_ARG;
+  }
+  {
+    const size_t op = ctx->op_index++;
+    if (ctx->use_umma && umma_eligible<T>(a)) return launch_conv_umma<T>(ctx, a, op, st);
   }
   if (a.stride == 1) {
     if ((a.KW - 1) * a.dil > 64) { gsv_set_error("conv: halo too large"); return GSV_ERR_ARG; }
@@ -437,6 +574,7 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
   carve(ar);
 
   int rc;
+  ctx->op_index = 0;
   const dim3 tb(32, 8);
   // ---- boundary transposes ------------------------------------------------------------------------------
   to_time_major_kernel<T><<<dim3((Tn + 31) / 32, (C + 31) / 32, B), tb, 0, st>>>(z_p, z32, zT, C, Tn);
@@ -633,6 +771,12 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
   GSV_ARG(ctx != nullptr);
   ctx->dims = *dims;
   ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->debug_z = nullptr; ctx->launches = 0;
+  ctx->op_index = 0;
+  {
+    const char* e = getenv("GSV_VOC_IMPL");
+    ctx->use_umma = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
+  }
+  GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
   GSV_CUDA(cudaMalloc(&ctx->zero_bias, 8192));
   GSV_CUDA(cudaMemset(ctx->zero_bias, 0, 8192));
   *out = ctx;
