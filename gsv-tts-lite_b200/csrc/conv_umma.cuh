@@ -6,27 +6,34 @@
 // sites: models.py:114-130, modules.py:84-103, 190-203):
 //     M = 128 consecutive time steps of one batch element        (TMEM lanes)
 //     N = BN output channels                                     (TMEM columns, fp32 accumulators)
-//     K = 64 input channels of one tap per pipeline stage        (4 x tcgen05.mma M128 N(BN) K16)
-// Activations are channels-last [B][T][C], so a tap is just a ROW SHIFT of the same matrix: the A tile of tap
-// k is a TMA box at row t0 + k*dil - pad of the 3-D tensor map (C, T, B); rows outside [0, T) are zero-filled
-// by TMA, which is exactly the convolution's zero padding (and never crosses into the next batch element).
-// Weights are tap-major [k][Cout][Cin], i.e. K-major N x K tiles: B tile = TMA box (64, BN) of tap k.
+//     K = BK (64/32/16) input channels of one tap per MMA group  (BK/16 x tcgen05.mma M128 N(BN) K16)
+// Activations are channels-last [B][T][C], so a tap is just a ROW SHIFT of the same matrix.  Per BK-channel
+// chunk ONE TMA box of 128 + halo rows starting at row t0 - pad of the 3-D tensor map (C, T, B) is loaded
+// (rows outside [0, T) are zero-filled by TMA = the convolution's zero padding, and a box never crosses into
+// the next batch element); tap k reads it through a shared-memory descriptor whose start address is advanced
+// by k*dil rows -- the 128/64/32-byte swizzle is a function of the shared-memory address, so a row-shifted
+// view of a swizzled tile is still a valid K-major operand (verified on B200 against the oracle).  A bytes per
+// tile therefore do not scale with the kernel width.
+// Weights are tap-major [k][Cout][Cin], i.e. K-major N x K tiles: B tile = TMA box (BK, BN) of tap k, streamed
+// through its own, deeper ring.
 // ConvTranspose1d (models.py:120) runs in polyphase form: output phase r = (t + pad) mod s only sees the taps
 // k = r + j*s, and frame index q = (t + pad) div s, so phase r is an ordinary convolution over input frames
 // with row shift -j whose results land on the strided rows t = q*s + r - pad.  One CTA = one (M tile, N tile,
 // batch element, phase).
 //
 // Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 = TMEM allocator + (lane 0) MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused conv epilogue -> global).  kStages-deep mbarrier ring.
+// warps 2..5 = epilogue (TMEM -> registers -> fused conv epilogue -> global).  Two mbarrier rings: activation
+// chunks (sa stages) and weight taps (sw stages).
 #pragma once
 #include <cuda.h>
 
 namespace umma {
 
 constexpr int BM = 128;          // time steps per tile
-constexpr int BK = 64;           // channels per stage: 128 bytes of 16-bit elements = one SWIZZLE_128B row
-constexpr int kStages = 4;
+constexpr int kMaxSA = 4;        // activation ring depth (upper bound)
+constexpr int kMaxSW = 12;       // weight ring depth (upper bound)
 constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -47,10 +54,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         : "=r"(done) : "r"(a), "r"(parity) : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -74,11 +81,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address
-// and offsets in 16-byte units, LBO unused (1), SBO = 1024 B between 8-row groups, version 1, layout type 2.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address and
+// offsets in 16-byte units, LBO unused (1), SBO = 8 rows, version 1, layout type 2 / 4 / 6 = 128 / 64 / 32-byte
+// swizzle (row length BK * 2 bytes = swizzle span).
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+  constexpr uint32_t row_bytes = BK * 2;
+  constexpr uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t hi = ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
   return ((uint64_t)hi << 32) | lo;
 }
 
@@ -88,43 +99,50 @@ template <> struct UmmaFmt<__nv_bfloat16> { static constexpr uint32_t v = 1; };
 
 template <typename T>
 struct Params {
-  CUtensorMap tm_a;      // activations (C, Tin, B), box (64, 128, 1), SWIZZLE_128B
-  CUtensorMap tm_w;      // weights (Cin, Cout, KW), box (64, BN, 1), SWIZZLE_128B
-  int kchunks;           // ceil(Cin / 64)
+  CUtensorMap tm_a;      // activations (C, Tin, B), box (BK, a_rows, 1)
+  CUtensorMap tm_w;      // weights (Cin, Cout, KW), box (BK, BN, 1)
+  int kchunks;           // ceil(Cin / BK)
   int in_off;            // first input channel
   int KW, n_phase;       // taps; output phases (1: convolution, s: transposed convolution with stride s)
   int dil, pad;          // convolution: row shift of tap k is k*dil - pad
   int t_pad;             // transposed convolution: t = q*s + r - t_pad
   int m_ext;             // rows q in [0, m_ext) are computed
+  int a_rows;            // rows of the activation box = 128 + halo
+  int a_stage_bytes;     // a_rows * BK * 2 rounded up to 1024
+  int sa, sw;            // ring depths
   ConvArgs<T> ep;
 };
 
-template <typename T, int BN>
+template <typename T, int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ Params<T> P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  // carve: [stages][A | B] (1024-byte aligned), then barriers
-  const uint32_t base_u = smem_u32(smem_raw);
-  uint8_t* tiles = smem_raw + ((1024u - (base_u & 1023u)) & 1023u);
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_bar;
+  constexpr int ROW_BYTES = BK * 2, W_BYTES = BN * ROW_BYTES;
+  constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], w_full[kMaxSW], w_empty[kMaxSW], acc_bar;
   __shared__ uint32_t tmem_base_s;
+  // carve (1024-byte aligned): [sa][A stage] | [sw][W stage]
+  const uint32_t base_u = smem_u32(smem_raw);
+  const uint32_t tiles_a = base_u + ((1024u - (base_u & 1023u)) & 1023u);
+  const uint32_t tiles_w = tiles_a + (uint32_t)(P.sa * P.a_stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int b = blockIdx.z / P.n_phase, r = blockIdx.z - b * P.n_phase;
   const bool transposed = P.n_phase > 1;
   const int n_taps = transposed ? (P.KW - r + P.n_phase - 1) / P.n_phase : P.KW;
-  const int n_kb = n_taps * P.kchunks;
+  const int SA = P.sa, SW = P.sw;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -134,17 +152,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- TMA producer ----
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(&empty_bar[s], ((kb / kStages) - 1) & 1);
-        const int j = kb / P.kchunks, c = kb - j * P.kchunks;
-        const int wtap = transposed ? r + j * P.n_phase : j;
-        const int shift = transposed ? -j : j * P.dil - P.pad;
-        uint8_t* sa = tiles + s * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_3d(sa, &P.tm_a, &full_bar[s], P.in_off + c * BK, q0 + shift, b);
-        tma_load_3d(sa + A_BYTES, &P.tm_w, &full_bar[s], c * BK, n0, wtap);
+      // ---- TMA producer: per channel chunk one activation box (with halo), then one weight box per tap ----
+      const int row0 = q0 - (transposed ? n_taps - 1 : P.pad);
+      int i = 0;
+      for (int c = 0; c < P.kchunks; ++c) {
+        const int s = c % SA;
+        if (c >= SA) mbar_wait(&a_empty[s], ((c / SA) - 1) & 1);
+        mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
+        tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, row0, b);
+        for (int j = 0; j < n_taps; ++j, ++i) {
+          const int w = i % SW;
+          if (i >= SW) mbar_wait(&w_empty[w], ((i / SW) - 1) & 1);
+          mbar_expect_tx(&w_full[w], W_BYTES);
+          tma_load_3d(tiles_w + (uint32_t)(w * W_STAGE), &P.tm_w, &w_full[w], c * BK, n0, transposed ? r + j * P.n_phase : j);
+        }
       }
     }
   } else if (warp == 1) {
@@ -152,16 +173,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       // ---- MMA issuer ----
       constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < n_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(&full_bar[s], (kb / kStages) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES);
-        const uint64_t ad = smem_desc_sw128(sa), bd = smem_desc_sw128(sa + A_BYTES);
+      int i = 0;
+      for (int c = 0; c < P.kchunks; ++c) {
+        const int s = c % SA;
+        mbar_wait(&a_full[s], (c / SA) & 1);
+        const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
+        for (int j = 0; j < n_taps; ++j, ++i) {
+          const int w = i % SW;
+          mbar_wait(&w_full[w], (i / SW) & 1);
+          tc_fence_after();
+          const int row_off = transposed ? n_taps - 1 - j : j * P.dil;
+          const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(row_off * ROW_BYTES));
+          const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)(w * W_STAGE));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&w_empty[w]);          // frees the weight slot when these MMAs have read it
+        }
+        tc_commit(&a_empty[s]);            // all taps of this chunk issued: frees the activation slot
       }
       tc_commit(&acc_bar);                 // accumulator complete
     }
@@ -191,11 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
   }
 }
-
-template <int BN> constexpr size_t smem_bytes() { return (size_t)kStages * (BM * BK * 2 + BN * BK * 2) + 1024; }
 
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -215,6 +242,7 @@ inline EncodeTiledFn encode_fn() {
 // 3-D map over 16-bit elements: dims (d0, d1, d2) with byte strides (s1, s2) for dims 1 and 2; box (b0, b1, 1)
 inline int make_map(CUtensorMap* m, bool bf16, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
                     uint32_t b0, uint32_t b1) {
+  const CUtensorMapSwizzle swz = b0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (b0 == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   EncodeTiledFn fn = encode_fn();
   if (!fn) { gsv_set_error("cuTensorMapEncodeTiled entry point not available"); return GSV_ERR_CUDA; }
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -222,7 +250,7 @@ inline int make_map(CUtensorMap* m, bool bf16, const void* base, uint64_t d0, ui
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult rc = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims,
-                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     gsv_set_error("cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu strides %llu,%llu box %u,%u", (int)rc,

@@ -375,7 +375,7 @@ struct Weight {
 // one cached pair of tensor maps per convolution call site of a flow_dec pass (re-encoded when the signature changes)
 struct MapCacheEntry {
   const void *in, *w;
-  int in_ld, Tin, B, Cin, Cout, KW, bn;
+  int in_ld, Tin, B, Cin, Cout, KW, bn, a_rows;
   long long w_tap;
   alignas(64) CUtensorMap tm_a;
   alignas(64) CUtensorMap tm_w;
@@ -402,19 +402,20 @@ namespace {
 // ---- tensor-core path (conv_umma.cuh) ---------------------------------------------------------------------
 template <typename T>
 bool umma_eligible(const ConvArgs<T>& a) {
-  return !a.in_rev && a.Cin >= 64 && a.Cin % 8 == 0 && a.in_ld % 8 == 0 && a.Cout % 32 == 0 && a.KW <= 16 &&
+  return !a.in_rev && a.Cin >= 16 && a.Cin % 8 == 0 && a.in_ld % 8 == 0 && a.Cout % 16 == 0 && a.KW <= 16 &&
+         (a.Cin >= 64 || a.Cin == 32 || a.Cin == 16) && (a.KW - 1) * a.dil <= 120 &&
          (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.w) & 15) == 0 && (a.w_tap % 8) == 0;
 }
 
-template <typename T, int BN>
-int launch_umma_bn(const umma::Params<T>& P, dim3 grid, cudaStream_t st) {
+template <typename T, int BN, int BK>
+int launch_umma_inst(const umma::Params<T>& P, dim3 grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)umma::smem_bytes<BN>()));
+    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_kernel<T, BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  umma::kSmemBudget + 2048));
     attr_set = true;
   }
-  umma::conv_umma_kernel<T, BN><<<grid, umma::kThreads, umma::smem_bytes<BN>(), st>>>(P);
+  umma::conv_umma_kernel<T, BN, BK><<<grid, umma::kThreads, smem, st>>>(P);
   return GSV_OK;
 }
 
@@ -422,39 +423,64 @@ template <typename T>
 int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStream_t st) {
   const bool transposed = a.stride > 1;
   const int n_phase = transposed ? a.stride : 1;
+  const int max_taps = transposed ? (a.KW + a.stride - 1) / a.stride : a.KW;
+  const int halo = transposed ? max_taps - 1 : (a.KW - 1) * a.dil;
   const int m_ext = transposed ? a.Tin + (a.KW - 1) / a.stride + 1 : a.Tout;
   const int mt = (m_ext + umma::BM - 1) / umma::BM;
+  const int bk = a.Cin >= 64 ? 64 : a.Cin;                 // 64 / 32 / 16 channels per chunk
   // N tile: as wide as divides Cout, narrowed while the grid would leave most SMs idle
-  int bn = a.Cout % 128 == 0 ? 128 : (a.Cout % 64 == 0 ? 64 : 32);
-  while (bn > 32 && (long long)mt * (a.Cout / bn) * a.B * n_phase < ctx->num_sms) bn >>= 1;
+  int bn = a.Cout % 128 == 0 ? 128 : (a.Cout % 64 == 0 ? 64 : (a.Cout % 32 == 0 ? 32 : 16));
+  const int bn_min = bk == 64 ? 32 : 16;
+  while (bn > bn_min && (long long)mt * (a.Cout / bn) * a.B * n_phase < ctx->num_sms) bn >>= 1;
+  if (bk == 32 && bn > 32) bn = 32;
+  if (bk == 16) bn = 16;
+  if (a.Cout % bn != 0) { gsv_set_error("conv: Cout=%d not a multiple of the N tile %d", a.Cout, bn); return GSV_ERR_ARG; }
+  const int a_rows = umma::BM + halo;
   if (op >= ctx->map_cache.size()) ctx->map_cache.resize(op + 1);
   MapCacheEntry& e = ctx->map_cache[op];
   if (e.in != a.in || e.w != a.w || e.in_ld != a.in_ld || e.Tin != a.Tin || e.B != a.B || e.Cin != a.Cin || e.Cout != a.Cout ||
-      e.KW != a.KW || e.bn != bn || e.w_tap != a.w_tap) {
-    const bool bf16 = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value;
+      e.KW != a.KW || e.bn != bn || e.w_tap != a.w_tap || e.a_rows != a_rows) {
+    const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
     int rc = umma::make_map(&e.tm_a, bf16, a.in, (uint64_t)a.in_ld, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.in_ld * 2,
-                            (uint64_t)a.Tin * a.in_ld * 2, umma::BK, umma::BM);
+                            (uint64_t)a.Tin * a.in_ld * 2, (uint32_t)bk, (uint32_t)a_rows);
     if (rc) return rc;
     rc = umma::make_map(&e.tm_w, bf16, a.w, (uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)a.KW, (uint64_t)a.Cin * 2,
-                        (uint64_t)a.w_tap * 2, umma::BK, (uint32_t)bn);
+                        (uint64_t)a.w_tap * 2, (uint32_t)bk, (uint32_t)bn);
     if (rc) return rc;
     e.in = a.in; e.w = a.w; e.in_ld = a.in_ld; e.Tin = a.Tin; e.B = a.B; e.Cin = a.Cin; e.Cout = a.Cout; e.KW = a.KW;
-    e.bn = bn; e.w_tap = a.w_tap;
+    e.bn = bn; e.w_tap = a.w_tap; e.a_rows = a_rows;
   }
   umma::Params<T> P;
   P.tm_a = e.tm_a; P.tm_w = e.tm_w;
-  P.kchunks = (a.Cin + umma::BK - 1) / umma::BK;
+  P.kchunks = (a.Cin + bk - 1) / bk;
   P.in_off = a.in_off;
   P.KW = a.KW; P.n_phase = n_phase;
   P.dil = a.dil; P.pad = (a.KW - 1) * a.dil / 2;
   P.t_pad = transposed ? (a.KW - a.stride) / 2 : 0;
   P.m_ext = m_ext;
+  P.a_rows = a_rows;
+  P.a_stage_bytes = (a_rows * bk * 2 + 1023) & ~1023;
+  const int w_stage = (bn * bk * 2 + 1023) & ~1023;
+  P.sa = P.kchunks < 3 ? P.kchunks : 3;
+  int sw = (umma::kSmemBudget - P.sa * P.a_stage_bytes) / w_stage;
+  const int n_w = P.kchunks * max_taps;
+  sw = sw > umma::kMaxSW ? umma::kMaxSW : sw;
+  P.sw = sw > n_w ? n_w : sw;
   P.ep = a;
+  const size_t smem = (size_t)P.sa * P.a_stage_bytes + (size_t)P.sw * w_stage + 1024;
   const dim3 grid(mt, a.Cout / bn, a.B * n_phase);
-  int rc;
-  if (bn == 128) rc = launch_umma_bn<T, 128>(P, grid, st);
-  else if (bn == 64) rc = launch_umma_bn<T, 64>(P, grid, st);
-  else rc = launch_umma_bn<T, 32>(P, grid, st);
+  int rc = GSV_ERR_ARG;
+  if (bk == 64) {
+    if (bn == 128) rc = launch_umma_inst<T, 128, 64>(P, grid, smem, st);
+    else if (bn == 64) rc = launch_umma_inst<T, 64, 64>(P, grid, smem, st);
+    else if (bn == 32) rc = launch_umma_inst<T, 32, 64>(P, grid, smem, st);
+    else rc = launch_umma_inst<T, 16, 64>(P, grid, smem, st);
+  } else if (bk == 32) {
+    if (bn == 32) rc = launch_umma_inst<T, 32, 32>(P, grid, smem, st);
+    else rc = launch_umma_inst<T, 16, 32>(P, grid, smem, st);
+  } else {
+    rc = launch_umma_inst<T, 16, 16>(P, grid, smem, st);
+  }
   if (rc) return rc;
   ctx->launches += 1;
   GSV_CHECK_LAUNCH();
