@@ -100,6 +100,8 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   {
     const char* e = getenv("GSV_DECODE_IMPL");
     ctx->force_barrier_kernel = (e && strcmp(e, "barrier") == 0) ? 1 : 0;
+    ctx->force_ll1 = (e && strcmp(e, "ll1") == 0) ? 1 : 0;
+    ctx->force_ll2 = (e && strcmp(e, "ll2") == 0) ? 1 : 0;
   }
   if ((rc = gsv_gpt_decode_configure(ctx))) { gsv_gpt_destroy(ctx); return rc; }
   *out = ctx;
@@ -134,6 +136,10 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   for (int i = 0; i < ctx->p.slots; ++i) live += ctx->slot_live[i];
   if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
   // 1..4 live sequences: latency-optimised flag-in-data kernel; otherwise the barrier kernel
+  // measured on B200 (tools/decode_speed.py, bf16, kv 164..289): 1 live sequence 299 us/token (ll) vs 317 (ll2);
+  // 2 live 381 vs 375; 4 live 595 vs 560 -> ll2 from two live sequences up, ll for one (GSV_DECODE_IMPL overrides)
+  if (!ctx->force_barrier_kernel && !ctx->force_ll1 && (live >= 2 || ctx->force_ll2) && gsv_gpt_ll2_supported(ctx, live, n_steps))
+    return gsv_gpt_decode_ll2_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (!ctx->force_barrier_kernel && gsv_gpt_ll_supported(ctx, live, n_steps))
     return gsv_gpt_decode_ll_launch(ctx, live, n_steps, (cudaStream_t)stream);
   return gsv_gpt_decode_launch(ctx, n_steps, (cudaStream_t)stream);

@@ -137,6 +137,7 @@ struct LLShared {
   float wscale[NWARP];
   float outv[MAXB][NWARP];                 // this trip's outputs, gathered for one coalesced LL store
   GemvDesc desc[5];        // 0 QKV, 1 out-proj, 2 MLP up, 3 MLP down, 4 head
+  const GptParams* pp;     // timeline builds only
 };
 
 // ---- staging (shared by all GEMV phases) ----------------------------------------------------------------
@@ -155,6 +156,10 @@ __device__ __forceinline__ void stage_input(const GemvDesc& d, const uint2* in, 
       v[s] = 0.f;
       if (s < nb && mine) v[s] = ll_wait(in + (size_t)sh.sl[s] * D + tid, tag);
     }
+#ifdef GSV_TIMELINE
+    __syncthreads();
+    mark(*sh.pp, 50);
+#endif
     if (ln) {
       // one pass: sum and sum of squares, reduced by all warps (values are O(1), D <= 512: E[v^2]-mean^2
       // in fp32 is accurate to ~1e-6 relative)
@@ -379,6 +384,7 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
 #pragma unroll
       for (int s = 0; s < NB; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
     }
+    mark(p, 60 + di);
     if (kq == 4) {
       if (lane == 0) {
 #pragma unroll
@@ -414,6 +420,7 @@ __device__ __noinline__ void gemv_phase(const GptParams& p, int di, int layer, i
     }
     if (j + 1 < trips) __syncthreads();
   }
+  mark(p, 70 + di);
   if (use_ring) {
     // same unit, RING_LAYERS layers later, into the slot just consumed (every thread commits a group,
     // valid row or not, so that wait_group counts line up)
@@ -600,6 +607,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll_kernel(const GptParams p,
 
   // ---- launch prologue: descriptor table, active slots, xin republished in LL form ----
   if (tid == 0) {
+    sh.pp = &p;
     GemvDesc* d = sh.desc;
     d[0] = GemvDesc{p.w_qkv, (long long)3 * D * D, D, p.b_qkv, 3 * D, 3 * D, 1, 0, ll_y2, p.ln2_g, p.ln2_b, xres, nullptr, 0, ll_qkv, 3 * D};
     d[1] = GemvDesc{p.w_o, (long long)D * D, D, p.b_o, D, D, 1, 1, nullptr, nullptr, nullptr, nullptr, xres, 0, ll_y1, D};

@@ -64,6 +64,8 @@ struct gsv_gpt_ctx {
   unsigned long long ll_seq;
   int slot_live[GSV_MAX_SLOTS];   // host-side view: prefilled and not yet released
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
+  int force_ll1;                  // GSV_DECODE_IMPL=ll1: first-generation small-batch kernel (A/B checks)
+  int force_ll2;                  // GSV_DECODE_IMPL=ll2: second-generation kernel also for a single live sequence
 };
 
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
@@ -74,3 +76,5 @@ int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);
 size_t gsv_gpt_ll_buffer_bytes(const gsv_gpt_ctx* ctx);
 bool gsv_gpt_ll_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
 int gsv_gpt_decode_ll_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
+bool gsv_gpt_ll2_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
+int gsv_gpt_decode_ll2_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);

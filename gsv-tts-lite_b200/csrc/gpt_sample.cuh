@@ -195,31 +195,59 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
     __syncthreads();
   }
 
-  // (4) top-k pivot = k-th largest value with multiplicity (utils.py:43-46); ties with the pivot survive
+  // (4) top-k pivot = k-th largest value with multiplicity (utils.py:43-46); ties with the pivot survive.
+  //     Exact radix select on an order-preserving integer image of the floats: 4 passes of 8 bits, each a
+  //     256-bin block histogram (instead of k rounds of block arg-max).
   if (sp.top_k > 0) {
-    const int k = min(sp.top_k, Vv);
+    int k = min(sp.top_k, Vv);
     constexpr int PER = GSV_VOCAB_MAX / GSV_DECODE_THREADS;   // blockDim.x == GSV_DECODE_THREADS
-    float cur[PER];
+    unsigned key[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-      int v = tid + i * NT;
-      cur[i] = v < Vv ? lg[v] : GSV_NEG_INF;
+      const int v = tid + i * NT;
+      const unsigned u = __float_as_uint(v < Vv ? lg[v] : GSV_NEG_INF);
+      key[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);    // larger float <=> larger key
     }
-    float pivot = GSV_NEG_INF;
-    for (int r = 0; r < k; ++r) {
-      ArgMax a;
-      a.v = GSV_NEG_INF; a.i = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        ArgMax b; b.v = cur[i]; b.i = tid + i * NT;
-        a = amax2(a, b);
-      }
-      a = block_argmax(a, red_v, red_i);
-      pivot = a.v;
+    unsigned* hist = reinterpret_cast<unsigned*>(kbuf);       // [256] (kbuf is only used by top-p, which is done)
+    unsigned* sel = hist + 256;                               // [2]: chosen bin, remaining rank
+    unsigned prefix = 0u, pmask = 0u;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (tid < 256) hist[tid] = 0u;
+      __syncthreads();
 #pragma unroll
       for (int i = 0; i < PER; ++i)
-        if (tid + i * NT == a.i) cur[i] = GSV_NEG_INF;    // remove exactly one instance
+        if (tid + i * NT < Vv && (key[i] & pmask) == prefix) atomicAdd(&hist[(key[i] >> shift) & 255u], 1u);
+      __syncthreads();
+      if (tid < 32) {
+        // lane owns bins [8*lane, 8*lane+8); walk from the top bin down until the rank falls inside a bin
+        unsigned c[8], tot = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[tid * 8 + j]; tot += c[j]; }
+        // inclusive suffix sum of tot over lanes: entries in this lane's bins and every higher bin
+        unsigned suf = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned n = __shfl_down_sync(0xffffffffu, suf, o);
+          if (tid + o < 32) suf += n;
+        }
+        const unsigned above = suf - tot;                     // entries in bins above this lane's
+        if ((unsigned)k > above && (unsigned)k <= above + tot) {
+          unsigned run = above;
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            if ((unsigned)k > run && (unsigned)k <= run + c[j]) { sel[0] = (unsigned)(tid * 8 + j); sel[1] = (unsigned)k - run; }
+            run += c[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix |= sel[0] << shift;
+      pmask |= 255u << shift;
+      k = (int)sel[1];
     }
+    const unsigned pk = prefix;                               // key of the k-th largest value
+    const float pivot = __uint_as_float((pk & 0x80000000u) ? (pk & 0x7fffffffu) : ~pk);
     for (int v = tid; v < Vv; v += NT)
       if (lg[v] < pivot) lg[v] = GSV_NEG_INF;
     __syncthreads();
