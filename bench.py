@@ -174,11 +174,12 @@ def main():
     model = syn.SOVITS_MODEL["v2Pro"]
     vsd = syn.sovits_flow_dec_state_dict(model, 0)
     if world > 1:
-        for sd in (gsd, vsd):
-            for k in sorted(sd):
-                t = sd[k].to(dev) if rank == 0 else torch.empty_like(sd[k], device=dev)
-                dist.broadcast(t, 0)
-                sd[k] = t.cpu()
+        from gsv_tts import _shard
+        if rank != 0:       # only rank 0's copy counts: the others start from garbage and receive the broadcast
+            gsd = {k: torch.empty_like(v) for k, v in gsd.items()}
+            vsd = {k: torch.empty_like(v) for k, v in vsd.items()}
+        gsd = _shard.broadcast_state_dict(gsd, 0, dev)
+        vsd = _shard.broadcast_state_dict(vsd, 0, dev)
     gpt = Text2SemanticDecoder(syn.GPT_CONFIG)
     gpt.load_state_dict(gsd)
     gpt.initialize_runtime(dtype, dev, [(1, 512)])
@@ -270,14 +271,14 @@ def main():
     value = tokens / (ms_total / 1e3)
     e2e_value = tokens / (ms_e2e / 1e3)
     audio_s = N_TOK * 0.04
-    # ---- roofline of the dominant kernel: gpt_decode_kernel (HBM bound; DESIGN.md "roofline") ----
+    # ---- roofline of the dominant kernel: the small-batch persistent decode kernel (HBM bound) ----
     pk, pk_kind = peaks()
     w_bytes = (24 * (12 * 512 * 512 + 13 * 512) + 1025 * 512) * 2
     kv_mean = NX + NY + (N_TOK + 1) / 2.0
     bytes_per_token = w_bytes + 49152 * kv_mean                 # weights once + 49 152 B per live position
     mean_launch_ms = sum(decode_launch_ms) / len(decode_launch_ms)
     achieved = bytes_per_token * CHUNK / (mean_launch_ms / 1e3) / 1e9
-    roofline = {"kernel": "gpt_decode_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+    roofline = {"kernel": "gpt_decode_ll_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
                 "bytes_per_launch": bytes_per_token * CHUNK, "launch_ms": mean_launch_ms,
                 "decode_only_tok_s": CHUNK / (mean_launch_ms / 1e3)}
