@@ -278,8 +278,15 @@ def main():
     bytes_per_token = w_bytes + 49152 * kv_mean                 # weights once + 49 152 B per live position
     mean_launch_ms = sum(decode_launch_ms) / len(decode_launch_ms)
     achieved = bytes_per_token * CHUNK / (mean_launch_ms / 1e3) / 1e9
+    traffic = None      # dram bytes per launch of the same kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_decode_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * CHUNK / tj["tokens_per_launch"]
+    except Exception:
+        pass
     roofline = {"kernel": "gpt_decode_ll_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                 "bytes_per_launch": bytes_per_token * CHUNK, "launch_ms": mean_launch_ms,
                 "decode_only_tok_s": CHUNK / (mean_launch_ms / 1e3)}
 

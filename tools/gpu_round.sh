@@ -5,7 +5,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/benc
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-300
-ncu --set full --clock-control none --import-source on -k regex:gpt_decode_kernel -s 2 -c 2 -o gpurun_out/prof_decode -f \
+ncu --set full --clock-control none --import-source on -k regex:gpt_decode_ll -s 2 -c 1 -o gpurun_out/prof_decode -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-300
 ls -la gpurun_out
