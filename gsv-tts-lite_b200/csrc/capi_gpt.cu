@@ -96,12 +96,21 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(ctx->pf_h, S * F * 2, false);
   A(ctx->pf_tmp, S * d * 2, false);
   A(ctx->ll_buf, gsv_gpt_ll_buffer_bytes(ctx), true);
+  A(ctx->dx, B * d * 2, true);
+  A(ctx->dqkv, B * 3 * d * 2, true);
+  A(ctx->datt, B * d * 2, true);
+  A(ctx->dh, B * F * 2, true);
+  A(ctx->dtmp, B * d * 2, true);
 #undef A
   {
     const char* e = getenv("GSV_DECODE_IMPL");
     ctx->force_barrier_kernel = (e && strcmp(e, "barrier") == 0) ? 1 : 0;
     ctx->force_ll1 = (e && strcmp(e, "ll1") == 0) ? 1 : 0;
     ctx->force_ll2 = (e && strcmp(e, "ll2") == 0) ? 1 : 0;
+    ctx->force_gemm = (e && strcmp(e, "gemm") == 0) ? 1 : 0;
+    const char* g = getenv("GSV_GPT_GEMM");
+    ctx->use_umma_linear = (g && strcmp(g, "cuda") == 0) ? 0 : 1;
+    ctx->umma = gsv_umma_cache_create(ctx->num_sms);
   }
   if ((rc = gsv_gpt_decode_configure(ctx))) { gsv_gpt_destroy(ctx); return rc; }
   *out = ctx;
@@ -111,6 +120,8 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
 extern "C" int gsv_gpt_destroy(gsv_gpt_ctx* ctx) {
   if (!ctx) return GSV_OK;
   for (int i = 0; i < ctx->n_allocs; ++i) cudaFree(ctx->all_allocs[i]);
+  if (ctx->step_graph_exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(ctx->step_graph_exec));
+  gsv_umma_cache_destroy(ctx->umma);
   delete ctx;
   return GSV_OK;
 }
@@ -136,6 +147,8 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   for (int i = 0; i < ctx->p.slots; ++i) live += ctx->slot_live[i];
   if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
   // 1..4 live sequences: latency-optimised flag-in-data kernel; otherwise the barrier kernel
+  if (ctx->force_gemm || (live > 4 && !ctx->force_barrier_kernel && ctx->use_umma_linear))
+    return gsv_gpt_decode_gemm_launch(ctx, n_steps, (cudaStream_t)stream);
   // measured on B200 (tools/decode_speed.py, bf16, kv 164..289): 1 live sequence 299 us/token (ll) vs 317 (ll2);
   // 2 live 381 vs 375; 4 live 595 vs 560 -> ll2 from two live sequences up, ll for one (GSV_DECODE_IMPL overrides)
   if (!ctx->force_barrier_kernel && !ctx->force_ll1 && (live >= 2 || ctx->force_ll2) && gsv_gpt_ll2_supported(ctx, live, n_steps))

@@ -30,7 +30,7 @@
 namespace umma {
 
 constexpr int BM = 128;          // time steps per tile
-constexpr int kMaxSA = 4;        // activation ring depth (upper bound)
+constexpr int kMaxSA = 12;       // activation ring depth (upper bound)
 constexpr int kMaxSW = 12;       // weight ring depth (upper bound)
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
@@ -59,6 +59,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor is still running; everything that does not depend on the predecessor's output (barrier set-up,
+// TMEM allocation, tensor-map fetch, the first WEIGHT tiles) runs before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -110,6 +115,7 @@ struct Params {
   int a_rows;            // rows of the activation box = 128 + halo
   int a_stage_bytes;     // a_rows * BK * 2 rounded up to 1024
   int sa, sw;            // ring depths
+  int pdl_early;         // small grid (latency-bound): let the next kernel start its set-up as soon as this one is set up
   ConvArgs<T> ep;
 };
 
@@ -149,11 +155,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
+  // Small grids are latency-bound: the next kernel may begin its own set-up right away.  Large grids keep the SMs
+  // to themselves until their accumulators are done (a waiting successor CTA would only hold shared memory).
+  if (P.pdl_early && threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer: per channel chunk one activation box (with halo), then one weight box per tap ----
       const int row0 = q0 - (transposed ? n_taps - 1 : P.pad);
+      // weights do not depend on the previous kernel: fill the weight ring first, then wait for the predecessor
+      const int n_w = P.kchunks * n_taps;
+      const int pre = n_w < SW ? n_w : SW;
+      for (int i = 0; i < pre; ++i) {
+        const int c = i / n_taps, j = i - c * n_taps;
+        mbar_expect_tx(&w_full[i], W_BYTES);
+        tma_load_3d(tiles_w + (uint32_t)(i * W_STAGE), &P.tm_w, &w_full[i], c * BK, n0, transposed ? r + j * P.n_phase : j);
+      }
+      pdl_wait();
       int i = 0;
       for (int c = 0; c < P.kchunks; ++c) {
         const int s = c % SA;
@@ -161,8 +179,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
         tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, row0, b);
         for (int j = 0; j < n_taps; ++j, ++i) {
+          if (i < pre) continue;                            // already in flight
           const int w = i % SW;
-          if (i >= SW) mbar_wait(&w_empty[w], ((i / SW) - 1) & 1);
+          mbar_wait(&w_empty[w], ((i / SW) - 1) & 1);
           mbar_expect_tx(&w_full[w], W_BYTES);
           tma_load_3d(tiles_w + (uint32_t)(w * W_STAGE), &P.tm_w, &w_full[w], c * BK, n0, transposed ? r + j * P.n_phase : j);
         }
@@ -197,8 +216,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   } else {
     // ---- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = rows q0 + 32*(w%4) + lane ----
     const int quarter = warp & 3;
+    pdl_wait();                            // the epilogue reads residual / accumulator streams of earlier kernels
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
+    if (!P.pdl_early && threadIdx.x == 64) pdl_launch_dependents();
     const int q = q0 + quarter * 32 + lane;
     const int t = transposed ? q * P.n_phase + r - P.t_pad : q;
     const bool row_ok = q < P.m_ext && t >= 0 && t < P.ep.Tout;

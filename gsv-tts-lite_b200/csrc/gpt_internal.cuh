@@ -46,6 +46,8 @@ struct GptParams {
   long long* prof; int prof_max; int prof_cta;
 };
 
+struct gsv_umma_cache;
+
 struct gsv_gpt_ctx {
   gsv_gpt_dims dims;
   GptParams p;
@@ -63,10 +65,23 @@ struct gsv_gpt_ctx {
   void* ll_buf;
   unsigned long long ll_seq;
   int slot_live[GSV_MAX_SLOTS];   // host-side view: prefilled and not yet released
+  gsv_umma_cache* umma;           // tensor-map cache of the prefill / batched-decode linears
+  void *dx, *dqkv, *datt, *dh, *dtmp;   // batched decode step rows [slots][.] (T)
+  void* step_graph_exec;          // cudaGraphExec_t of one batched decode step
+  int force_gemm;                 // GSV_DECODE_IMPL=gemm: multi-kernel tensor-core step for any live count
+  int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
   int force_ll1;                  // GSV_DECODE_IMPL=ll1: first-generation small-batch kernel (A/B checks)
   int force_ll2;                  // GSV_DECODE_IMPL=ll2: second-generation kernel also for a single live sequence
 };
+
+// nn.Linear on the tcgen05 implicit-GEMM kernel (vocoder.cu / conv_umma.cuh): out[r][n] = act(X[r] . W[n] + bias[n]),
+// X [rows_cap][K] T (rows >= `rows` are ignored), W [N][K] T, out [rows][N] T.  `op` names the call site (tensor maps
+// are cached per call site).
+gsv_umma_cache* gsv_umma_cache_create(int num_sms);
+void gsv_umma_cache_destroy(gsv_umma_cache* c);
+int gsv_umma_linear(gsv_umma_cache* c, size_t op, int dtype, const void* X, int rows, int rows_cap, int K, const void* W,
+                    const void* bias, int N, void* out, int relu, cudaStream_t st);
 
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
 int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
@@ -78,3 +93,4 @@ bool gsv_gpt_ll_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
 int gsv_gpt_decode_ll_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
 bool gsv_gpt_ll2_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
 int gsv_gpt_decode_ll2_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
+int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(128) add_ln_kernel(T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ g,
                                                      const T* __restrict__ b, int n, int d) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a tensor-core linear follows: let it set up early
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= n) return;
@@ -254,7 +255,12 @@ __global__ void __launch_bounds__(GSV_DECODE_THREADS, 1) first_token_kernel(cons
 
 template <typename T>
 int gemm(const T* A, int lda, const T* W, const T* bias, T* C, int ldc, int M, int N, int K, bool relu, cudaStream_t st,
-         long long& launches) {
+         long long& launches, gsv_gpt_ctx* ctx = nullptr, size_t op = 0, int rows_cap = 0) {
+  // tensor-core path: the tcgen05 implicit-GEMM kernel with one tap (conv_umma.cuh); tensor maps cached per call site
+  if (ctx && ctx->use_umma_linear && ctx->umma && bias && lda == K && ldc == N && K >= 64 && K % 8 == 0 && N % 16 == 0) {
+    launches += 1;
+    return gsv_umma_linear(ctx->umma, op, ctx->dims.dtype, A, M, rows_cap, K, W, bias, N, C, relu ? 1 : 0, st);
+  }
   if (K % 32 != 0) { gsv_set_error("gemm: K=%d must be a multiple of 32", K); return GSV_ERR_ARG; }
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   if (relu) gemm_tn_kernel<T, true><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K);
@@ -277,7 +283,7 @@ int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int
   int rc;
   // bert_proj (nn.Linear(1024, d), t2s_model.py:172, 354)
   if ((rc = gemm<T>(reinterpret_cast<const T*>(bert), p.d_bert, reinterpret_cast<const T*>(p.w_bert),
-                    reinterpret_cast<const T*>(p.b_bert), TMP, d, nx, d, p.d_bert, false, st, ctx->launches)))
+                    reinterpret_cast<const T*>(p.b_bert), TMP, d, nx, d, p.d_bert, false, st, ctx->launches)))   // bert rows are caller-owned: CUDA cores
     return rc;
   embed_kernel<T><<<n, 128, 0, st>>>(p, x, nx, y, ny, TMP, X);
   ctx->launches += 1;
@@ -285,23 +291,26 @@ int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int
   for (int l = 0; l < L; ++l) {
     const T* wqkv = reinterpret_cast<const T*>(p.w_qkv) + (size_t)l * 3 * d * d;
     const T* bqkv = reinterpret_cast<const T*>(p.b_qkv) + (size_t)l * 3 * d;
-    if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches))) return rc;
+    if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches, ctx, (size_t)l * 4 + 0, p.S))) return rc;
     kv_scatter_kernel<T><<<n, 128, 0, st>>>(p, l, slot, QKV, n);
     prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(QKV, ATT, n, nx, d, p.H);
     ctx->launches += 2;
     GSV_CHECK_LAUNCH();
     if ((rc = gemm<T>(ATT, d, reinterpret_cast<const T*>(p.w_o) + (size_t)l * d * d,
-                      reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, n, d, d, false, st, ctx->launches)))
+                      reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, n, d, d, false, st, ctx->launches, ctx,
+                      (size_t)l * 4 + 1, p.S)))
       return rc;
     add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln1_g) + (size_t)l * d,
                                                  reinterpret_cast<const T*>(p.ln1_b) + (size_t)l * d, n, d);
     ctx->launches += 1;
     GSV_CHECK_LAUNCH();
     if ((rc = gemm<T>(X, d, reinterpret_cast<const T*>(p.w_1) + (size_t)l * F * d,
-                      reinterpret_cast<const T*>(p.b_1) + (size_t)l * F, Hh, F, n, F, d, true, st, ctx->launches)))
+                      reinterpret_cast<const T*>(p.b_1) + (size_t)l * F, Hh, F, n, F, d, true, st, ctx->launches, ctx,
+                      (size_t)l * 4 + 2, p.S)))
       return rc;
     if ((rc = gemm<T>(Hh, F, reinterpret_cast<const T*>(p.w_2) + (size_t)l * d * F,
-                      reinterpret_cast<const T*>(p.b_2) + (size_t)l * d, TMP, d, n, d, F, false, st, ctx->launches)))
+                      reinterpret_cast<const T*>(p.b_2) + (size_t)l * d, TMP, d, n, d, F, false, st, ctx->launches, ctx,
+                      (size_t)l * 4 + 3, p.S)))
       return rc;
     add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln2_g) + (size_t)l * d,
                                                  reinterpret_cast<const T*>(p.ln2_b) + (size_t)l * d, n, d);
@@ -317,7 +326,232 @@ int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int
   return GSV_OK;
 }
 
+
+// =====================================================================================================================
+// Batched decode step as a short sequence of kernels (5..32 live sequences; GSV_DECODE_IMPL=gemm forces it):
+// the four linears of every layer run on the tcgen05 kernel with the live sequences as rows (M tile 128, rows past
+// the slot count are zero-filled by TMA), attention / add+LayerNorm / head / sampling are small kernels over
+// (slot, head) or slot.  One step = 7 L + 2 launches, captured once into a CUDA graph and replayed per token.
+// Same arithmetic as T2STransformer.decode_next_token + sample (t2s_model.py:129-143, 637-653) with activations
+// rounded to the storage type between ops, as the reference rounds them.
+// =====================================================================================================================
+
+// x rows of the step: Xd[slot] = T(xin[slot]) (xin is written by prefill / the sampler as fp32 values already rounded to T)
+template <typename T>
+__global__ void xin_to_x_kernel(const GptParams p, T* __restrict__ X) {
+  const int slot = blockIdx.x;
+  if (!p.active[slot]) return;
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) X[(size_t)slot * p.d + c] = Elem<T>::from_f(p.xin[(size_t)slot * p.d + c]);
+}
+
+// KV append + attention of one (head, slot) over positions 0..kv_len inclusive; 4 warps, 8 positions per warp pass
+template <typename T>
+__global__ void __launch_bounds__(128) dec_attn_kernel(const GptParams p, int layer, const T* __restrict__ qkv, T* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int h = blockIdx.x, slot = blockIdx.y;
+  if (!p.active[slot]) return;
+  __shared__ float part[4][GSV_HEAD_DIM + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = p.d, kv = p.kv_len[slot];
+  const int sub = lane & 3, pg = lane >> 2;
+  const size_t head_base = ((size_t)(layer * p.slots + slot) * p.H + h) * (size_t)p.S * GSV_HEAD_DIM;
+  T* kc = reinterpret_cast<T*>(p.kc) + head_base;
+  T* vc = reinterpret_cast<T*>(p.vc) + head_base;
+  const T* row = qkv + (size_t)slot * 3 * d + h * GSV_HEAD_DIM;
+  if (threadIdx.x < GSV_HEAD_DIM) {
+    kc[(size_t)kv * GSV_HEAD_DIM + threadIdx.x] = row[d + threadIdx.x];
+    vc[(size_t)kv * GSV_HEAD_DIM + threadIdx.x] = row[2 * d + threadIdx.x];
+  }
+  __syncthreads();
+  const float qscale = rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f;
+  float q[8];
+  unpack8<T>(*reinterpret_cast<const uint4*>(row + sub * 8), q);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] *= qscale;
+  const int n = kv + 1;
+  float m = GSV_NEG_INF, l = 0.f, o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  for (int base = warp * 8; base < n; base += 32) {
+    const int t = base + pg;
+    const bool ok = t < n;
+    float s = GSV_NEG_INF, vf[8];
+    if (ok) {
+      float kf[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(kc + (size_t)t * GSV_HEAD_DIM + sub * 8), kf);
+      unpack8<T>(*reinterpret_cast<const uint4*>(vc + (size_t)t * GSV_HEAD_DIM + sub * 8), vf);
+      s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(q[j], kf[j], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float sc = exp2f(m - mn), pr = exp2f(s - mn);
+      l = l * sc + pr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, vf[j], o[j] * sc);
+      m = mn;
+    }
+  }
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, m2);
+    const float a = mn > GSV_NEG_INF ? exp2f(m - mn) : 0.f;
+    const float b = mn > GSV_NEG_INF ? exp2f(m2 - mn) : 0.f;
+    l = l * a + l2 * b;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = o[j] * a + __shfl_xor_sync(0xffffffffu, o[j], off) * b;
+    m = mn;
+  }
+  if (pg == 0) {
+    if (sub == 0) { part[warp][0] = m; part[warp][1] = l; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[warp][2 + sub * 8 + j] = o[j];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float M = GSV_NEG_INF;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, part[w][0]);
+    float L = 0.f, acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = part[w][0];
+      if (mw > GSV_NEG_INF) {
+        const float sc = exp2f(mw - M);
+        L = fmaf(part[w][1], sc, L);
+        acc = fmaf(part[w][2 + lane], sc, acc);
+      }
+    }
+    out[(size_t)slot * d + h * GSV_HEAD_DIM + lane] = Elem<T>::from_f(acc / L);
+  }
+}
+
+// logits[slot][row] = X[slot] . Whead[row] (fp32; ar_predict_layer has no bias, t2s_model.py:442)
+template <typename T>
+__global__ void __launch_bounds__(256) head_rows_kernel(const GptParams p, const T* __restrict__ X) {
+  const int slot = blockIdx.y;
+  if (!p.active[slot]) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.V) return;
+  const T* w = reinterpret_cast<const T*>(p.w_head) + (size_t)row * p.d;
+  const T* xrow = X + (size_t)slot * p.d;
+  float acc = 0.f;
+  for (int c = lane * 8; c < p.d; c += 256) {
+    float wf[8], xf[8];
+    unpack8<T>(ld_weight(w + c), wf);
+    unpack8<T>(*reinterpret_cast<const uint4*>(xrow + c), xf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(wf[j], xf[j], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) p.logits[(size_t)slot * GSV_VOCAB_MAX + row] = acc;
+}
+
+// kv_len += 1 (t2s_model.py:142), sample, stop flags, next input row
+template <typename T>
+__global__ void __launch_bounds__(GSV_DECODE_THREADS, 1) sample_step_kernel(const GptParams p, T* __restrict__ X) {
+  extern __shared__ __align__(16) float sm[];
+  const int slot = blockIdx.x;
+  if (!p.active[slot]) return;
+  if (threadIdx.x == 0) st_cg(p.kv_len + slot, p.kv_len[slot] + 1);
+  __syncthreads();
+  sample_slot<T>(p, slot, sm);
+  for (int c = threadIdx.x; c < p.d; c += blockDim.x) X[(size_t)slot * p.d + c] = Elem<T>::from_f(ld_cg(p.xin + (size_t)slot * p.d + c));
+}
+
+template <typename T>
+int decode_step_launches(gsv_gpt_ctx* ctx, cudaStream_t st) {
+  const GptParams& p = ctx->p;
+  const int d = p.d, F = p.F, L = p.L, nb = p.slots;
+  T* X = reinterpret_cast<T*>(ctx->dx);
+  T* QKV = reinterpret_cast<T*>(ctx->dqkv);
+  T* ATT = reinterpret_cast<T*>(ctx->datt);
+  T* Hh = reinterpret_cast<T*>(ctx->dh);
+  T* TMP = reinterpret_cast<T*>(ctx->dtmp);
+  const size_t op0 = (size_t)4 * L + 8;        // call sites of the decode linears (prefill uses [0, 4L))
+  long long dummy = 0;
+  int rc;
+  for (int l = 0; l < L; ++l) {
+    if ((rc = gemm<T>(X, d, reinterpret_cast<const T*>(p.w_qkv) + (size_t)l * 3 * d * d,
+                      reinterpret_cast<const T*>(p.b_qkv) + (size_t)l * 3 * d, QKV, 3 * d, nb, 3 * d, d, false, st, dummy, ctx,
+                      op0 + (size_t)l * 4 + 0, nb)))
+      return rc;
+    dec_attn_kernel<T><<<dim3(p.H, nb), 128, 0, st>>>(p, l, QKV, ATT);
+    if ((rc = gemm<T>(ATT, d, reinterpret_cast<const T*>(p.w_o) + (size_t)l * d * d,
+                      reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, nb, d, d, false, st, dummy, ctx,
+                      op0 + (size_t)l * 4 + 1, nb)))
+      return rc;
+    add_ln_kernel<T><<<(nb + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln1_g) + (size_t)l * d,
+                                                  reinterpret_cast<const T*>(p.ln1_b) + (size_t)l * d, nb, d);
+    if ((rc = gemm<T>(X, d, reinterpret_cast<const T*>(p.w_1) + (size_t)l * F * d,
+                      reinterpret_cast<const T*>(p.b_1) + (size_t)l * F, Hh, F, nb, F, d, true, st, dummy, ctx,
+                      op0 + (size_t)l * 4 + 2, nb)))
+      return rc;
+    if ((rc = gemm<T>(Hh, F, reinterpret_cast<const T*>(p.w_2) + (size_t)l * d * F,
+                      reinterpret_cast<const T*>(p.b_2) + (size_t)l * d, TMP, d, nb, d, F, false, st, dummy, ctx,
+                      op0 + (size_t)l * 4 + 3, nb)))
+      return rc;
+    add_ln_kernel<T><<<(nb + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln2_g) + (size_t)l * d,
+                                                  reinterpret_cast<const T*>(p.ln2_b) + (size_t)l * d, nb, d);
+  }
+  head_rows_kernel<T><<<dim3((p.V + 7) / 8, nb), 256, 0, st>>>(p, X);
+  sample_step_kernel<T><<<nb, GSV_DECODE_THREADS, GSV_SAMPLE_SMEM_FLOATS * sizeof(float), st>>>(p, X);
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
+template <typename T>
+int decode_gemm_impl(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
+  const GptParams& p = ctx->p;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSV_CUDA(cudaFuncSetAttribute(sample_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(GSV_SAMPLE_SMEM_FLOATS * sizeof(float))));
+    attr_set = true;
+  }
+  xin_to_x_kernel<T><<<p.slots, 128, 0, st>>>(p, reinterpret_cast<T*>(ctx->dx));
+  ctx->launches += 1;
+  GSV_CHECK_LAUNCH();
+  const long long per_step = 7LL * p.L + 2;
+  if (!ctx->step_graph_exec) {
+    // one eager step first (it also encodes and caches every tensor map), then capture the same launches once
+    int rc = decode_step_launches<T>(ctx, st);
+    if (rc) return rc;
+    ctx->launches += per_step;
+    n_steps -= 1;
+    if (n_steps == 0) return GSV_OK;
+    cudaStream_t cs;
+    GSV_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    GSV_CUDA(cudaStreamSynchronize(st));
+    GSV_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    rc = decode_step_launches<T>(ctx, cs);
+    cudaError_t ce = cudaStreamEndCapture(cs, &g);
+    cudaStreamDestroy(cs);
+    if (rc) return rc;
+    GSV_CUDA(ce);
+    cudaGraphExec_t ge = nullptr;
+    GSV_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    ctx->step_graph_exec = ge;
+  }
+  for (int i = 0; i < n_steps; ++i) GSV_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(ctx->step_graph_exec), st));
+  ctx->launches += per_step * n_steps;
+  return GSV_OK;
+}
+
 }  // namespace
+
+int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return decode_gemm_impl<__half>(ctx, n_steps, st);
+  return decode_gemm_impl<__nv_bfloat16>(ctx, n_steps, st);
+}
 
 int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert,
                          const gsv_gpt_sampling* samp, cudaStream_t st) {

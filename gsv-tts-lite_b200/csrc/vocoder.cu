@@ -32,7 +32,7 @@
 
 namespace {
 
-enum { ACT_NONE = 0, ACT_LRELU_01 = 1, ACT_LRELU_001 = 2 };
+enum { ACT_NONE = 0, ACT_LRELU_01 = 1, ACT_LRELU_001 = 2, ACT_RELU = 3 };
 
 template <typename T>
 struct ConvArgs {
@@ -68,6 +68,7 @@ struct ConvArgs {
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_LRELU_01) return v > 0.f ? v : 0.1f * v;
   if (act == ACT_LRELU_001) return v > 0.f ? v : 0.01f * v;
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 
@@ -415,12 +416,21 @@ int launch_umma_inst(const umma::Params<T>& P, dim3 grid, size_t smem, cudaStrea
                                   umma::kSmemBudget + 2048));
     attr_set = true;
   }
-  umma::conv_umma_kernel<T, BN, BK><<<grid, umma::kThreads, smem, st>>>(P);
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("GSV_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(umma::kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::conv_umma_kernel<T, BN, BK>, P));
   return GSV_OK;
 }
 
 template <typename T>
-int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStream_t st) {
+int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const ConvArgs<T>& a, size_t op, cudaStream_t st) {
   const bool transposed = a.stride > 1;
   const int n_phase = transposed ? a.stride : 1;
   const int max_taps = transposed ? (a.KW + a.stride - 1) / a.stride : a.KW;
@@ -430,14 +440,14 @@ int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStre
   const int bk = a.Cin >= 64 ? 64 : a.Cin;                 // 64 / 32 / 16 channels per chunk
   // N tile: as wide as divides Cout, narrowed while the grid would leave most SMs idle
   int bn = a.Cout % 128 == 0 ? 128 : (a.Cout % 64 == 0 ? 64 : (a.Cout % 32 == 0 ? 32 : 16));
-  const int bn_min = bk == 64 ? 32 : 16;
-  while (bn > bn_min && (long long)mt * (a.Cout / bn) * a.B * n_phase < ctx->num_sms) bn >>= 1;
+  const int bn_min = 16;
+  while (bn > bn_min && (long long)mt * (a.Cout / bn) * a.B * n_phase < num_sms) bn >>= 1;
   if (bk == 32 && bn > 32) bn = 32;
   if (bk == 16) bn = 16;
   if (a.Cout % bn != 0) { gsv_set_error("conv: Cout=%d not a multiple of the N tile %d", a.Cout, bn); return GSV_ERR_ARG; }
   const int a_rows = umma::BM + halo;
-  if (op >= ctx->map_cache.size()) ctx->map_cache.resize(op + 1);
-  MapCacheEntry& e = ctx->map_cache[op];
+  if (op >= map_cache.size()) map_cache.resize(op + 1);
+  MapCacheEntry& e = map_cache[op];
   if (e.in != a.in || e.w != a.w || e.in_ld != a.in_ld || e.Tin != a.Tin || e.B != a.B || e.Cin != a.Cin || e.Cout != a.Cout ||
       e.KW != a.KW || e.bn != bn || e.w_tap != a.w_tap || e.a_rows != a_rows) {
     const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
@@ -461,7 +471,11 @@ int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStre
   P.a_rows = a_rows;
   P.a_stage_bytes = (a_rows * bk * 2 + 1023) & ~1023;
   const int w_stage = (bn * bk * 2 + 1023) & ~1023;
-  P.sa = P.kchunks < 3 ? P.kchunks : 3;
+  // ring depths: with one tap (a linear) activations and weights advance together, so both rings get the same
+  // depth; with many taps per chunk the weight ring paces the pipeline and 3 activation stages are enough
+  int sa = max_taps == 1 ? umma::kSmemBudget / (P.a_stage_bytes + w_stage) : 3;
+  sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
+  P.sa = P.kchunks < sa ? P.kchunks : sa;
   int sw = (umma::kSmemBudget - P.sa * P.a_stage_bytes) / w_stage;
   const int n_w = P.kchunks * max_taps;
   sw = sw > umma::kMaxSW ? umma::kMaxSW : sw;
@@ -469,6 +483,7 @@ int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStre
   P.ep = a;
   const size_t smem = (size_t)P.sa * P.a_stage_bytes + (size_t)P.sw * w_stage + 1024;
   const dim3 grid(mt, a.Cout / bn, a.B * n_phase);
+  P.pdl_early = (long long)grid.x * grid.y * grid.z <= num_sms ? 1 : 0;
   int rc = GSV_ERR_ARG;
   if (bk == 64) {
     if (bn == 128) rc = launch_umma_inst<T, 128, 64>(P, grid, smem, st);
@@ -482,7 +497,6 @@ int launch_conv_umma(gsv_voc_ctx* ctx, const ConvArgs<T>& a, size_t op, cudaStre
     rc = launch_umma_inst<T, 16, 16>(P, grid, smem, st);
   }
   if (rc) return rc;
-  ctx->launches += 1;
   GSV_CHECK_LAUNCH();
   return GSV_OK;
 }
@@ -495,7 +509,10 @@ int launch_conv(gsv_voc_ctx* ctx, const ConvArgs<T>& a, cudaStream_t st) {
   }
   {
     const size_t op = ctx->op_index++;
-    if (ctx->use_umma && umma_eligible<T>(a)) return launch_conv_umma<T>(ctx, a, op, st);
+    if (ctx->use_umma && umma_eligible<T>(a)) {
+      ctx->launches += 1;
+      return launch_conv_umma<T>(ctx->map_cache, ctx->num_sms, a, op, st);
+    }
   }
   if (a.stride == 1) {
     if ((a.KW - 1) * a.dil > 64) { gsv_set_error("conv: halo too large"); return GSV_ERR_ARG; }
@@ -838,4 +855,37 @@ extern "C" int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const voi
   if (ctx->dims.dtype == GSV_F16)
     return flow_dec_impl<__half>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
   return flow_dec_impl<__nv_bfloat16>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
+}
+
+// ---- nn.Linear on the same tensor-core kernel (a convolution with one tap), for the GPT prefill and the
+//      batched decode step: out[r][n] = act(sum_k X[r][k] W[n][k] + bias[n]) --------------------------------------
+struct gsv_umma_cache {
+  std::vector<MapCacheEntry> maps;
+  int num_sms;
+};
+
+gsv_umma_cache* gsv_umma_cache_create(int num_sms) {
+  gsv_umma_cache* c = new (std::nothrow) gsv_umma_cache();
+  if (c) c->num_sms = num_sms;
+  return c;
+}
+void gsv_umma_cache_destroy(gsv_umma_cache* c) { delete c; }
+
+template <typename T>
+static int umma_linear_t(gsv_umma_cache* c, size_t op, const void* X, int rows, int rows_cap, int K, const void* W, const void* bias,
+                         int N, void* out, int relu, cudaStream_t st) {
+  ConvArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.in = reinterpret_cast<const T*>(X); a.in_ld = K; a.B = 1; a.Tin = rows_cap; a.Tout = rows; a.Cin = K; a.Cout = N;
+  a.KW = 1; a.dil = 1; a.stride = 1; a.res_sign = 1.f; a.acc_scale = 1.f;
+  a.w = reinterpret_cast<const T*>(W); a.w_tap = (long long)N * K; a.bias = reinterpret_cast<const T*>(bias);
+  a.outT = reinterpret_cast<T*>(out); a.o_ld = N; a.act = relu ? ACT_RELU : ACT_NONE;
+  if (!umma_eligible<T>(a)) { gsv_set_error("umma linear: unsupported shape K=%d N=%d", K, N); return GSV_ERR_ARG; }
+  return launch_conv_umma<T>(c->maps, c->num_sms, a, op, st);
+}
+
+int gsv_umma_linear(gsv_umma_cache* c, size_t op, int dtype, const void* X, int rows, int rows_cap, int K, const void* W,
+                    const void* bias, int N, void* out, int relu, cudaStream_t st) {
+  if (dtype == GSV_F16) return umma_linear_t<__half>(c, op, X, rows, rows_cap, K, W, bias, N, out, relu, st);
+  return umma_linear_t<__nv_bfloat16>(c, op, X, rows, rows_cap, K, W, bias, N, out, relu, st);
 }
