@@ -26,6 +26,8 @@
 // Safety of single-buffered exchange buffers: every CTA produces rows in every GEMV phase and consumes
 // the full vector of the previous one, so no CTA can run more than one phase ahead of the slowest
 // (DESIGN.md "LL hazards").
+#include <cstdlib>
+
 #include "gpt_sample.cuh"
 
 namespace {
@@ -702,6 +704,8 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll_kernel(const GptParams p,
         io.status_ll = ll_stat + slot;
         io.tag = tag;
         io.kv_len = sh.kv[cta] + 1;
+        io.xin_smem = nullptr;
+        io.alive_smem = nullptr;
         sample_slot<T>(p, slot, smem, &io);
       }
       __syncthreads();
@@ -740,7 +744,14 @@ int launch_ll_nb(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   unsigned tag_base = (unsigned)(ctx->ll_seq << 16);
   uint2* buf = reinterpret_cast<uint2*>(ctx->ll_buf);
   void* args[] = {&p, &ns, &tag_base, &buf};
-  GSV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctx->num_sms), dim3(NT), args, bytes, st));
+  int grid = ctx->num_sms;
+  {
+    // tuning hook: fewer CTAs = fewer pollers per exchange, more rows per CTA
+    static int env_grid = -1;
+    if (env_grid < 0) { const char* e = getenv("GSV_LL_GRID"); env_grid = e ? atoi(e) : 0; }
+    if (env_grid >= ctx->p.H * NB && env_grid <= ctx->num_sms) grid = env_grid;
+  }
+  GSV_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, bytes, st));
   ctx->launches += 1;
   return GSV_OK;
 }

@@ -733,6 +733,8 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
         io.status_ll = ll_stat + slot;
         io.tag = tag;
         io.kv_len = sh.kv[samp_i] + 1;
+        io.xin_smem = nullptr;
+        io.alive_smem = nullptr;
         sample_slot<T>(p, slot, smem, &io);
       }
       __syncthreads();

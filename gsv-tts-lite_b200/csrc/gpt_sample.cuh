@@ -51,10 +51,12 @@ __device__ __forceinline__ float block_sum(float a, float* red_v) {
 // {value, tag} words, and kv_len comes from the caller instead of global memory.
 struct SampleLL {
   bool preloaded;
-  uint2* xin_ll;
+  uint2* xin_ll;        // LL kernels: next input published as {value, tag} words (or null)
   uint2* status_ll;
   unsigned tag;
   int kv_len;
+  float* xin_smem;      // cluster kernel: next input [d] and alive flag left in shared memory instead (or null)
+  int* alive_smem;
 };
 // One naturally aligned 64-bit SCALAR access per word: {value (low 32 bits), tag (high 32 bits)}.  A
 // vector access (st.v2.u32 / ld.v2.u32) is modelled by the PTX memory model as two scalar accesses in
@@ -314,7 +316,8 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
     if (stop) st_cg(p.active + slot, 0);
     if (ll) {
       st_cg(p.kv_len + slot, kvl);
-      ll_store(ll->status_ll, stop ? 0.f : 1.f, ll->tag);
+      if (ll->status_ll) ll_store(ll->status_ll, stop ? 0.f : 1.f, ll->tag);
+      if (ll->alive_smem) *ll->alive_smem = stop ? 0 : 1;
     }
   }
   // next input: emb_audio[tok] * x_scale(=1) + (alpha*pe)[kv_len - Nx]  (:455-456, :727-728)
@@ -327,7 +330,8 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
       // the reference adds two T values and rounds to T
       float s = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(emb[c]) + Elem<T>::to_f(pe[c])));
       st_cg(p.xin + (size_t)slot * p.d + c, s);
-      if (ll) ll_store(ll->xin_ll + c, s, ll->tag);
+      if (ll && ll->xin_ll) ll_store(ll->xin_ll + c, s, ll->tag);
+      if (ll && ll->xin_smem) ll->xin_smem[c] = s;
     }
   }
   __syncthreads();
