@@ -120,7 +120,7 @@ struct Params {
 };
 
 template <typename T, int BN, int BK>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ Params<T> P) {
+__global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_constant__ Params<T> P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROW_BYTES = BK * 2, W_BYTES = BN * ROW_BYTES;
   constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;

@@ -473,10 +473,14 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
   const int w_stage = (bn * bk * 2 + 1023) & ~1023;
   // ring depths: with one tap (a linear) activations and weights advance together, so both rings get the same
   // depth; with many taps per chunk the weight ring paces the pipeline and 3 activation stages are enough
-  int sa = max_taps == 1 ? umma::kSmemBudget / (P.a_stage_bytes + w_stage) : 3;
+  // large grids: keep a CTA under ~100 KB so that two share an SM (one's epilogue overlaps the other's main loop)
+  const long long n_ctas = (long long)mt * (a.Cout / bn) * a.B * n_phase;
+  const int budget = n_ctas >= 2LL * num_sms ? 100 * 1024 : umma::kSmemBudget;
+  int sa = max_taps == 1 ? budget / (P.a_stage_bytes + w_stage) : (n_ctas >= 2LL * num_sms ? 2 : 3);
   sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
   P.sa = P.kchunks < sa ? P.kchunks : sa;
-  int sw = (umma::kSmemBudget - P.sa * P.a_stage_bytes) / w_stage;
+  int sw = (budget - P.sa * P.a_stage_bytes) / w_stage;
+  if (sw < 2) sw = 2;
   const int n_w = P.kchunks * max_taps;
   sw = sw > umma::kMaxSW ? umma::kMaxSW : sw;
   P.sw = sw > n_w ? n_w : sw;

@@ -232,6 +232,32 @@ def test_batched_slots_match_single_slot_logits(dev):
             assert len(alone) <= 30 and len(together[r]) <= 30
 
 
+@pytest.mark.parametrize("impl", ["ll1", "ll2", "cl", "gemm", "barrier"])
+@pytest.mark.parametrize("name,cfg", [("tiny", syn.GPT_CONFIG_TINY), ("full", syn.GPT_CONFIG)])
+def test_every_decode_kernel_teacher_forced_logits(dev, monkeypatch, impl, name, cfg):
+    """Every decode implementation behind gsv_gpt_decode (flag-in-data ll / ll2, cluster-per-sequence,
+    multi-kernel tcgen05 step, grid-barrier) on the same teacher-forced case: logits within the
+    16-bit tolerance of the fp32 oracle on the same rounded weights and of the reference's golden."""
+    from tests import gpu_harness as H
+    monkeypatch.setenv("GSV_DECODE_IMPL", impl)
+    e = H.gpt_teacher_forced_error(cfg, name, torch.float16, dev)
+    print(impl, name, "vs_oracle", e["vs_oracle"], "vs_golden", e["vs_golden"])
+    assert e["vs_oracle"] < TOL[torch.float16]
+    assert e["vs_golden"] < 1.5 * TOL[torch.float16]
+
+
+def test_cuda_core_prefill_matches_tensor_core_prefill(dev, monkeypatch):
+    """GSV_GPT_GEMM=cuda (tiled CUDA-core GEMMs) and the default tcgen05 linears: first-row logits
+    (pure prefill) of the full-size model agree within the 16-bit tolerance of the oracle."""
+    from tests import gpu_harness as H
+    cfg = syn.GPT_CONFIG
+    e_tc = H.gpt_teacher_forced_error(cfg, "full", torch.float16, dev)
+    monkeypatch.setenv("GSV_GPT_GEMM", "cuda")
+    e_cc = H.gpt_teacher_forced_error(cfg, "full", torch.float16, dev)
+    print("tcgen05", e_tc["per_row_vs_oracle"][0], "cuda cores", e_cc["per_row_vs_oracle"][0])
+    assert e_tc["per_row_vs_oracle"][0] < TOL[torch.float16] and e_cc["per_row_vs_oracle"][0] < TOL[torch.float16]
+
+
 def test_barrier_kernel_teacher_forced_logits(dev, monkeypatch):
     """The >4-sequence (grid-barrier) decode kernel on the same teacher-forced case as the
     small-batch flag-in-data kernel: both within tolerance of the oracle and of each other."""
