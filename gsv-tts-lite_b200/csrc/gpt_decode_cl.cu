@@ -14,6 +14,12 @@
 //     per layer), ~10 KB in flight per warp (a 16-byte cp.async ring sustained only 36 GB/s per SM);
 //   * sequences do not interact at all: B live sequences = B clusters (grid = B x H), no cross-cluster traffic; the
 //     152 MB weight stream of concurrent clusters is shared through L2.
+// Measured limits of this design (B200): the cluster lives on ONE GPC, whose memory port sustains ~0.7-0.8 TB/s
+// (16 SMs x ~45 GB/s; tools/ubench/bulk_bw.cu reaches 200 GB/s per SM only when the 16 CTAs sit on different GPCs),
+// so one sequence cannot go below ~190 us/token here however the copies are shaped (per-warp 1 KB units, below, and
+// CTA-wide 32 KB chunks were both tried: 355 vs 400 us/token).  A single sequence is therefore still served by
+// the grid-wide flag-in-data kernel (299 us); from two sequences up the clusters win because they scale with the
+// number of GPCs (6 co-resident clusters: 16.8k tok/s) and never exchange anything through L2.
 // Two inboxes alternate between consecutive phases.  A CTA re-arms an inbox right after reading it and before it
 // pushes its own outputs; a peer can only start the next fill of that inbox after it has received those outputs,
 // so a fill never overtakes the read of the previous one.
