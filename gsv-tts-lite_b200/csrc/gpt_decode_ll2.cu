@@ -16,20 +16,21 @@
 //     with cp.async into the warp's private shared-memory slot right after the current one is consumed.  (Holding
 //     it in registers instead was measured 25 % SLOWER: an outstanding HBM load shares one of the warp's six
 //     scoreboards with the polling loads, so every spin inherited the HBM latency of the prefetch.)
-//   * Outputs are published by the lane that holds them.  The four K-quarters of an MLP-down row are published
-//     as four partial words and summed (in fixed order) by the consumers, so no cross-warp reduction is needed.
+//   * A CTA's outputs are gathered in shared memory and published by one warp with one coalesced store into a
+//     128-byte line that only this CTA writes.
 //
 // Phases of layer l (tags t..t+3):
 //   A   all CTAs: x = l == 0 ? xin : LN2(sum of the 4 y2 partials)  -> residual copy; attention CTAs: q,k,v of
 //       their head, KV append, attention over 0..kv -> att[slot][h*32..]
 //   O   y1 = x + att Wo^T + bo
 //   M1  x1 = LN1(y1) -> residual copy; h = relu(x1 W1^T + b1)
-//   M2  y2 partial[q] = h[q*D..] W2[:, q*D..]^T (+ b2 + x1 for q == 0)
+//   M2  y2 = x1 + h W2^T + b2 (four K-quarter warps per row, summed inside the CTA)
 // then the head (LN2 + ar_predict_layer) and the sampler CTAs (gpt_sample.cuh).
 //
-// Buffer-reuse safety (single-buffered exchange areas): in O, M1, M2 and the head EVERY CTA produces rows and
-// consumes the full previous vector, and every CTA polls the y2 partials in A; a CTA can therefore never run
-// more than one phase ahead of the slowest one, and each area is rewritten only one layer later.
+// Buffer-reuse safety (single-buffered exchange areas): every CTA polls the full input of every phase, and every
+// CTA PRODUCES in at least one of any three consecutive phases (M1: all CTAs; M2: CTAs [0, D/4); O: the top D/16
+// CTAs, which include every CTA without M2 rows).  The writers of an area's next version transitively wait for
+// the outputs of those phases, hence for every reader of the previous version.
 #include "gpt_sample.cuh"
 
 namespace {
@@ -263,21 +264,31 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
   //   O, head : 16 consecutive rows per producer CTA (D/16 resp. ceil(V/16) CTAs produce; the rest only consume)
   //   M1, M2  : all G CTAs produce (needed for the buffer-reuse argument above): CTA c owns tasks
   //             [c*F/G, (c+1)*F/G) (<= 16) and publishes them into ITS line: word index c*16 + (task - begin)
-  const int o_cta = cta - (G - 4 - D / 16);                 // O producers: a block of CTAs away from attention/sampler roles
+  const int o_cta = cta - (G - D / 16);                     // O producers: the top D/16 CTAs (they include every CTA without MLP-down rows)
   const int o_b = (o_cta >= 0 && o_cta < D / 16) ? o_cta * 16 : 0, o_e = (o_cta >= 0 && o_cta < D / 16) ? o_b + 16 : 0;
   const int m1_b = (int)((long long)cta * F / G), m1_e = (int)((long long)(cta + 1) * F / G);
-  const int m2_b = m1_b, m2_e = m1_e;                       // task = quarter*D + row
+  // MLP-down: CTA c < D/4 owns rows [4c, 4c+4); warp w = quarter (w & 3) of row 4c + (w >> 2); the four K-quarters are
+  // summed inside the CTA, so consumers poll ONE word per element (4-word polls made this exchange 2x slower)
   const int hd_b = min(V, cta * 16), hd_e = min(V, cta * 16 + 16);
-  const int o_t = o_b + warp, m1_t = m1_b + warp, m2_t = m2_b + warp;
-  const bool o_ok = o_t < o_e, m1_ok = m1_t < m1_e, m2_ok = m2_t < m2_e;
-  const int m2_q = m2_t / D, m2_row = m2_t - m2_q * D;
+  const int o_t = o_b + warp, m1_t = m1_b + warp;
+  const bool o_ok = o_t < o_e, m1_ok = m1_t < m1_e, m2_ok = cta < D / 4;
+  const int m2_q = warp & 3, m2_row = cta * 4 + (warp >> 2);
+#ifdef GSV_LL2_PADDED
+  const int y2_off = (tid >> 2) * 16 + (tid & 3);           // where element `tid` of y2 lives: line of CTA tid/4, word tid%4
+#else
+  const int y2_off = tid;
+#endif
   // where this thread finds element `tid` of the h vector / of each y2 partial in the padded layout
   int pad_off[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int t = e * D + tid;                              // task index (valid for tid < D)
     const int owner = (int)((((long long)t + 1) * G - 1) / F);
+    (void)owner;
+    pad_off[e] = t;                                         // dense layout (GSV_LL2_PADDED: one line per producer CTA)
+#ifdef GSV_LL2_PADDED
     pad_off[e] = owner * 16 + (t - (int)((long long)owner * F / G));
+#endif
   }
   const int PADW = G * 16;                                  // words per slot of a padded area
 
@@ -391,9 +402,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
             if (l == 0) {
               raw[s] = ll_wait(ll_xin + (size_t)sh.sl[s] * D + tid, tag);
             } else {
-              float a4[4];
-              ll_wait4p(ll_y2 + (size_t)sh.sl[s] * PADW, pad_off, tag, a4);
-              raw[s] = ((a4[0] + a4[1]) + a4[2]) + a4[3];
+              raw[s] = ll_wait(ll_y2 + (size_t)sh.sl[s] * PADW + y2_off, tag);
             }
             xa[s * D + split_pos(tid, D)] = raw[s];
           }
@@ -619,7 +628,11 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
         if (warp == 0 && m1_b + lane < m1_e) {
 #pragma unroll
           for (int s = 0; s < NB; ++s)
+#ifdef GSV_LL2_PADDED
             if (s < nb) ll_store(ll_h + (size_t)sh.sl[s] * PADW + cta * 16 + lane, sh.outv[s][lane], tag + 1);
+#else
+            if (s < nb) ll_store(ll_h + (size_t)sh.sl[s] * PADW + m1_b + lane, sh.outv[s][lane], tag + 1);
+#endif
         }
         if (m1_ok) slot_fetch<T, NCH>(slot_1, W1 + ((size_t)ln * F + m1_t) * D, lane);
         cp_async_commit();
@@ -664,10 +677,17 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
           }
         }
         __syncthreads();
-        if (warp == 0 && m2_b + lane < m2_e) {
+        if (warp == 0 && m2_ok && lane < 4) {             // rows 4c .. 4c+3: sum of the four K-quarters, one 32-byte store
 #pragma unroll
           for (int s = 0; s < NB; ++s)
-            if (s < nb) ll_store(ll_y2 + (size_t)sh.sl[s] * PADW + cta * 16 + lane, sh.outv[s][lane], tag + 1);
+            if (s < nb) {
+              const float* q4 = &sh.outv[s][lane * 4];
+#ifdef GSV_LL2_PADDED
+              ll_store(ll_y2 + (size_t)sh.sl[s] * PADW + cta * 16 + lane, ((q4[0] + q4[1]) + q4[2]) + q4[3], tag + 1);
+#else
+              ll_store(ll_y2 + (size_t)sh.sl[s] * PADW + cta * 4 + lane, ((q4[0] + q4[1]) + q4[2]) + q4[3], tag + 1);
+#endif
+            }
         }
         if (m2_ok) slot_fetch<T, NCH>(slot_2, W2 + ((size_t)ln * D + m2_row) * F + (size_t)m2_q * D, lane);
         cp_async_commit();
@@ -685,9 +705,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
 #pragma unroll
       for (int s = 0; s < NB; ++s) {
         if (s < nb && tid < D) {
-          float a4[4];
-          ll_wait4p(ll_y2 + (size_t)sh.sl[s] * PADW, pad_off, tag, a4);
-          xa[s * D + split_pos(tid, D)] = ((a4[0] + a4[1]) + a4[2]) + a4[3];
+          xa[s * D + split_pos(tid, D)] = ll_wait(ll_y2 + (size_t)sh.sl[s] * PADW + y2_off, tag);
         }
       }
       __syncthreads();
@@ -799,7 +817,7 @@ bool gsv_gpt_ll2_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps) 
   // phases per launch < 2^16 so that tags are unique
   return shape && live_slots >= 1 && live_slots <= MAXB && ctx->p.H * live_slots <= ctx->num_sms &&
          (ctx->p.F + ctx->num_sms - 1) / ctx->num_sms <= NWARP && ctx->p.F >= ctx->num_sms &&
-         (ctx->p.V + 15) / 16 <= ctx->num_sms && ctx->p.d / 16 + 4 + live_slots * ctx->p.H <= ctx->num_sms &&
+         (ctx->p.V + 15) / 16 <= ctx->num_sms && ctx->p.d / 4 <= ctx->num_sms && ctx->p.d / 4 + ctx->p.d / 16 >= ctx->num_sms &&
          gsv_gpt_ll2_words_per_slot(ctx) * ctx->p.slots * sizeof(uint2) <= gsv_gpt_ll_buffer_bytes(ctx) && (long long)n_steps * (4 * ctx->p.L + 2) < 65000;
 }
 
