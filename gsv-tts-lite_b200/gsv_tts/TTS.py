@@ -1,0 +1,156 @@
+"""``gsv_tts.TTS`` on the B200 backend: the reference's constructor and model-management surface
+(reference gsv_tts/TTS.py:38-147, 1164-1290) over the two native hot paths.
+
+What is here: the constructor keywords, ``load_gpt_model`` / ``load_sovits_model`` / ``unload_*`` /
+``get_*_list``, and ``infer_features`` / ``infer_features_batched``: the hot-path halves of ``infer`` /
+``infer_batched`` (TTS.py:232-247, 695-764) for callers that already hold phoneme ids, BERT features, prompt
+tokens and the vocoder latents.
+
+What is not: the text front end (G2P, language segmentation, BERT / HuBERT / speaker-embedding featurisers)
+and ``enc_p`` are outside the scope of this package.  ``infer`` /
+``infer_stream`` / ``infer_batched`` therefore need a ``frontend`` object that supplies those pieces and raise a
+clear error without one -- they never fall back to a CPU path.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import Loader
+from .Config import Config
+from .Player import AudioClip
+
+log = logging.getLogger(__name__)
+
+
+def cut_text(text: str, max_len: int = 50) -> List[str]:
+    """Sentence cutting on terminal punctuation, merged up to ``max_len`` characters (the reference cuts with
+    pysbd per language, TextProcessor.py:18-59; this is the dependency-free equivalent used by tests)."""
+    import re
+    parts = [p for p in re.split(r"(?<=[。！？!?.;；\n])", text) if p.strip()]
+    out, cur = [], ""
+    for p in parts:
+        if cur and len(cur) + len(p) > max_len:
+            out.append(cur)
+            cur = ""
+        cur += p
+    if cur:
+        out.append(cur)
+    return out
+
+
+class FrontendRequired(RuntimeError):
+    pass
+
+
+class TTS:
+    def __init__(self, gpt_cache=None, sovits_cache=None, models_dir: Optional[str] = None, device=None, dtype=None,
+                 use_flash_attn: bool = False, use_bert: bool = False, auto_bert: bool = True, use_jieba_fast: bool = True,
+                 always_load_cnhubert: bool = False, always_load_sv: bool = False, frontend=None):
+        cfg = Config()
+        if gpt_cache is not None:
+            cfg.gpt_cache = [tuple(x) for x in gpt_cache]
+        if sovits_cache is not None:
+            cfg.sovits_cache = list(sovits_cache)
+        if device is not None:
+            cfg.device = torch.device(device)
+        if dtype is not None:
+            cfg.dtype = getattr(torch, dtype) if isinstance(dtype, str) else dtype
+        cfg.use_flash_attn, cfg.use_bert = use_flash_attn, use_bert
+        if cfg.device.type != "cuda":
+            raise RuntimeError("gsv_tts (B200 backend) needs an sm_100 CUDA device; there is no CPU path")
+        self.tts_config = cfg
+        self.models_dir = models_dir
+        self.frontend = frontend
+        self.gpt_models: Dict[str, Loader.Gpt] = {}
+        self.sovits_models: Dict[str, Loader.Sovits] = {}
+        self.samplerate, self.gpt_hz, self.sovits_hz = cfg.samplerate, cfg.gpt_hz, cfg.sovits_hz
+
+    # ---- model management (TTS.py:1164-1290) -------------------------------------------------------------
+    def load_gpt_model(self, *paths: str):
+        for p in paths:
+            if p not in self.gpt_models:
+                self.gpt_models[p] = Loader.get_gpt_weights(p, self.tts_config)
+                log.info("loaded GPT model %s", p)
+
+    def load_sovits_model(self, *paths: str):
+        for p in paths:
+            if p not in self.sovits_models:
+                self.sovits_models[p] = Loader.get_sovits_weights(p, self.tts_config)
+                log.info("loaded SoVITS model %s", p)
+
+    def unload_gpt_model(self, *paths: str):
+        for p in paths:
+            self.gpt_models.pop(p, None)
+
+    def unload_sovits_model(self, *paths: str):
+        for p in paths:
+            self.sovits_models.pop(p, None)
+
+    def get_gpt_list(self):
+        return list(self.gpt_models)
+
+    def get_sovits_list(self):
+        return list(self.sovits_models)
+
+    def _pick(self, table, path, what):
+        if path is None:
+            if not table:
+                raise RuntimeError(f"no {what} model loaded")
+            path = next(iter(table))
+        if path not in table:
+            raise KeyError(f"{what} model {path!r} is not loaded")
+        return table[path]
+
+    # ---- hot-path entry points ---------------------------------------------------------------------------------
+    @torch.inference_mode()
+    def infer_features(self, phoneme_ids, bert, prompt_tokens, z_p, y_mask, ge, gpt_model: Optional[str] = None,
+                       sovits_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35):
+        """GPT decode then flow + HiFi-GAN for ONE utterance whose features are already computed: returns
+        ``(semantic tokens int64 [1,1,N], AudioClip)``.  ``z_p`` / ``y_mask`` / ``ge`` are what the reference's
+        ``enc_p`` hands to ``flow_dec`` (models.py:404-406)."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        tokens = gpt.infer(phoneme_ids, prompt_tokens, bert, top_k=top_k, top_p=top_p, temperature=temperature,
+                           repetition_penalty=repetition_penalty)
+        audio = voc.flow_dec(z_p, y_mask, ge)[0, 0].float().cpu().numpy()
+        return tokens, self._clip(audio)
+
+    @torch.inference_mode()
+    def infer_features_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence,
+                               gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0):
+        """Continuous-batched GPT stage of ``infer_batched`` (TTS.py:695-703): token lists in request order."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        outs, order = gpt.infer_batched(list(phoneme_ids), list(prompt_tokens), list(bert), top_k=top_k, top_p=top_p,
+                                        temperature=temperature)
+        res = [None] * len(outs)
+        for o, i in zip(outs, order.tolist()):
+            res[i] = o
+        return res
+
+    def _clip(self, audio: np.ndarray, text: str = "") -> AudioClip:
+        peak = float(np.abs(audio).max()) if audio.size else 0.0
+        if peak > 1.0:
+            audio = audio / peak                                    # TTS.py:276-278
+        return AudioClip(audio, self.samplerate, orig_text=text)
+
+    # ---- text entry points need the front end -----------------------------------------------------------------------
+    def _need_frontend(self, name):
+        if self.frontend is None:
+            raise FrontendRequired(
+                f"TTS.{name} needs the text / audio front end (G2P, BERT, HuBERT, speaker embedding, enc_p), which is "
+                "outside this package's scope (SURVEY.md 2 rows 7-9): pass frontend=..., or call infer_features().")
+        return self.frontend
+
+    def infer(self, *args, **kwargs):
+        return self._need_frontend("infer").infer(self, *args, **kwargs)
+
+    def infer_stream(self, *args, **kwargs):
+        return self._need_frontend("infer_stream").infer_stream(self, *args, **kwargs)
+
+    def infer_batched(self, *args, **kwargs):
+        return self._need_frontend("infer_batched").infer_batched(self, *args, **kwargs)

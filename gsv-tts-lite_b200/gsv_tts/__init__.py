@@ -8,10 +8,15 @@ __all__ = ["TTS", "AudioClip", "cut_text"]
 
 
 def __getattr__(name):
+    # `from . import TTS` would re-enter this hook (the submodule and the class share the name)
+    import importlib
     if name in ("TTS", "cut_text"):
-        from . import TTS as _t
-        return getattr(_t, name)
+        mod = importlib.import_module(__name__ + ".TTS")
+        value = getattr(mod, name)
+        globals()[name] = value
+        return value
     if name == "AudioClip":
-        from .Player import AudioClip
-        return AudioClip
+        value = importlib.import_module(__name__ + ".Player").AudioClip
+        globals()[name] = value
+        return value
     raise AttributeError(name)

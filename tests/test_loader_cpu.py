@@ -1,0 +1,88 @@
+"""CPU: checkpoint ingestion of the B200 backend accepts the reference's three formats
+(reference gsv_tts/Loader.py:42-170): upstream .ckpt / .pth (incl. the 2-byte version tag) and
+safetensors directories; the public package surface imports without the front-end dependencies."""
+import json
+import os
+
+import pytest
+import torch
+
+from gsv_tts import Loader, _synthetic as syn
+
+
+def _upstream_gpt_names(sd, n_layer):
+    """Inverse of the remap: Lite names -> upstream GPT-SoVITS names (what a user's .ckpt holds)."""
+    back = {"qkv.weight": "self_attn.in_proj_weight", "qkv.bias": "self_attn.in_proj_bias",
+            "out_proj.weight": "self_attn.out_proj.weight", "out_proj.bias": "self_attn.out_proj.bias",
+            "mlp.0.weight": "linear1.weight", "mlp.0.bias": "linear1.bias",
+            "mlp.2.weight": "linear2.weight", "mlp.2.bias": "linear2.bias"}
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("t2s_transformer.blocks."):
+            _, _, i, tail = k.split(".", 3)
+            out[f"model.h.layers.{i}.{back.get(tail, tail)}"] = v
+        else:
+            out["model." + k] = v
+    return out
+
+
+def test_gpt_ckpt_and_safetensors_dir(tmp_path):
+    cfg = syn.GPT_CONFIG_TINY
+    sd = syn.gpt_state_dict(cfg, 0)
+    ckpt = tmp_path / "s1.ckpt"
+    torch.save({"config": cfg, "weight": _upstream_gpt_names(sd, cfg["model"]["n_layer"])}, ckpt)
+    config, got = Loader.read_gpt_checkpoint(str(ckpt))
+    assert config == cfg and sorted(got) == sorted(sd)
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    # the mirror class accepts exactly this key set (strict load)
+    from gsv_tts.GPT_SoVITS.GPT.t2s_model_b200 import Text2SemanticDecoder
+    Text2SemanticDecoder(config).load_state_dict(got)
+    # safetensors directory (Lite layout, as TTS.to_safetensors writes it)
+    from safetensors.torch import save_file
+    d = tmp_path / "gpt_dir"
+    d.mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(d / "model.safetensors"))
+    (d / "config.json").write_text(json.dumps(cfg))
+    config2, got2 = Loader.read_gpt_checkpoint(str(d))
+    assert config2 == cfg and all(torch.equal(got2[k], sd[k]) for k in sd)
+
+
+@pytest.mark.parametrize("tag,version", [(b"05", "v2Pro"), (b"06", "v2ProPlus"), (None, "v2")])
+def test_sovits_pth_version_tag_and_dir(tmp_path, tag, version):
+    model = dict(syn.SOVITS_MODEL["tiny"], version=version)
+    sd = syn.sovits_flow_dec_state_dict(model, 0)
+    hps = {"data": {"filter_length": 2048, "hop_length": 640, "n_speakers": 300}, "train": {"segment_size": 20480},
+           "model": {k: v for k, v in model.items() if k != "version" or tag is None}}
+    pth = tmp_path / "s2.pth"
+    torch.save({"config": hps, "weight": sd}, pth)
+    if tag is not None:                                    # versioned files carry the tag instead of the zip magic
+        raw = pth.read_bytes()
+        assert raw[:2] == b"PK"
+        pth.write_bytes(tag + raw[2:])
+    got_hps, got_sd, got_version = Loader.read_sovits_checkpoint(str(pth))
+    assert got_version == version and got_hps["model"]["version"] == version
+    assert got_hps["model"]["semantic_frame_rate"] == "25hz"
+    assert all(torch.equal(got_sd[k], sd[k]) for k in sd)
+    from gsv_tts.GPT_SoVITS.SoVITS.models_b200 import FlowDecoder
+    fd = FlowDecoder(**got_hps["model"])
+    fd.load_state_dict(got_sd)
+    assert sorted(fd.state_dict()) == sorted(sd)
+
+
+def test_sovits_rejects_unknown_version(tmp_path):
+    model = dict(syn.SOVITS_MODEL["tiny"])
+    model.pop("version")
+    pth = tmp_path / "old.pth"
+    torch.save({"config": {"model": model}, "weight": {}}, pth)
+    with pytest.raises(ValueError):
+        Loader.read_sovits_checkpoint(str(pth))
+
+
+def test_public_surface_imports_and_refuses_cpu():
+    import gsv_tts
+    from gsv_tts import AudioClip, TTS, cut_text
+    assert cut_text("你好。今天天气不错！Hello there. Bye.", max_len=8) == ["你好。", "今天天气不错！", "Hello there.", " Bye."]
+    clip = AudioClip([0.0, 0.5, -0.5, 0.25], samplerate=4)
+    assert clip.audio_len_s == 1.0 and clip.audio_data.dtype.name == "float32"
+    with pytest.raises(RuntimeError):
+        TTS(device="cpu")
