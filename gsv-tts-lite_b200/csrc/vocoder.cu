@@ -368,6 +368,30 @@ __global__ void to_channel_major_kernel(const float* __restrict__ in32, T* __res
 
 #include "conv_umma.cuh"
 
+// ---- MRF combine: x = (r0 + r1 + r2) / n (models.py:121-127), then the next stage's leaky-ReLU -> 16-bit --------------
+template <typename T>
+__global__ void mrf_combine_kernel(const float* __restrict__ r0, const float* __restrict__ r1, const float* __restrict__ r2, int n_r,
+                                   T* __restrict__ out, long long n8, int act) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float inv = 1.f / (float)n_r;
+  float v[8];
+  const float4 a0 = reinterpret_cast<const float4*>(r0)[2 * i], a1 = reinterpret_cast<const float4*>(r0)[2 * i + 1];
+  v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+  if (n_r > 1) {
+    const float4 b0 = reinterpret_cast<const float4*>(r1)[2 * i], b1 = reinterpret_cast<const float4*>(r1)[2 * i + 1];
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (n_r > 2) {
+    const float4 c0 = reinterpret_cast<const float4*>(r2)[2 * i], c1 = reinterpret_cast<const float4*>(r2)[2 * i + 1];
+    v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w; v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j] * inv, act);
+  reinterpret_cast<uint4*>(out)[i] = pack8<T>(v);
+}
+
 struct Weight {
   const void* w;
   const void* b;
@@ -395,6 +419,9 @@ struct gsv_voc_ctx {
   std::vector<MapCacheEntry> map_cache;   // indexed by call site order within one flow_dec pass
   size_t op_index;
   int use_umma;                           // GSV_VOC_IMPL=cuda disables the tensor-core path (A/B checks)
+  cudaStream_t side[2];                   // the three ResBlocks of an MRF stage run as three concurrent chains
+  cudaEvent_t ev_fork, ev_join[2];
+  int mrf_streams;                        // GSV_VOC_MRF=serial: one chain after the other on the caller's stream
   int num_sms;
 };
 
@@ -584,8 +611,8 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
     for (int i = 0; i < D.n_ups; ++i) { spf *= D.upsample_rates[i]; ch /= 2; maxn = spf * ch > maxn ? spf * ch : maxn; }
   }
   const size_t BT = (size_t)B * Tn;
-  float *z32, *h32, *a32, *o32, *condF, *condD, *X0, *XJ, *ACC;
-  T *zT, *hT, *uT, *oT, *geT, *preT, *XA0, *XAJ, *TA, *NEXT;
+  float *z32, *h32, *a32, *o32, *condF, *condD, *X0, *XJ[4];
+  T *zT, *hT, *uT, *oT, *geT, *preT, *XA0, *XAJ[4], *TA[4], *NEXT;
   auto carve = [&](Arena& ar) {
     z32 = ar.take<float>(BT * C);
     zT = ar.take<T>(BT * C);
@@ -601,10 +628,11 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
     preT = ar.take<T>(BT * C0);
     X0 = ar.take<float>(BT * maxn);
     XA0 = ar.take<T>(BT * maxn);
-    XJ = ar.take<float>(BT * maxn);
-    XAJ = ar.take<T>(BT * maxn);
-    TA = ar.take<T>(BT * maxn);
-    ACC = ar.take<float>(BT * maxn);
+    for (int j = 0; j < NK; ++j) {     // one residual stream / activated copy / temporary per ResBlock chain
+      XJ[j] = ar.take<float>(BT * maxn);
+      XAJ[j] = ar.take<T>(BT * maxn);
+      TA[j] = ar.take<T>(BT * maxn);
+    }
     NEXT = ar.take<T>(BT * maxn);
   };
   Arena dry{nullptr, 0, 0};
@@ -749,9 +777,17 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
       if ((rc = launch_conv<T>(ctx, a, st))) return rc;
     }
     ch = cout; Tcur = Tnext;
+    // MRF: the NK ResBlocks read the same x and are independent until their mean: chain j runs on its own stream
+    // (chain 0 on the caller's), so the critical path of a stage is 6 convolutions instead of 18
+    const bool fork = ctx->mrf_streams && NK >= 2 && NK <= 3;
+    if (fork) {
+      GSV_CUDA(cudaEventRecord(ctx->ev_fork, st));
+      for (int j = 1; j < NK; ++j) GSV_CUDA(cudaStreamWaitEvent(ctx->side[j - 1], ctx->ev_fork, 0));
+    }
     for (int j = 0; j < NK; ++j) {
       const int k = D.resblock_kernel_sizes[j];
       const std::string R = "dec.resblocks." + std::to_string(i * NK + j) + ".";
+      cudaStream_t sj = (fork && j > 0) ? ctx->side[j - 1] : st;
       for (int c = 0; c < 3; ++c) {
         const int dl = D.resblock_dilations[j][c];
         Weight w1, w2;
@@ -759,30 +795,34 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
         if ((rc = W(R + "convs2." + std::to_string(c), w2))) return rc;
         {   // xt = lrelu(conv_d(lrelu(x)))
           ConvArgs<T> a = base_args();
-          a.in = c == 0 ? XA0 : XAJ; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k; a.dil = dl;
+          a.in = c == 0 ? XA0 : XAJ[j]; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k; a.dil = dl;
           a.w = reinterpret_cast<const T*>(w1.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w1.b);
-          a.outT = TA; a.act = ACT_LRELU_01; a.o_ld = ch;
-          if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+          a.outT = TA[j]; a.act = ACT_LRELU_01; a.o_ld = ch;
+          if ((rc = launch_conv<T>(ctx, a, sj))) return rc;
         }
-        {   // x = conv_1(xt) + x
+        {   // x = conv_1(xt) + x   (the last one leaves the ResBlock's output in its fp32 stream)
           ConvArgs<T> a = base_args();
-          a.in = TA; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k;
+          a.in = TA[j]; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k;
           a.w = reinterpret_cast<const T*>(w2.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w2.b);
-          a.res32 = c == 0 ? X0 : XJ; a.o_ld = ch;
-          if (c < 2) {
-            a.out32 = XJ; a.outT = XAJ; a.act = ACT_LRELU_01;
-          } else {
-            // xs += resblock(x); after the third block x = xs / 3 (models.py:121-127), then the next
-            // stage's leaky-ReLU (0.1) or the final one (default slope 0.01, models.py:128)
-            a.acc32 = ACC; a.acc_init = j == 0;
-            if (j == NK - 1) {
-              a.acc_scale = 1.f / (float)NK;
-              a.outT = NEXT; a.act = (i == D.n_ups - 1) ? ACT_LRELU_001 : ACT_LRELU_01;
-            }
-          }
-          if ((rc = launch_conv<T>(ctx, a, st))) return rc;
+          a.res32 = c == 0 ? X0 : XJ[j]; a.o_ld = ch;
+          a.out32 = XJ[j];
+          if (c < 2) { a.outT = XAJ[j]; a.act = ACT_LRELU_01; }
+          if ((rc = launch_conv<T>(ctx, a, sj))) return rc;
         }
       }
+      if (fork && j > 0) {
+        GSV_CUDA(cudaEventRecord(ctx->ev_join[j - 1], sj));
+        GSV_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[j - 1], 0));
+      }
+    }
+    {
+      // x = mean of the ResBlock outputs (summed in order 0, 1, 2), then the next stage's leaky-ReLU (0.1) or the final
+      // one (default slope 0.01, models.py:128)
+      const long long n8 = (long long)BT * (Tcur / Tn) * ch / 8;
+      mrf_combine_kernel<T><<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(XJ[0], NK > 1 ? XJ[1] : nullptr, NK > 2 ? XJ[2] : nullptr, NK,
+                                                                         NEXT, n8, (i == D.n_ups - 1) ? ACT_LRELU_001 : ACT_LRELU_01);
+      ctx->launches += 1;
+      GSV_CHECK_LAUNCH();
     }
     stage_in = NEXT;
     // NEXT is consumed by the next stage's upsampling before it is written again (same stream)
@@ -818,12 +858,22 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
   GSV_ARG(ctx != nullptr);
   ctx->dims = *dims;
   ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->debug_z = nullptr; ctx->launches = 0;
+  ctx->side[0] = ctx->side[1] = nullptr; ctx->ev_fork = nullptr; ctx->ev_join[0] = ctx->ev_join[1] = nullptr;
   ctx->op_index = 0;
   {
     const char* e = getenv("GSV_VOC_IMPL");
     ctx->use_umma = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
   }
   GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  {
+    const char* e = getenv("GSV_VOC_MRF");
+    ctx->mrf_streams = (e && strcmp(e, "serial") == 0) ? 0 : 1;
+  }
+  for (int i = 0; i < 2; ++i) {
+    GSV_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    GSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+  }
+  GSV_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   GSV_CUDA(cudaMalloc(&ctx->zero_bias, 8192));
   GSV_CUDA(cudaMemset(ctx->zero_bias, 0, 8192));
   *out = ctx;
@@ -840,6 +890,11 @@ extern "C" int gsv_voc_destroy(gsv_voc_ctx* ctx) {
   if (!ctx) return GSV_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->zero_bias) cudaFree(ctx->zero_bias);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
   return GSV_OK;
 }
