@@ -329,7 +329,7 @@ def extras(gpt, voc, dev, dtype, lib, N, syn):
         m.load_state_dict(syn.gpt_state_dict(syn.GPT_CONFIG, 0))
         m.initialize_runtime(dtype, dev, [(32, 512)])
         g = torch.Generator().manual_seed(7)
-        for B in (8, 32):
+        for B in (4, 8, 32):
             m._release_all()
             for s in range(B):
                 samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0,
@@ -362,6 +362,20 @@ def extras(gpt, voc, dev, dtype, lib, N, syn):
         out["vocoder_b8_100f_ms"] = ms
         out["vocoder_audio_s_per_s"] = 8 * 2.0 / (ms / 1e3)
         out["vocoder_tflops"] = 8 * 100 * (813.1e6 + 14.2e6) / (ms / 1e3) / 1e12
+        # a quarter of BASELINE config 5 (10 s of tokens, batch 64): batch 16 x 500 frames
+        z = torch.randn(16, 192, 500, device=dev, dtype=dtype)
+        mk = torch.ones(16, 1, 500, device=dev, dtype=dtype)
+        ge = torch.randn(16, 1024, 1, device=dev, dtype=dtype)
+        voc.flow_dec(z, mk, ge)
+        torch.cuda.synchronize()
+        e0.record()
+        voc.flow_dec(z, mk, ge)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["vocoder_b16_500f_ms"] = ms
+        out["vocoder_b16_500f_tflops"] = 16 * 500 * (813.1e6 + 14.2e6) / (ms / 1e3) / 1e12
+        out["vocoder_b16_500f_audio_s_per_s"] = 16 * 10.0 / (ms / 1e3)
     except Exception as e:      # extras must never break the headline line
         out["error"] = f"{type(e).__name__}: {e}"
     return out
