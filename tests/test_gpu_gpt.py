@@ -294,3 +294,26 @@ def test_eight_slots_batched_matches_two_slots(dev):
     same = sum(outs[8][r] == outs[2][r] for r in range(n))
     print("requests identical across kernels:", same, "/", n)
     assert same >= n - 2
+
+
+def test_minimal_prompt_and_cache_edge(dev):
+    """Smallest legal prompt (one phoneme, one prompt token) and a cache that fills up: decode stops by itself when
+    kv_len reaches the bucket length (t2s_model.py:425-428 has no larger bucket to roll into), tokens stay in range,
+    and an over-long prompt is rejected instead of overflowing the cache."""
+    from tests import gpu_harness as H
+    from gsv_tts import _native as N
+    cfg = syn.GPT_CONFIG_TINY
+    sd = syn.gpt_state_dict(cfg, 0, 0.0)
+    S = 32
+    m = H.build_gpt(cfg, sd, torch.float16, dev, [(1, S)])
+    m.debug_seed = 5
+    x = torch.randint(0, 732, (1, 1))
+    y = torch.randint(0, 1024, (1, 1))
+    out = m.infer(x, y, torch.zeros(1, 1, 1024), force_steps=200)      # EOS masked: only the cache can stop it
+    n = out.shape[-1]
+    assert out.shape[:2] == (1, 1) and 0 < n <= S - 2
+    assert int(out.min()) >= 0 and int(out.max()) < cfg["model"]["EOS"]
+    m._read(1)
+    assert int(m._h_active[0]) == 0
+    with pytest.raises(N.NativeError):
+        m.infer(torch.randint(0, 732, (1, 20)), torch.randint(0, 1024, (1, 12)), torch.zeros(1, 20, 1024))

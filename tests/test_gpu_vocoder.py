@@ -73,3 +73,28 @@ def test_masked_tail_equals_zero_latent(dev):
     zero = fd.flow_dec(z_p, torch.zeros_like(mask), ge)
     # generator receptive field is < 12 frames per side at 50 Hz
     assert torch.equal(a[..., 40 * 640: 60 * 640], zero[..., 40 * 640: 60 * 640])
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 127, 129])
+def test_edge_lengths_match_oracle(dev, T):
+    """Lengths around the kernels' tile edges (one frame; one below / above the 128-row tensor-core tile after
+    upsampling) and ragged masks: waveform of the tiny model vs the fp32 oracle on the same rounded weights."""
+    from tests import gpu_harness as H
+    from oracle.vocoder_oracle import VocoderOracle
+    dtype = torch.float16
+    fd, sd, model = H.build_vocoder("tiny", dtype, dev)
+    g = torch.Generator().manual_seed(100 + T)
+    B = 2
+    z_p = torch.randn(B, 192, T, generator=g)
+    mask = torch.ones(B, 1, T)
+    if T > 2:
+        mask[1, :, T - T // 3:] = 0                        # ragged second row
+    ge = torch.randn(B, model["gin_channels"], 1, generator=g)
+    audio = fd.flow_dec(z_p.to(dev), mask.to(dev), ge.to(dev)).float().cpu()
+    assert audio.shape == (B, 1, T * 640) and torch.isfinite(audio).all()
+    vo = VocoderOracle(H.folded_rounded_vocoder_sd(sd, dtype), model)
+    zin, gin_ = z_p.to(dtype).float(), ge.to(dtype).float()
+    want = vo.generator(vo.flow_reverse(zin, mask, gin_) * mask, gin_)
+    err = float((audio - want).abs().max())
+    print("T", T, "max|audio - oracle|", err)
+    assert err < TOL_AUDIO[dtype]
