@@ -39,6 +39,7 @@ constexpr int NT = GSV_DECODE_THREADS;   // 512
 constexpr int NWARP = NT / 32;           // 16
 constexpr int MAXB = 4;
 constexpr int QKV_ROWS = 3 * GSV_HEAD_DIM;   // 96 rows of Wqkv per head
+constexpr int WQ_PAD = 8;                    // elements of padding per staged Wqkv row: conflict-free mma fragment loads
 
 __device__ __forceinline__ int split_pos(int k, int K) {
   const int ch = k >> 3, j = k & 7;
@@ -200,12 +201,28 @@ __device__ __forceinline__ void ll_wait4p(const uint2* base, const int (&off)[4]
   for (int e = 0; e < 4; ++e) out[e] = __uint_as_float(w[e].x);
 }
 
+// m16n8k16 tensor-core tile, 16-bit inputs, fp32 accumulate: D = A(16x16, row) * B(16x8, col) + C
+template <typename T> struct Mma16816;
+template <> struct Mma16816<__nv_bfloat16> {
+  static __device__ __forceinline__ void run(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+template <> struct Mma16816<__half> {
+  static __device__ __forceinline__ void run(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+
 struct L2Shared {
   int sl[MAXB], kv[MAXB], nb;
   float q[GSV_HEAD_DIM], knew[GSV_HEAD_DIM], vnew[GSV_HEAD_DIM];
   float wpart[NWARP][GSV_HEAD_DIM + 2];
   float wscale[NWARP];
   float outv[MAXB][NWARP];      // this phase's outputs, gathered for one coalesced publication by warp 0
+  float qkv_part[2][QKV_ROWS];  // attention CTAs: K-half partial sums of the tensor-core QKV projection
 };
 
 template <typename T, int NCH, int NB>
@@ -228,7 +245,9 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
   constexpr int kScratch = kAct > GSV_SAMPLE_SMEM_FLOATS ? kAct : GSV_SAMPLE_SMEM_FLOATS;
   T* wq = reinterpret_cast<T*>(smem + ((kScratch + 3) & ~3));
   // per-warp weight slots [3 units][NWARP][D/8] uint4 (one D-wide row segment each)
-  uint4* wslot = reinterpret_cast<uint4*>(wq + (size_t)QKV_ROWS * D);
+  constexpr int LDW = D + WQ_PAD;
+  T* xbf = wq + (size_t)QKV_ROWS * LDW;                      // the attention CTA's normalised input in the storage type [D]
+  uint4* wslot = reinterpret_cast<uint4*>(xbf + D);
   uint4* const slot_o = wslot + (size_t)(0 * NWARP + warp) * (D / 8);
   uint4* const slot_1 = wslot + (size_t)(1 * NWARP + warp) * (D / 8);
   uint4* const slot_2 = wslot + (size_t)(2 * NWARP + warp) * (D / 8);
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
     for (int i = tid; i < QKV_ROWS * (D / 8); i += NT) {
       const int rr = i / (D / 8), c = i - rr * (D / 8);
       const int grow = (rr >> 5) * D + att_h * GSV_HEAD_DIM + (rr & 31);
-      cp_async16(wq + (size_t)rr * D + c * 8, Wqkv + (size_t)grow * D + c * 8);
+      cp_async16(wq + (size_t)rr * LDW + c * 8, Wqkv + (size_t)grow * D + c * 8);
     }
   }
   cp_async_commit();
@@ -360,20 +379,14 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
         const T* kb = reinterpret_cast<const T*>(p.kc) + head_base + sub * 8;
         const T* vb = reinterpret_cast<const T*>(p.vc) + head_base + sub * 8;
         uint4 kr0 = make_uint4(0, 0, 0, 0), vr0 = kr0, kr1 = kr0, vr1 = kr0;
-        unsigned short bq[QKV_ROWS / NWARP];
-#pragma unroll
-        for (int it = 0; it < QKV_ROWS / NWARP; ++it) bq[it] = 0;
+        uint4 kr2 = kr0, vr2 = kr0;
+        unsigned short bq = 0;                              // thread r < 96: bias of staged row r (q | k | v of this head)
         if (att) {
-          if (lane == 0) {
-#pragma unroll
-            for (int it = 0; it < QKV_ROWS / NWARP; ++it) {
-              const int rr = warp + it * NWARP;
-              bq[it] = ld_raw16(Bqkv + (size_t)l * 3 * D + (rr >> 5) * D + att_h * GSV_HEAD_DIM + (rr & 31));
-            }
-          }
-          const int p0 = warp * 8 + pg, p1 = p0 + NWARP * 8;
+          if (tid < QKV_ROWS) bq = ld_raw16(Bqkv + (size_t)l * 3 * D + (tid >> 5) * D + att_h * GSV_HEAD_DIM + (tid & 31));
+          const int p0 = warp * 8 + pg, p1 = p0 + NWARP * 8, p2 = p1 + NWARP * 8;
           if (p0 < kvn) { kr0 = ld_cg16(kb + (size_t)p0 * GSV_HEAD_DIM); vr0 = ld_cg16(vb + (size_t)p0 * GSV_HEAD_DIM); }
           if (p1 < kvn) { kr1 = ld_cg16(kb + (size_t)p1 * GSV_HEAD_DIM); vr1 = ld_cg16(vb + (size_t)p1 * GSV_HEAD_DIM); }
+          if (p2 < kvn) { kr2 = ld_cg16(kb + (size_t)p2 * GSV_HEAD_DIM); vr2 = ld_cg16(vb + (size_t)p2 * GSV_HEAD_DIM); }
           if (tid == 0 && l + 1 < L && kvn > 0) {
             // next layer's K/V stream of this (slot, head) into L2
             const size_t nxt = (size_t)p.slots * H * S * GSV_HEAD_DIM;
@@ -432,29 +445,50 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
           }
         }
         if (att) {
-          // ---- q, k, v of this head: warp w computes rows w, w+16, ... of the 96 staged rows
+          // ---- q, k, v of this head on the tensor cores: [96 x D] staged weight rows times the normalised input
+          //      (rounded to the storage type, as the reference's LayerNorm output is).  Warp w < 12: 16-row tile
+          //      w % 6, K half w / 6; the input sits in column 0 of the 16x8 B operand (lanes 0..3).
+          if (warp == 0) {
 #pragma unroll
-          for (int it = 0; it < QKV_ROWS / NWARP; ++it) {
-            const int rr = warp + it * NWARP;
-            uint4 wr[NCH];
-            const uint4* src = reinterpret_cast<const uint4*>(wq + (size_t)rr * D);
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) wr[c] = src[c * 32 + lane];
-            float a = dot_regs<T, NCH>(wr, xq);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) {
-              const int which = rr >> 5, c = rr & 31;
-              const float v = a + raw16_to_f<T>(bq[it]);
-              if (which == 0) {
-                sh.q[c] = v * (rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f);
-              } else {
-                // the reference attends over the 16-bit cache entry it has just written
-                const T t16 = Elem<T>::from_f(v);
-                (which == 1 ? sh.knew : sh.vnew)[c] = Elem<T>::to_f(t16);
-                T* cache = reinterpret_cast<T*>(which == 1 ? p.kc : p.vc);
-                cache[head_base + (size_t)kvn * GSV_HEAD_DIM + c] = t16;
+            for (int c = 0; c < NCH; ++c)
+              *reinterpret_cast<uint4*>(xbf + c * 256 + lane * 8) = pack8<T>(&xq[c * 8]);
+          }
+          __syncthreads();
+          if (warp < 12) {
+            const int mt = warp % 6, kh = warp / 6;
+            const int g = lane >> 2, t = lane & 3;
+            const T* a_lo = wq + (size_t)(16 * mt + g) * LDW + 2 * t;
+            const T* a_hi = a_lo + 8 * LDW;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int ks = 0; ks < D / 32; ++ks) {
+              const int k0 = kh * (D / 2) + ks * 16;
+              const unsigned a0 = *reinterpret_cast<const unsigned*>(a_lo + k0), a1 = *reinterpret_cast<const unsigned*>(a_hi + k0);
+              const unsigned a2 = *reinterpret_cast<const unsigned*>(a_lo + k0 + 8), a3 = *reinterpret_cast<const unsigned*>(a_hi + k0 + 8);
+              unsigned b0 = 0u, b1 = 0u;
+              if (g == 0) {
+                b0 = *reinterpret_cast<const unsigned*>(xbf + k0 + 2 * t);
+                b1 = *reinterpret_cast<const unsigned*>(xbf + k0 + 8 + 2 * t);
               }
+              Mma16816<T>::run(acc, a0, a1, a2, a3, b0, b1);
+            }
+            if (t == 0) {                                  // column 0 of the accumulator tile: rows g and g + 8
+              sh.qkv_part[kh][16 * mt + g] = acc[0];
+              sh.qkv_part[kh][16 * mt + g + 8] = acc[2];
+            }
+          }
+          __syncthreads();
+          if (tid < QKV_ROWS) {
+            const int which = tid >> 5, c = tid & 31;
+            const float v = (sh.qkv_part[0][tid] + sh.qkv_part[1][tid]) + raw16_to_f<T>(bq);
+            if (which == 0) {
+              sh.q[c] = v * (rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f);
+            } else {
+              // the reference attends over the 16-bit cache entry it has just written
+              const T t16 = Elem<T>::from_f(v);
+              (which == 1 ? sh.knew : sh.vnew)[c] = Elem<T>::to_f(t16);
+              T* cache = reinterpret_cast<T*>(which == 1 ? p.kc : p.vc);
+              cache[head_base + (size_t)kvn * GSV_HEAD_DIM + c] = t16;
             }
           }
           __syncthreads();
@@ -465,7 +499,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
             for (int i = tid; i < QKV_ROWS * (D / 8); i += NT) {
               const int rr = i / (D / 8), c = i - rr * (D / 8);
               const int grow = (rr >> 5) * D + att_h * GSV_HEAD_DIM + (rr & 31);
-              cp_async16(wq + (size_t)rr * D + c * 8, src + (size_t)grow * D + c * 8);
+              cp_async16(wq + (size_t)rr * LDW + c * 8, src + (size_t)grow * D + c * 8);
             }
           }
           // ---- attention over cached positions [0, kvn) + the new one; 4 lanes per position, 8 positions per warp pass
@@ -480,8 +514,8 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
           for (int base = warp * 8; base < kvn; base += NWARP * 8, ++pass) {
             const int pos = base + pg;
             const bool ok = pos < kvn;
-            uint4 kr = pass == 0 ? kr0 : kr1, vr = pass == 0 ? vr0 : vr1;
-            if (pass > 1 && ok) {
+            uint4 kr = pass == 0 ? kr0 : (pass == 1 ? kr1 : kr2), vr = pass == 0 ? vr0 : (pass == 1 ? vr1 : vr2);
+            if (pass > 2 && ok) {
               kr = ld_cg16(kb + (size_t)pos * GSV_HEAD_DIM);
               vr = ld_cg16(vb + (size_t)pos * GSV_HEAD_DIM);
             }
@@ -782,7 +816,7 @@ int launch_ll2_nb(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   else return GSV_ERR_ARG;
   const size_t act = (size_t)(NB * ctx->p.F + 3 * NB * ctx->p.d);
   const size_t scratch = act > (size_t)GSV_SAMPLE_SMEM_FLOATS ? act : (size_t)GSV_SAMPLE_SMEM_FLOATS;
-  const size_t bytes = ((scratch + 3) & ~(size_t)3) * sizeof(float) + (size_t)QKV_ROWS * ctx->p.d * 2 +
+  const size_t bytes = ((scratch + 3) & ~(size_t)3) * sizeof(float) + (size_t)QKV_ROWS * (ctx->p.d + WQ_PAD) * 2 + (size_t)ctx->p.d * 2 +
                        (size_t)3 * NWARP * ctx->p.d * 2;       // + Wqkv rows + per-warp weight slots
   GSV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   GptParams p = ctx->p;
