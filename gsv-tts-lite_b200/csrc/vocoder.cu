@@ -392,6 +392,16 @@ __global__ void mrf_combine_kernel(const float* __restrict__ r0, const float* __
   reinterpret_cast<uint4*>(out)[i] = pack8<T>(v);
 }
 
+// ---- Flip folded into the weights (modules.py:504-511): a coupling layer that sees channel-reversed data is the same
+//      layer with its 1x1 `pre` reversed along Cin and its `post` (weight rows and bias) reversed along Cout -------------
+template <typename T>
+__global__ void flip_rows_or_cols_kernel(const T* __restrict__ in, T* __restrict__ out, int rows, int cols, int flip_cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  out[i] = flip_cols ? in[r * cols + (cols - 1 - c)] : in[(rows - 1 - r) * cols + c];
+}
+
 struct Weight {
   const void* w;
   const void* b;
@@ -422,6 +432,7 @@ struct gsv_voc_ctx {
   cudaStream_t side[2];                   // the three ResBlocks of an MRF stage run as three concurrent chains
   cudaEvent_t ev_fork, ev_join[2];
   int mrf_streams;                        // GSV_VOC_MRF=serial: one chain after the other on the caller's stream
+  std::vector<void*> owned;               // library-owned copies of weights (channel-reversed pre / post of odd flows)
   int num_sms;
 };
 
@@ -690,7 +701,7 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
     if ((rc = W(P + "pre", w))) return rc;
     {
       ConvArgs<T> a = base_args();
-      a.in = zT; a.in_ld = C; a.in_off = x0_off; a.in_rev = odd; a.Tin = a.Tout = Tn; a.Cin = half; a.Cout = Hc;
+      a.in = zT; a.in_ld = C; a.in_off = x0_off; a.in_rev = 0; a.Tin = a.Tout = Tn; a.Cin = half; a.Cout = Hc;   // reversal folded into the weights
       a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)Hc * half; a.bias = reinterpret_cast<const T*>(w.b);
       a.mask = mask; a.out32 = h32; a.outT = hT; a.o_ld = Hc;
       if ((rc = launch_conv<T>(ctx, a, st))) return rc;
@@ -741,7 +752,7 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
       a.in = oT; a.in_ld = Hc; a.Tin = a.Tout = Tn; a.Cin = Hc; a.Cout = half;
       a.w = reinterpret_cast<const T*>(w.w); a.w_tap = (long long)half * Hc; a.bias = reinterpret_cast<const T*>(w.b);
       a.res32 = z32; a.res_sign = -1.f; a.mask = mask; a.out32 = z32; a.outT = zT;
-      a.o_ld = C; a.o_off = x1_off; a.o_rev = odd;
+      a.o_ld = C; a.o_off = x1_off; a.o_rev = 0;
       if ((rc = launch_conv<T>(ctx, a, st))) return rc;
     }
   }
@@ -882,6 +893,42 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
 
 extern "C" int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias) {
   GSV_ARG(ctx && name && dev_weight);
+  // flows applied after an odd number of Flips (reverse order: flow f sees NF - f flips): fold the channel reversal
+  // into `pre` (along Cin) and `post` (along Cout, bias too), so that no convolution reads or writes reversed channels
+  int f2 = -1;
+  char tail[16] = "";
+  if (sscanf(name, "flow.flows.%d.%15s", &f2, tail) == 2 && (strcmp(tail, "pre") == 0 || strcmp(tail, "post") == 0)) {
+    const int f = f2 / 2, NF = ctx->dims.n_flows;
+    if (((NF - f) & 1) != 0) {
+      const bool pre = strcmp(tail, "pre") == 0;
+      const int half = ctx->dims.inter_channels / 2, Hc = ctx->dims.hidden_channels;
+      const int rows = pre ? Hc : half, cols = pre ? half : Hc;          // [Cout][Cin], one tap
+      const size_t esz = 2;
+      void* wcopy = nullptr;
+      GSV_CUDA(cudaMalloc(&wcopy, (size_t)rows * cols * esz));
+      ctx->owned.push_back(wcopy);
+      const int n = rows * cols;
+      if (ctx->dims.dtype == GSV_F16)
+        flip_rows_or_cols_kernel<__half><<<(n + 255) / 256, 256>>>(reinterpret_cast<const __half*>(dev_weight), reinterpret_cast<__half*>(wcopy), rows, cols, pre ? 1 : 0);
+      else
+        flip_rows_or_cols_kernel<__nv_bfloat16><<<(n + 255) / 256, 256>>>(reinterpret_cast<const __nv_bfloat16*>(dev_weight), reinterpret_cast<__nv_bfloat16*>(wcopy), rows, cols, pre ? 1 : 0);
+      const void* bcopy = dev_bias;
+      if (!pre && dev_bias) {
+        void* b2 = nullptr;
+        GSV_CUDA(cudaMalloc(&b2, (size_t)rows * esz));
+        ctx->owned.push_back(b2);
+        if (ctx->dims.dtype == GSV_F16)
+          flip_rows_or_cols_kernel<__half><<<(rows + 255) / 256, 256>>>(reinterpret_cast<const __half*>(dev_bias), reinterpret_cast<__half*>(b2), rows, 1, 0);
+        else
+          flip_rows_or_cols_kernel<__nv_bfloat16><<<(rows + 255) / 256, 256>>>(reinterpret_cast<const __nv_bfloat16*>(dev_bias), reinterpret_cast<__nv_bfloat16*>(b2), rows, 1, 0);
+        bcopy = b2;
+      }
+      GSV_CHECK_LAUNCH();
+      GSV_CUDA(cudaDeviceSynchronize());
+      ctx->weights[std::string(name)] = Weight{wcopy, bcopy};
+      return GSV_OK;
+    }
+  }
   ctx->weights[std::string(name)] = Weight{dev_weight, dev_bias};
   return GSV_OK;
 }
@@ -890,6 +937,7 @@ extern "C" int gsv_voc_destroy(gsv_voc_ctx* ctx) {
   if (!ctx) return GSV_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->zero_bias) cudaFree(ctx->zero_bias);
+  for (void* q : ctx->owned) cudaFree(q);
   for (int i = 0; i < 2; ++i) {
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);

@@ -159,10 +159,10 @@ def main():
         make_gpt_batched("tiny_batched", syn.GPT_CONFIG_TINY, n_req=7, slots=4, max_seq=256, eos_boost=6.0)
     if "voc" in which:
         make_vocoder("tiny", "tiny", B=2, T=20, masked_tail=5)
-        make_vocoder("tiny_ge_t", "tiny", B=1, T=16, masked_tail=0, ge_per_frame=True, with16=False)
+        make_vocoder("tiny_ge_t", "tiny", B=1, T=16, masked_tail=0, ge_per_frame=True)
         make_vocoder("v2pro", "v2Pro", B=1, T=12, masked_tail=0)
-        make_vocoder("v2proplus", "v2ProPlus", B=1, T=8, masked_tail=0, with16=False)
-        make_vocoder("v2", "v2", B=1, T=8, masked_tail=0, with16=False)
+        make_vocoder("v2proplus", "v2ProPlus", B=1, T=8, masked_tail=0)
+        make_vocoder("v2", "v2", B=1, T=8, masked_tail=0)
 
 
 if __name__ == "__main__":

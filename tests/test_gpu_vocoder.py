@@ -9,10 +9,10 @@ pytestmark = pytest.mark.gpu
 
 # north_star: waveform within 1e-3 max-abs of the reference PyTorch path in fp16.
 #  * kernel arithmetic (same fp16-rounded weights, fp32 oracle): < 1e-3, asserted for every case;
-#  * against the reference's fp32 golden: < 1e-3, except where the golden also records the reference's
-#    own fp16 output (audio_fp16): that path is 1.2e-3..1.3e-3 away from its fp32 path on these inputs
-#    (16-bit weight storage alone costs that much), so there the bound is "no further from fp32 than the
-#    reference's fp16 path is".  bf16 ~1e-2 for scale.
+#  * against the reference's fp32 golden: every golden also records the reference's OWN fp16 output
+#    (audio_fp16), which is 1.18e-3..1.52e-3 away from its fp32 output on these inputs (16-bit weight
+#    storage alone costs that much), so the bound is max(1e-3, that distance): "no further from the fp32
+#    reference than the reference's fp16 path is".  bf16 ~1e-2 for scale.
 TOL_AUDIO = {torch.float16: 1e-3, torch.bfloat16: 1.2e-2}
 TOL_Z = {torch.float16: 4e-3, torch.bfloat16: 4e-2}
 
