@@ -216,6 +216,34 @@ template <> struct Mma16816<__half> {
   }
 };
 
+// Experiment (GSV_LL2_WARPPOLL=n): only n warps of a CTA poll an exchanged D-vector (D/n/32 words per lane, all in
+// flight, re-polling only what is missing) and scatter it into shared memory; the other warps wait at the phase's
+// __syncthreads.  Fewer polling warps = fewer requests queued on the lines being written.
+#ifdef GSV_LL2_WARPPOLL
+template <int D>
+__device__ __forceinline__ void poll_vec(const uint2* src, unsigned tag, float* dst) {
+  constexpr int PW = GSV_LL2_WARPPOLL, PER = D / PW / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= PW) return;
+  uint2 w[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) w[i] = make_uint2(0u, ~tag);
+  bool ok;
+  do {
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      if (w[i].y != tag) {
+        w[i] = ll_peek(src + warp * (D / PW) + lane + 32 * i);
+        ok = ok && (w[i].y == tag);
+      }
+    }
+  } while (!ok);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) dst[split_pos(warp * (D / PW) + lane + 32 * i, D)] = __uint_as_float(w[i].x);
+}
+#endif
+
 struct L2Shared {
   int sl[MAXB], kv[MAXB], nb;
   float q[GSV_HEAD_DIM], knew[GSV_HEAD_DIM], vnew[GSV_HEAD_DIM];
@@ -411,6 +439,9 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
 #pragma unroll
         for (int s = 0; s < NB; ++s) {
           raw[s] = 0.f;
+#ifdef GSV_LL2_WARPPOLL
+          if (s < nb) poll_vec<D>(l == 0 ? ll_xin + (size_t)sh.sl[s] * D : ll_y2 + (size_t)sh.sl[s] * PADW, tag, xa + s * D);
+#else
           if (s < nb && tid < D) {
             if (l == 0) {
               raw[s] = ll_wait(ll_xin + (size_t)sh.sl[s] * D + tid, tag);
@@ -419,9 +450,15 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
             }
             xa[s * D + split_pos(tid, D)] = raw[s];
           }
+#endif
         }
         cp_async_wait<3>();                                 // this layer's Wqkv rows (requested one layer ago)
         __syncthreads();
+#ifdef GSV_LL2_WARPPOLL
+#pragma unroll
+        for (int s = 0; s < NB; ++s)
+          if (s < nb && tid < D) raw[s] = xa[s * D + split_pos(tid, D)];
+#endif
         mark(p, 40);
         // ---- residual copy x = LN2(raw) (or raw for layer 0): every warp derives the statistics itself
         float xq[NCH * 8];                                  // attention CTAs keep their slot's normalised operand
@@ -589,7 +626,11 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
         if (o_ok && lane == 0) braw = ld_raw16(Bo + (size_t)l * D + o_t);
 #pragma unroll
         for (int s = 0; s < NB; ++s)
+#ifdef GSV_LL2_WARPPOLL
+          if (s < nb) poll_vec<D>(ll_att + (size_t)sh.sl[s] * D, tag, xb + s * F);
+#else
           if (s < nb && tid < D) xb[s * F + split_pos(tid, D)] = ll_wait(ll_att + (size_t)sh.sl[s] * D + tid, tag);
+#endif
         __syncthreads();
         mark(p, 41);
         cp_async_wait<3>();
@@ -631,12 +672,21 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_ll2_kernel(const GptParams p
 #pragma unroll
         for (int s = 0; s < NB; ++s) {
           raw[s] = 0.f;
+#ifdef GSV_LL2_WARPPOLL
+          if (s < nb) poll_vec<D>(ll_y1 + (size_t)sh.sl[s] * D, tag, xa + s * D);
+#else
           if (s < nb && tid < D) {
             raw[s] = ll_wait(ll_y1 + (size_t)sh.sl[s] * D + tid, tag);
             xa[s * D + split_pos(tid, D)] = raw[s];
           }
+#endif
         }
         __syncthreads();
+#ifdef GSV_LL2_WARPPOLL
+#pragma unroll
+        for (int s = 0; s < NB; ++s)
+          if (s < nb && tid < D) raw[s] = xa[s * D + split_pos(tid, D)];
+#endif
         mark(p, 42);
         cp_async_wait<3>();
         uint4 w_1[NCH];
