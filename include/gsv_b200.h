@@ -97,8 +97,9 @@ typedef struct {
 typedef struct gsv_gpt_ctx gsv_gpt_ctx;
 
 /* Allocates KV cache [L][slots][H][S][32] x2 and all step buffers (initialize_runtime,
- * t2s_model.py:210-298: one K root, one V root, static step I/O).  No graph capture is needed
- * here: the decode kernel is one persistent launch per call. */
+ * t2s_model.py:210-298: one K root, one V root, static step I/O).  Nothing is captured here: decode is one
+ * persistent launch per call for up to 24 live sequences, and one CUDA graph per step (captured on first
+ * use) above that. */
 int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w, gsv_gpt_ctx** out);
 int gsv_gpt_destroy(gsv_gpt_ctx* ctx);
 
@@ -109,10 +110,12 @@ int gsv_gpt_destroy(gsv_gpt_ctx* ctx);
 int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
                     const void* dev_bert, const gsv_gpt_sampling* samp, void* stream);
 
-/* Run up to n_steps decode steps over every active slot in ONE persistent kernel launch:
- * T2STransformer.decode_next_token x n (t2s_model.py:129-143) + ar_predict_layer + sample +
- * next-token embedding (:430-456, :637-653, :727-728), with per-slot stop at EOS / full cache
- * evaluated on the device (no host sync per token, cf. :426, :451-453). */
+/* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
+ * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
+ * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).
+ * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..24 -> one
+ * thread-block cluster per sequence, more -> tcgen05 linears + small kernels replayed from a CUDA graph.
+ * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | gemm | barrier; GSV_GPT_GEMM = cuda. */
 int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream);
 
 /* Copy slot state to host memory (asynchronously on `stream`; caller synchronises):
@@ -177,7 +180,9 @@ int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out);
 int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias);
 int gsv_voc_destroy(gsv_voc_ctx* ctx);
 
-/* o = dec(flow(z_p, mask, ge, reverse) * mask, g=ge).
+/* o = dec(flow(z_p, mask, ge, reverse) * mask, g=ge).  Every convolution with >= 16 input channels runs on the
+ * tcgen05 implicit-GEMM kernel (csrc/conv_umma.cuh); GSV_VOC_IMPL=cuda selects the CUDA-core kernels and
+ * GSV_VOC_MRF=serial / GSV_PDL=0 switch off stream-level and launch-level overlap (A-B only).
  * dev_z_p [B][192][T] T (torch layout, as handed to flow_dec), dev_mask [B][T] T,
  * dev_ge [B][gin][Tg] T with Tg == 1 or Tg == T (batched path, reference TTS.py:740-744),
  * dev_out [B][T*samples_per_frame] T.  Scratch is grown on demand and cached in ctx. */
