@@ -70,6 +70,7 @@ struct gsv_gpt_ctx {
   void* step_graph_exec;          // cudaGraphExec_t of one batched decode step
   int force_gemm;                 // GSV_DECODE_IMPL=gemm: multi-kernel tensor-core step for any live count
   int use_cl;                     // GSV_DECODE_IMPL=cl: cluster-per-sequence kernel
+  int use_cln;                    // GSV_DECODE_IMPL=cl2 / cl4: clusters serving 2 / 4 sequences each
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
   int force_ll1;                  // GSV_DECODE_IMPL=ll1: first-generation small-batch kernel (A/B checks)
@@ -97,3 +98,4 @@ int gsv_gpt_decode_ll2_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cud
 int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
 bool gsv_gpt_cl_supported(const gsv_gpt_ctx* ctx, int live_slots);
 int gsv_gpt_decode_cl_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
+int gsv_gpt_decode_cln_launch(gsv_gpt_ctx* ctx, int live_slots, int nb, int n_steps, cudaStream_t st);

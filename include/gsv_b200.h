@@ -113,9 +113,9 @@ int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, co
 /* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
  * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
  * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).
- * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..24 -> one
- * thread-block cluster per sequence, more -> tcgen05 linears + small kernels replayed from a CUDA graph.
- * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | gemm | barrier; GSV_GPT_GEMM = cuda. */
+ * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..28 -> thread-block
+ * clusters serving 1, 2 or 4 sequences each, more -> tcgen05 linears + small kernels replayed from a CUDA graph.
+ * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | cl2 | cl4 | gemm | barrier; GSV_GPT_GEMM = cuda. */
 int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream);
 
 /* Copy slot state to host memory (asynchronously on `stream`; caller synchronises):
