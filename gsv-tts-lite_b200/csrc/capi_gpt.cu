@@ -209,8 +209,17 @@ extern "C" int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream) {
   return GSV_OK;
 }
 
+// The batched step's CUDA graph bakes the parameter block into its kernel nodes: drop it whenever a hook changes it.
+static void invalidate_step_graph(gsv_gpt_ctx* ctx) {
+  if (ctx->step_graph_exec) {
+    cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(ctx->step_graph_exec));
+    ctx->step_graph_exec = nullptr;
+  }
+}
+
 extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows) {
   GSV_ARG(ctx);
+  invalidate_step_graph(ctx);
   ctx->p.noise = dev_noise;
   ctx->p.noise_rows = dev_noise ? n_rows : 0;
   return GSV_OK;
@@ -218,6 +227,7 @@ extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n
 
 extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n) {
   GSV_ARG(ctx);
+  invalidate_step_graph(ctx);
   ctx->p.forced = dev_forced;
   ctx->p.n_forced = dev_forced ? n : 0;
   return GSV_OK;
@@ -225,6 +235,7 @@ extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, i
 
 extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows) {
   GSV_ARG(ctx);
+  invalidate_step_graph(ctx);
   ctx->p.trace = dev_rows;
   ctx->p.trace_max = dev_rows ? max_rows : 0;
   return GSV_OK;
@@ -234,6 +245,7 @@ extern "C" int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx) { return ctx ? ctx->la
 
 extern "C" int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta) {
   GSV_ARG(ctx);
+  invalidate_step_graph(ctx);
   ctx->p.prof = reinterpret_cast<long long*>(dev_records);
   ctx->p.prof_max = dev_records ? max_records : 0;
   ctx->p.prof_cta = cta;
