@@ -219,7 +219,7 @@ static void invalidate_step_graph(gsv_gpt_ctx* ctx) {
 
 extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows) {
   GSV_ARG(ctx);
-  invalidate_step_graph(ctx);
+  if (ctx->p.noise != dev_noise || ctx->p.noise_rows != (dev_noise ? n_rows : 0)) invalidate_step_graph(ctx);
   ctx->p.noise = dev_noise;
   ctx->p.noise_rows = dev_noise ? n_rows : 0;
   return GSV_OK;
@@ -227,7 +227,7 @@ extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n
 
 extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n) {
   GSV_ARG(ctx);
-  invalidate_step_graph(ctx);
+  if (ctx->p.forced != dev_forced || ctx->p.n_forced != (dev_forced ? n : 0)) invalidate_step_graph(ctx);
   ctx->p.forced = dev_forced;
   ctx->p.n_forced = dev_forced ? n : 0;
   return GSV_OK;
@@ -235,7 +235,7 @@ extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, i
 
 extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows) {
   GSV_ARG(ctx);
-  invalidate_step_graph(ctx);
+  if (ctx->p.trace != dev_rows || ctx->p.trace_max != (dev_rows ? max_rows : 0)) invalidate_step_graph(ctx);
   ctx->p.trace = dev_rows;
   ctx->p.trace_max = dev_rows ? max_rows : 0;
   return GSV_OK;
