@@ -109,7 +109,7 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
     ctx->force_ll2 = (e && strcmp(e, "ll2") == 0) ? 1 : 0;
     ctx->force_gemm = (e && strcmp(e, "gemm") == 0) ? 1 : 0;
     ctx->use_cl = (e && strcmp(e, "cl") == 0) ? 1 : 0;
-    ctx->use_cln = (e && strcmp(e, "cl2") == 0) ? 2 : ((e && strcmp(e, "cl4") == 0) ? 4 : 0);
+    ctx->use_cln = (e && strcmp(e, "cl2") == 0) ? 2 : ((e && strcmp(e, "cl4") == 0) ? 4 : ((e && strcmp(e, "cl8") == 0) ? 8 : 0));
     const char* g = getenv("GSV_GPT_GEMM");
     ctx->use_umma_linear = (g && strcmp(g, "cuda") == 0) ? 0 : 1;
     ctx->umma = gsv_umma_cache_create(ctx->num_sms);
@@ -162,6 +162,7 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   // -> 1: ll; 2..7: one cluster per sequence; 8..14: two per cluster; 15..28: four per cluster; more: the
   //    multi-kernel step (GSV_DECODE_IMPL overrides).
   const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_ll2 || ctx->force_gemm;
+  if (ctx->use_cln == 8 && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (ctx->use_cln && gsv_gpt_cl_supported(ctx, live)) return gsv_gpt_decode_cln_launch(ctx, live, ctx->use_cln, n_steps, (cudaStream_t)stream);
   if (!explicit_impl && !ctx->use_cl && gsv_gpt_cl_supported(ctx, live)) {
     if (live >= 8 && live <= 14) return gsv_gpt_decode_cln_launch(ctx, live, 2, n_steps, (cudaStream_t)stream);

@@ -99,3 +99,4 @@ int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
 bool gsv_gpt_cl_supported(const gsv_gpt_ctx* ctx, int live_slots);
 int gsv_gpt_decode_cl_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
 int gsv_gpt_decode_cln_launch(gsv_gpt_ctx* ctx, int live_slots, int nb, int n_steps, cudaStream_t st);
+int gsv_gpt_decode_cl8_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);

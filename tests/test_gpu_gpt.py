@@ -232,7 +232,7 @@ def test_batched_slots_match_single_slot_logits(dev):
             assert len(alone) <= 30 and len(together[r]) <= 30
 
 
-@pytest.mark.parametrize("impl", ["ll1", "ll2", "cl", "cl2", "cl4", "gemm", "barrier"])
+@pytest.mark.parametrize("impl", ["ll1", "ll2", "cl", "cl2", "cl4", "cl8", "gemm", "barrier"])
 @pytest.mark.parametrize("name,cfg", [("tiny", syn.GPT_CONFIG_TINY), ("full", syn.GPT_CONFIG)])
 def test_every_decode_kernel_teacher_forced_logits(dev, monkeypatch, impl, name, cfg):
     """Every decode implementation behind gsv_gpt_decode (flag-in-data ll / ll2, cluster-per-sequence,
