@@ -124,6 +124,8 @@ extern "C" int gsv_gpt_destroy(gsv_gpt_ctx* ctx) {
   for (int i = 0; i < ctx->n_allocs; ++i) cudaFree(ctx->all_allocs[i]);
   if (ctx->step_graph_exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(ctx->step_graph_exec));
   gsv_umma_cache_destroy(ctx->umma);
+  if (ctx->cl8_pack) cudaFree(ctx->cl8_pack);
+  if (ctx->cl8_head_pack) cudaFree(ctx->cl8_head_pack);
   delete ctx;
   return GSV_OK;
 }

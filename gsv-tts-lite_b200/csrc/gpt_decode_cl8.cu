@@ -2,18 +2,24 @@
 //
 // Same arithmetic as the other decode kernels (reference t2s_model.py:67-105, 129-143, 442-456) and the same
 // skeleton as gpt_decode_cl.cu / gpt_decode_cln.cu (one CTA per attention head, push exchanges completing on the
-// receiver's mbarrier, per-warp bulk-copy weight ring).  What changes: the cluster's live sequences are the N = 8
-// columns of mma.sync m16n8k16 tiles whose M rows are the warp's weight rows, so a weight row that has been streamed
-// from HBM is multiplied with all eight inputs by ONE instruction stream (gpt_decode_cln.cu pays the full CUDA-core
-// dot product per sequence: 1.8x / 2.85x the step time for 2 / 4 sequences).  Consequences:
-//   * activations cross CTAs in the storage type (bf16 / fp16 pairs, as the reference rounds them) and land directly
-//     in the layout the B operand is read from ([sequence][k], rows padded by 8 elements: conflict-free fragment
-//     loads); the residual stream (y1, y2, next input) stays fp32;
-//   * weight units sit in padded ring slots (row stride D*2 + 16 bytes) so that the A fragments of the 2..4 rows of
-//     a batch come from different banks;
-//   * LayerNorm of sequence n is done once per CTA by warp n; attention of sequence n by warps 2n and 2n+1;
-//   * results are staged per warp and pushed with 8- / 16-byte st.async (one per (target CTA, sequence)).
-// The accumulator fragment gives thread (g = lane / 4, t = lane % 4) row g of the batch for sequences 2t and 2t + 1.
+// receiver's mbarrier).  What changes: the cluster's live sequences are the N = 8 columns of mma.sync m16n8k16 tiles
+// whose M = 16 rows are weight rows, so a weight row that has been streamed from HBM is multiplied with all eight
+// inputs by one instruction (gpt_decode_cln.cu pays the full CUDA-core dot product per sequence).
+//
+// Weights are re-tiled ONCE (first launch, cl8_pack_*_kernel) into the order the kernel consumes them: per (layer,
+// head CTA) twelve CHUNKS of 32 rows x D columns (q, k, v rows of the head; its 32 out-proj rows; 4 x 32 MLP-up
+// rows; its 32 MLP-down rows, one K-quarter per chunk), each chunk stored in mma A-FRAGMENT order
+// [M-tile][k-step][lane][16 B].  Measured reasons (tools/cl8_timeline.py, tools/ubench/bulk_bw.cu): (1) an SM ingests
+// 1 KB bulk copies at 20 GB/s but >= 8 KB copies at ~200 GB/s -- a chunk is ONE 32 KB copy into a 3-slot ring shared
+// by the CTA; (2) legacy mma.sync issues at about one per 16 cycles per sub-partition, so tiles must use all 16 rows
+// -- a row-per-warp mapping that fills 2..4 of them spends 9 us per layer in the tensor pipe; (3) fragment order makes
+// the A operand one conflict-free 16-byte shared load per lane and k-step.
+// Per chunk the 16 warps split (M-tile, K-eighth); partial accumulators meet in shared memory and warps 0..7 (warp n
+// = sequence n, lane = row) finish bias / residual / activation.  The head is 33 more chunks (vocabulary rows padded
+// to 32) dealt round-robin to the CTAs.  Activations cross CTAs in the storage type (as the reference rounds them)
+// and land in the layout the B operand is read from ([sequence][k], rows padded by 8 elements); the residual stream
+// (y1, y2, next input) stays fp32.  LayerNorm of sequence n is done once per CTA by warp n; attention of sequence n
+// by warps 2n and 2n+1.
 #include <type_traits>
 
 #include "gpt_cluster_common.cuh"
@@ -21,8 +27,10 @@
 namespace {
 
 constexpr int NB8 = 8;                   // sequences per cluster
-constexpr int RING8 = 6;                 // weight units in flight per warp (batches are at most 4 units)
+constexpr int NSLOT = 3;                 // chunk ring slots
+constexpr int CHUNKS = 12;               // chunks per layer
 constexpr int XPAD = 8;                  // padding elements per staged activation row
+constexpr int RW = 176;                  // floats per warp in the partial-accumulator buffer: [8 sequences][20] (+16: bank shift between M-tiles)
 
 template <typename T> struct Mma16816;
 template <> struct Mma16816<__nv_bfloat16> {
@@ -62,37 +70,91 @@ struct Cl8Shared {
   float alive[NB8];                         // pushed by the sampler CTAs together with the next inputs
   int alive_i;
   int slot[NB8], kv[NB8];
-  uint64_t wbar[NWARP][RING8];
+  uint64_t cbar[NSLOT];                     // chunk ring: bytes landed
   uint64_t xbar[4];                         // inboxes: 0 inA (fp32: xin / y1 / y2), 1 att, 2 h, 3 logits (CTA n for sequence n)
 };
 
+// One thread per 16-byte fragment element: lane (g = lane / 4, t = lane % 4) of k-step ks of M-tile `tile` holds
+// A[g][k0..k0+1], A[g+8][k0..], A[g][k0+8..], A[g+8][k0+8..] with k0 = 16 ks + 2 t.
+template <typename T>
+__global__ void cl8_pack_layers_kernel(const T* __restrict__ Wqkv, const T* __restrict__ Wo, const T* __restrict__ W1,
+                                       const T* __restrict__ W2, uint4* __restrict__ out, int L, int H, int D) {
+  const size_t total = (size_t)L * H * CHUNKS * 2 * (D / 16) * 32;
+  const int F = 4 * D;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int lane = (int)(r & 31); r >>= 5;
+    const int ks = (int)(r % (D / 16)); r /= (D / 16);
+    const int tile = (int)(r & 1); r >>= 1;
+    const int c = (int)(r % CHUNKS); r /= CHUNKS;
+    const int rank = (int)(r % H);
+    const int l = (int)(r / H);
+    const int g = lane >> 2, t = lane & 3, r0 = tile * 16 + g, k0 = ks * 16 + 2 * t;
+    const T* base; size_t ld;
+    if (c < 3) { base = Wqkv + ((size_t)l * 3 * D + (size_t)c * D + rank * GSV_HEAD_DIM) * D; ld = D; }
+    else if (c == 3) { base = Wo + ((size_t)l * D + rank * GSV_HEAD_DIM) * D; ld = D; }
+    else if (c < 8) { base = W1 + ((size_t)l * F + rank * (4 * GSV_HEAD_DIM) + (c - 4) * 32) * D; ld = D; }
+    else { base = W2 + ((size_t)l * D + rank * GSV_HEAD_DIM) * F + (size_t)(c - 8) * D; ld = F; }
+    uint4 v;
+    v.x = *reinterpret_cast<const unsigned*>(base + (size_t)r0 * ld + k0);
+    v.y = *reinterpret_cast<const unsigned*>(base + (size_t)(r0 + 8) * ld + k0);
+    v.z = *reinterpret_cast<const unsigned*>(base + (size_t)r0 * ld + k0 + 8);
+    v.w = *reinterpret_cast<const unsigned*>(base + (size_t)(r0 + 8) * ld + k0 + 8);
+    out[idx] = v;
+  }
+}
+template <typename T>
+__global__ void cl8_pack_head_kernel(const T* __restrict__ Wh, uint4* __restrict__ out, int n_chunks, int V, int D) {
+  const size_t total = (size_t)n_chunks * 2 * (D / 16) * 32;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int lane = (int)(r & 31); r >>= 5;
+    const int ks = (int)(r % (D / 16)); r /= (D / 16);
+    const int tile = (int)(r & 1); r >>= 1;
+    const int hc = (int)r;
+    const int g = lane >> 2, t = lane & 3, r0 = hc * 32 + tile * 16 + g, k0 = ks * 16 + 2 * t;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 < V) {
+      v.x = *reinterpret_cast<const unsigned*>(Wh + (size_t)r0 * D + k0);
+      v.z = *reinterpret_cast<const unsigned*>(Wh + (size_t)r0 * D + k0 + 8);
+    }
+    if (r0 + 8 < V) {
+      v.y = *reinterpret_cast<const unsigned*>(Wh + (size_t)(r0 + 8) * D + k0);
+      v.w = *reinterpret_cast<const unsigned*>(Wh + (size_t)(r0 + 8) * D + k0 + 8);
+    }
+    out[idx] = v;
+  }
+}
+
 template <typename T, int NCH>
-__global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p, const int n_steps) {
+__global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p, const int n_steps, const unsigned char* __restrict__ pack,
+                                                                const unsigned char* __restrict__ hpack) {
   extern __shared__ __align__(16) float smem[];
   __shared__ Cl8Shared sh;
   constexpr int D = NCH * 256, F = 4 * D;
   constexpr int LDX = D + XPAD, LDH = F + XPAD;          // element strides of the staged activation rows
-  constexpr int USTRIDE = D * 2 + 16;                     // bytes between weight ring slots
+  constexpr int KSW = D / 128;                            // k-steps of a chunk per warp (K split eight ways)
+  constexpr unsigned CHUNK_BYTES = 64u * D;               // 2 M-tiles x D/16 k-steps x 512 B
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;                  // mma fragment coordinates
   const int H = p.H, L = p.L, V = p.V, S = p.S;
   const unsigned rank = cluster_rank();                  // = head index
   const int cid = blockIdx.x / H;                         // cluster index: serves live sequences [cid*8, cid*8 + 8)
 
-  // shared memory: inA[8][D] fp32 | xa[8][LDX] T | attb[8][LDX] T | hb[8][LDH] T | xin_s[D] | sampler scratch (+ logits) | weight ring
+  // shared memory: inA[8][D] fp32 | xa[8][LDX] T | attb[8][LDX] T | hb[8][LDH] T | xin_s[D] | sampler scratch (+ logits) |
+  //                red[2][16][RW] | ystage[8][32] fp32 | hstage[8][128] T | chunk ring
   float* inA = smem;
   T* xa = reinterpret_cast<T*>(inA + NB8 * D);
   T* attb = xa + NB8 * LDX;
   T* hb = attb + NB8 * LDX;
   float* xin_s = reinterpret_cast<float*>(hb + NB8 * LDH);
   float* samp = xin_s + D;
-  unsigned char* ring = reinterpret_cast<unsigned char*>(samp + ((GSV_SAMPLE_SMEM_FLOATS + 3) & ~3)) + (size_t)warp * RING8 * USTRIDE;
+  float* red = samp + ((GSV_SAMPLE_SMEM_FLOATS + 3) & ~3);
+  float* ystage = red + 2 * NWARP * RW;
+  T* hstage = reinterpret_cast<T*>(ystage + NB8 * GSV_HEAD_DIM);
+  unsigned char* ring = reinterpret_cast<unsigned char*>(hstage + NB8 * 4 * GSV_HEAD_DIM);
+  const int mtile = warp & 1, kq = warp >> 1;             // this warp's share of a chunk
 
-  const T* const Wqkv = reinterpret_cast<const T*>(p.w_qkv);
-  const T* const Wo = reinterpret_cast<const T*>(p.w_o);
-  const T* const W1 = reinterpret_cast<const T*>(p.w_1);
-  const T* const W2 = reinterpret_cast<const T*>(p.w_2);
-  const T* const Wh = reinterpret_cast<const T*>(p.w_head);
   const T* const Bqkv = reinterpret_cast<const T*>(p.b_qkv);
   const T* const Bo = reinterpret_cast<const T*>(p.b_o);
   const T* const B1 = reinterpret_cast<const T*>(p.b_1);
@@ -120,78 +182,66 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
   if (livemask == 0) return;
   int na = __popc(livemask);
 
-  // ---- weight unit sequence of this warp: 6 QKV rows, 2 O rows, 8 MLP-up rows, then the MLP-down rows quarter by
-  //      quarter (row 0 quarter q, row 1 quarter q) so that a batch of 2 units is one K-quarter of both rows ----
-  auto unit_src = [&](int l, int u) -> const T* {
-    if (u < 6) {
-      const int rr = warp + NWARP * u;
-      const int row = (rr >> 5) * D + (int)rank * GSV_HEAD_DIM + (rr & 31);
-      return Wqkv + ((size_t)l * 3 * D + row) * D;
-    }
-    u -= 6;
-    if (u < 2) return Wo + ((size_t)l * D + rank * GSV_HEAD_DIM + warp * 2 + u) * D;
-    u -= 2;
-    if (u < 8) return W1 + ((size_t)l * F + rank * (4 * GSV_HEAD_DIM) + warp * 8 + u) * D;
-    u -= 8;
-    return W2 + ((size_t)l * D + rank * GSV_HEAD_DIM + warp * 2 + (u & 1)) * F + (size_t)(u >> 1) * D;
+  // ---- chunk ring: the CTA consumes, per token, CHUNKS chunks per layer and then its head chunks rank, rank + H, ... ----
+  const int n_hchunks = ((V + 31) >> 5);
+  const int HC = (n_hchunks - (int)rank + H - 1) / H;      // head chunks of this CTA
+  int iss_l = 0, iss_c = 0;                                // next chunk to request (thread 0)
+  int ck_slot = 0;
+  unsigned ck_par = 0;
+  auto issue_chunk = [&](int slot_i) {
+    const unsigned char* src = iss_l < L ? pack + (((size_t)iss_l * H + rank) * CHUNKS + iss_c) * CHUNK_BYTES
+                                         : hpack + (size_t)((int)rank + iss_c * H) * CHUNK_BYTES;
+    mbar_expect_tx(&sh.cbar[slot_i], CHUNK_BYTES);
+    bulk_g2s(ring + (size_t)slot_i * CHUNK_BYTES, src, CHUNK_BYTES, &sh.cbar[slot_i]);
+    ++iss_c;
+    if (iss_l < L) {
+      if (iss_c == CHUNKS) { iss_c = 0; ++iss_l; if (iss_l == L && HC == 0) iss_l = 0; }
+    } else if (iss_c == HC) { iss_c = 0; iss_l = 0; }
   };
-  int iss_l = 0, iss_u = 0, use_i = 0;
-  unsigned use_par = 0;
-  constexpr unsigned UNIT_BYTES = D * (unsigned)sizeof(T);
-  auto issue_at = [&](int slot_i, int ahead) {
-    int u = iss_u + ahead, l = iss_l;
-    if (u >= UNITS_PER_LAYER) { u -= UNITS_PER_LAYER; l = l + 1 == L ? 0 : l + 1; }
-    mbar_expect_tx(&sh.wbar[warp][slot_i], UNIT_BYTES);
-    bulk_g2s(ring + (size_t)slot_i * USTRIDE, unit_src(l, u), UNIT_BYTES, &sh.wbar[warp][slot_i]);
+  // the current chunk, once its bytes have landed
+  auto chunk_wait = [&]() -> const unsigned char* {
+    mbar_wait(&sh.cbar[ck_slot], ck_par);
+    return ring + (size_t)ck_slot * CHUNK_BYTES;
   };
-  auto advance_cursor = [&](int n) {
-    iss_u += n;
-    if (iss_u >= UNITS_PER_LAYER) { iss_u -= UNITS_PER_LAYER; iss_l = iss_l + 1 == L ? 0 : iss_l + 1; }
+  // after a __syncthreads() that follows the last read of the current chunk: refill its slot, move on
+  auto chunk_release = [&]() {
+    if (tid == 0) issue_chunk(ck_slot);
+    if (++ck_slot == NSLOT) { ck_slot = 0; ck_par ^= 1u; }
   };
-  // One batch of NV (<= 4) weight units against a staged operand: acc[0], acc[1] += row g of the batch (g < NV) times
-  // sequences 2t, 2t+1 over K = D starting at element `koff` of every sequence's row (row stride `ldb`).
-  auto mma_batch = [&](auto nv_tag, const T* xb, int ldb, int koff, float (&acc)[4]) {
-    constexpr int NV = decltype(nv_tag)::value;
+  // this warp's share of a chunk: M-tile `mtile`, k-steps [kq * KSW, +KSW), against the staged operand rows xb[n][koff + k]
+  auto mma_chunk = [&](const unsigned char* chunk, const T* xb, int ldb, int koff, float (&acc)[4]) {
+    const uint4* ap = reinterpret_cast<const uint4*>(chunk) + ((size_t)(mtile * (D / 16) + kq * KSW) * 32 + lane);
+    const T* brow = xb + (size_t)g * ldb + koff + kq * KSW * 16 + 2 * t;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int si = use_i + i;
-      unsigned par = use_par;
-      if (si >= RING8) { si -= RING8; par ^= 1u; }
-      mbar_wait(&sh.wbar[warp][si], par);
-    }
-    int sg = use_i + (g < NV ? g : 0);
-    if (sg >= RING8) sg -= RING8;
-    const T* arow = reinterpret_cast<const T*>(ring + (size_t)sg * USTRIDE) + 2 * t;
-    const T* brow = xb + (size_t)g * ldb + koff + 2 * t;
-#pragma unroll 4
-    for (int ks = 0; ks < D / 16; ++ks) {
-      unsigned a0 = 0u, a2 = 0u;
-      if (g < NV) {
-        a0 = *reinterpret_cast<const unsigned*>(arow + ks * 16);
-        a2 = *reinterpret_cast<const unsigned*>(arow + ks * 16 + 8);
-      }
+    for (int ks = 0; ks < KSW; ++ks) {
+      const uint4 a = ap[ks * 32];
       const unsigned b0 = *reinterpret_cast<const unsigned*>(brow + ks * 16);
       const unsigned b1 = *reinterpret_cast<const unsigned*>(brow + ks * 16 + 8);
-      Mma16816<T>::run(acc, a0, 0u, a2, 0u, b0, b1);
+      Mma16816<T>::run(acc, a.x, a.y, a.z, a.w, b0, b1);
     }
-    // release: refill the NV slots with the units RING8 ahead
-    __syncwarp();
-    if (lane < NV) {
-      int si = use_i + lane;
-      if (si >= RING8) si -= RING8;
-      issue_at(si, lane);
-    }
-    advance_cursor(NV);
-    use_i += NV;
-    if (use_i >= RING8) { use_i -= RING8; use_par ^= 1u; }
   };
-  if (lane == 0) {
-    for (int i = 0; i < RING8; ++i) mbar_init(&sh.wbar[warp][i], 1);
-    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&sh.xbar[i], 1); }
+  // partial accumulators: warp w writes rb[w][sequence][row of its M-tile]; thread (warp n < 8, lane = chunk row) sums
+  int rsel = 0;
+  auto red_write = [&](const float (&acc)[4]) {
+    float* w = red + (size_t)(rsel * NWARP + warp) * RW;
+    w[(2 * t) * 20 + g] = acc[0];
+    w[(2 * t + 1) * 20 + g] = acc[1];
+    w[(2 * t) * 20 + g + 8] = acc[2];
+    w[(2 * t + 1) * 20 + g + 8] = acc[3];
+  };
+  auto red_read = [&]() -> float {
+    const float* rb = red + (size_t)rsel * NWARP * RW + (size_t)(lane >> 4) * RW + warp * 20 + (lane & 15);
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += rb[(size_t)2 * q * RW];
+    return v;
+  };
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) mbar_init(&sh.cbar[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.xbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < RING8; ++i) issue_at(i, i);
+    for (int i = 0; i < NSLOT; ++i) issue_chunk(i);
   }
-  advance_cursor(RING8);
   __syncwarp();
   unsigned parA = 0, parT = 0, parH = 0, parL = 0;
   if (tid == 0) {
@@ -266,43 +316,36 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
           l2_prefetch(reinterpret_cast<const T*>(p.kc) + hb2, bytes);
           l2_prefetch(reinterpret_cast<const T*>(p.vc) + hb2, bytes);
         }
-        // biases of the rows this thread finishes: batch 0 -> it = g (g < 4), batch 1 -> it = 4 + g (g < 2)
-        float bq0 = 0.f, bq1 = 0.f;
-        {
-          const int rr0 = warp + NWARP * (g < 4 ? g : 0), rr1 = warp + NWARP * (4 + (g < 2 ? g : 0));
-          bq0 = Elem<T>::to_f(Bqkv[(size_t)l * 3 * D + (rr0 >> 5) * D + rank * GSV_HEAD_DIM + (rr0 & 31)]);
-          bq1 = Elem<T>::to_f(Bqkv[(size_t)l * 3 * D + (rr1 >> 5) * D + rank * GSV_HEAD_DIM + (rr1 & 31)]);
-        }
+        const bool epi = warp < NB8 && ((livemask >> warp) & 1u);      // this warp finishes sequence `warp`, lane = chunk row
+        float bq[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) bq[u] = Elem<T>::to_f(Bqkv[(size_t)l * 3 * D + u * D + rank * GSV_HEAD_DIM + lane]);
         if (l > 0) { mbar_wait(&sh.xbar[0], parA); parA ^= 1u; }      // y2 of the previous layer has arrived
         stage_ln(l > 0, &sh.xres[0][0]);
         __syncthreads();                                // xa staged by the LayerNorm warps; inA fully read
         if (l > 0 && tid == 0) mbar_expect_tx(&sh.xbar[0], (unsigned)na * D * 4u);     // re-arm inA for this layer's y1
-        // q, k, v rows: batch 0 = rows it 0..3, batch 1 = rows it 4..5 of this warp
-#pragma unroll
-        for (int bi = 0; bi < 2; ++bi) {
+        // chunks q, k, v: the 32 rows of this head
+#pragma unroll 1
+        for (int u = 0; u < 3; ++u) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          if (bi == 0) mma_batch(std::integral_constant<int, 4>{}, xa, LDX, 0, acc);
-          else mma_batch(std::integral_constant<int, 2>{}, xa, LDX, 0, acc);
-          const int nv = bi == 0 ? 4 : 2;
-          if (g < nv) {
-            const int rr = warp + NWARP * (bi * 4 + g), which = rr >> 5, c = rr & 31;
-            const float bias = bi == 0 ? bq0 : bq1;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int n = 2 * t + j;
-              if (!((livemask >> n) & 1u)) continue;
-              const float v = acc[j] + bias;
-              if (which == 0) {
-                sh.qs[n][c] = v * (rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f);
-              } else {
-                const T t16 = Elem<T>::from_f(v);       // the reference attends over the 16-bit cache entry it has just written
-                (which == 1 ? sh.kn : sh.vn)[n][c] = Elem<T>::to_f(t16);
-                T* cache = reinterpret_cast<T*>(which == 1 ? p.kc : p.vc);
-                const size_t hbase = ((size_t)(l * p.slots + sh.slot[n]) * H + rank) * (size_t)S * GSV_HEAD_DIM;
-                cache[hbase + (size_t)sh.kv[n] * GSV_HEAD_DIM + c] = t16;
-              }
+          mma_chunk(chunk_wait(), xa, LDX, 0, acc);
+          red_write(acc);
+          __syncthreads();
+          chunk_release();
+          if (epi) {
+            const int n = warp, c = lane;
+            const float v = red_read() + (u == 0 ? bq[0] : (u == 1 ? bq[1] : bq[2]));
+            if (u == 0) {
+              sh.qs[n][c] = v * (rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f);
+            } else {
+              const T t16 = Elem<T>::from_f(v);         // the reference attends over the 16-bit cache entry it has just written
+              (u == 1 ? sh.kn : sh.vn)[n][c] = Elem<T>::to_f(t16);
+              T* cache = reinterpret_cast<T*>(u == 1 ? p.kc : p.vc);
+              const size_t hbase = ((size_t)(l * p.slots + sh.slot[n]) * H + rank) * (size_t)S * GSV_HEAD_DIM;
+              cache[hbase + (size_t)sh.kv[n] * GSV_HEAD_DIM + c] = t16;
             }
           }
+          rsel ^= 1;
         }
         __syncthreads();                                // q / k / v of every sequence staged
         mark(p, 50);
@@ -324,34 +367,40 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
             float q[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) q[j] = sh.qs[n][sub * 8 + j];
-            uint4 krn = make_uint4(0, 0, 0, 0), vrn = krn;
-            if (pb + pg < pe) {
-              krn = ld_cg16(kb + (size_t)(pb + pg) * GSV_HEAD_DIM);
-              vrn = ld_cg16(vb + (size_t)(pb + pg) * GSV_HEAD_DIM);
+            // three passes of K/V rows in flight (L2 latency >> the arithmetic of a pass)
+            uint4 kq3[3], vq3[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              kq3[i] = make_uint4(0, 0, 0, 0); vq3[i] = kq3[i];
+              const int pp = pb + i * 8 + pg;
+              if (pp < pe) { kq3[i] = ld_cg16(kb + (size_t)pp * GSV_HEAD_DIM); vq3[i] = ld_cg16(vb + (size_t)pp * GSV_HEAD_DIM); }
             }
 #pragma unroll 1
-            for (int base = pb; base < pe; base += 8) {
-              const int pos = base + pg;
-              const bool ok = pos < pe;
-              const uint4 kr = krn, vr = vrn;
-              if (pos + 8 < pe) {
-                krn = ld_cg16(kb + (size_t)(pos + 8) * GSV_HEAD_DIM);
-                vrn = ld_cg16(vb + (size_t)(pos + 8) * GSV_HEAD_DIM);
-              }
-              float kf[8], vf[8], sc_ = 0.f;
-              unpack8<T>(kr, kf);
-              unpack8<T>(vr, vf);
+            for (int base = pb; base < pe; base += 24) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) sc_ = fmaf(q[j], kf[j], sc_);
-              sc_ += __shfl_xor_sync(0xffffffffu, sc_, 1);
-              sc_ += __shfl_xor_sync(0xffffffffu, sc_, 2);
-              if (ok) {
-                const float mn = fmaxf(mg, sc_);
-                const float sc = exp2f(mg - mn), pr = exp2f(sc_ - mn);
-                lsum = fmaf(lsum, sc, pr);
+              for (int i = 0; i < 3; ++i) {
+                const int pos = base + i * 8 + pg;
+                const bool ok = pos < pe;
+                const uint4 kr = kq3[i], vr = vq3[i];
+                if (pos + 24 < pe) {
+                  kq3[i] = ld_cg16(kb + (size_t)(pos + 24) * GSV_HEAD_DIM);
+                  vq3[i] = ld_cg16(vb + (size_t)(pos + 24) * GSV_HEAD_DIM);
+                }
+                float kf[8], vf[8], sc_ = 0.f;
+                unpack8<T>(kr, kf);
+                unpack8<T>(vr, vf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, vf[j], o[j] * sc);
-                mg = mn;
+                for (int j = 0; j < 8; ++j) sc_ = fmaf(q[j], kf[j], sc_);
+                sc_ += __shfl_xor_sync(0xffffffffu, sc_, 1);
+                sc_ += __shfl_xor_sync(0xffffffffu, sc_, 2);
+                if (ok) {
+                  const float mn = fmaxf(mg, sc_);
+                  const float sc = exp2f(mg - mn), pr = exp2f(sc_ - mn);
+                  lsum = fmaf(lsum, sc, pr);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) o[j] = fmaf(pr, vf[j], o[j] * sc);
+                  mg = mn;
+                }
               }
             }
           }
@@ -404,69 +453,58 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
       {
         load_vec<T, NCH>(G1 + (size_t)l * D, lane, gv);
         load_vec<T, NCH>(Be1 + (size_t)l * D, lane, bv);
-        const int o_loc = warp * 2 + (g < 2 ? g : 0);   // row of this CTA's 32 that thread (g < 2) finishes
-        const float o_bias = Elem<T>::to_f(Bo[(size_t)l * D + rank * GSV_HEAD_DIM + o_loc]);
+        const bool epi = warp < NB8 && ((livemask >> warp) & 1u);
+        const float o_bias = Elem<T>::to_f(Bo[(size_t)l * D + rank * GSV_HEAD_DIM + lane]);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_batch(std::integral_constant<int, 2>{}, attb, LDX, 0, acc);
+        mma_chunk(chunk_wait(), attb, LDX, 0, acc);
+        red_write(acc);
         __syncthreads();                                // every warp has read att: re-arm its inbox for the next layer
+        chunk_release();
         if (tid == 0 && l + 1 < L) mbar_expect_tx(&sh.xbar[1], (unsigned)na * D * 2u);
-        if (g < 2) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int n = 2 * t + j;
-            sh.stage[warp][n][g] = acc[j] + o_bias + sh.xres[n][o_loc];
-          }
+        if (epi) ystage[warp * GSV_HEAD_DIM + lane] = red_read() + o_bias + sh.xres[warp][lane];
+        rsel ^= 1;
+        __syncthreads();
+        // y1 rows of this CTA to every CTA: 16 bytes per store, (target, sequence, quad)
+        for (int i = tid; i < H * 64; i += NT) {
+          const int tgt = i >> 6, n = (i >> 3) & 7, q4 = i & 7;
+          if ((livemask >> n) & 1u)
+            st_async_v4(inA + n * D + (int)rank * GSV_HEAD_DIM + q4 * 4, &sh.xbar[0], (unsigned)tgt,
+                        *reinterpret_cast<const uint4*>(ystage + n * GSV_HEAD_DIM + q4 * 4));
         }
-        __syncwarp();
-        {
-          // lane -> target CTA lane & 15, sequences (lane >> 4) * 4 .. + 3; 8 bytes (rows 2w, 2w+1) per (target, sequence)
-          const int tgt = lane & 15;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = (lane >> 4) * 4 + i;
-            if (tgt < H && ((livemask >> n) & 1u))
-              st_async_v2(inA + n * D + (int)rank * GSV_HEAD_DIM + warp * 2, &sh.xbar[0], (unsigned)tgt,
-                          __float_as_uint(sh.stage[warp][n][0]), __float_as_uint(sh.stage[warp][n][1]));
-          }
-        }
-        __syncwarp();
       }
       mark(p, 53);
       mbar_wait(&sh.xbar[0], parA); parA ^= 1u;          // y1 has arrived
       mark(p, 4);
       // ================= M1: x1 = LN1(y1); h = relu(x1 W1^T + b1) ==================
       {
-        const int r_lo = warp * 8 + (g < 4 ? g : 0), r_hi = r_lo + 4;       // rows of this CTA's 128 that thread (g < 4) finishes
-        const float b_lo = Elem<T>::to_f(B1[(size_t)l * F + rank * (4 * GSV_HEAD_DIM) + r_lo]);
-        const float b_hi = Elem<T>::to_f(B1[(size_t)l * F + rank * (4 * GSV_HEAD_DIM) + r_hi]);
+        const bool epi = warp < NB8 && ((livemask >> warp) & 1u);
+        float b1v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b1v[u] = Elem<T>::to_f(B1[(size_t)l * F + rank * (4 * GSV_HEAD_DIM) + u * 32 + lane]);
         stage_ln(true, &sh.xres1[0][0]);
         __syncthreads();                                // xa staged; inA fully read
         if (tid == 0) mbar_expect_tx(&sh.xbar[0], (unsigned)na * D * 4u);             // re-arm inA for y2
-        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_batch(std::integral_constant<int, 4>{}, xa, LDX, 0, acc0);
-        mma_batch(std::integral_constant<int, 4>{}, xa, LDX, 0, acc1);
-        // stage h of rows 8w .. 8w+7 for every sequence in the storage type: 16 bytes per sequence
-        if (g < 4) {
-          T* stg = reinterpret_cast<T*>(&sh.stage[warp][0][0]);               // [8 sequences][8 rows] T
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int n = 2 * t + j;
-            stg[n * 8 + g] = Elem<T>::from_f(fmaxf(acc0[j] + b_lo, 0.f));
-            stg[n * 8 + 4 + g] = Elem<T>::from_f(fmaxf(acc1[j] + b_hi, 0.f));
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_chunk(chunk_wait(), xa, LDX, 0, acc);
+          red_write(acc);
+          __syncthreads();
+          chunk_release();
+          if (epi) {
+            const float bias = u == 0 ? b1v[0] : (u == 1 ? b1v[1] : (u == 2 ? b1v[2] : b1v[3]));
+            hstage[warp * (4 * GSV_HEAD_DIM) + u * 32 + lane] = Elem<T>::from_f(fmaxf(red_read() + bias, 0.f));
           }
+          rsel ^= 1;
         }
-        __syncwarp();
-        {
-          const int tgt = lane & 15;
-          const uint4* s4 = reinterpret_cast<const uint4*>(&sh.stage[warp][0][0]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = (lane >> 4) * 4 + i;
-            if (tgt < H && ((livemask >> n) & 1u))
-              st_async_v4(hb + n * LDH + (int)rank * (4 * GSV_HEAD_DIM) + warp * 8, &sh.xbar[2], (unsigned)tgt, s4[n]);
-          }
+        __syncthreads();
+        // h rows of this CTA (128 per sequence, storage type) to every CTA
+        for (int i = tid; i < H * 128; i += NT) {
+          const int tgt = i >> 7, n = (i >> 4) & 7, q8 = i & 15;
+          if ((livemask >> n) & 1u)
+            st_async_v4(hb + n * LDH + (int)rank * (4 * GSV_HEAD_DIM) + q8 * 8, &sh.xbar[2], (unsigned)tgt,
+                        *reinterpret_cast<const uint4*>(hstage + n * (4 * GSV_HEAD_DIM) + q8 * 8));
         }
-        __syncwarp();
       }
       mark(p, 54);
       mbar_wait(&sh.xbar[2], parH); parH ^= 1u;          // h has arrived
@@ -475,32 +513,27 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
       {
         load_vec<T, NCH>(G2 + (size_t)l * D, lane, gv);
         load_vec<T, NCH>(Be2 + (size_t)l * D, lane, bv);
-        const int m_loc = warp * 2 + (g < 2 ? g : 0);
-        const float m_bias = Elem<T>::to_f(B2[(size_t)l * D + rank * GSV_HEAD_DIM + m_loc]);
+        const bool epi = warp < NB8 && ((livemask >> warp) & 1u);
+        const float m_bias = Elem<T>::to_f(B2[(size_t)l * D + rank * GSV_HEAD_DIM + lane]);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) mma_batch(std::integral_constant<int, 2>{}, hb, LDH, q4 * D, acc);
-        __syncthreads();                                // every warp has read h: re-arm its inbox for the next layer
+#pragma unroll 1
+        for (int q4 = 0; q4 < 4; ++q4) {                // one K-quarter of the 32 rows per chunk
+          mma_chunk(chunk_wait(), hb, LDH, q4 * D, acc);
+          if (q4 == 3) red_write(acc);
+          __syncthreads();
+          chunk_release();
+        }
+        // every warp has read h: re-arm its inbox for the next layer
         if (tid == 0 && l + 1 < L) mbar_expect_tx(&sh.xbar[2], (unsigned)na * F * 2u);
-        if (g < 2) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int n = 2 * t + j;
-            sh.stage[warp][n][g] = acc[j] + m_bias + sh.xres1[n][m_loc];
-          }
+        if (epi) ystage[warp * GSV_HEAD_DIM + lane] = red_read() + m_bias + sh.xres1[warp][lane];
+        rsel ^= 1;
+        __syncthreads();
+        for (int i = tid; i < H * 64; i += NT) {
+          const int tgt = i >> 6, n = (i >> 3) & 7, q = i & 7;
+          if ((livemask >> n) & 1u)
+            st_async_v4(inA + n * D + (int)rank * GSV_HEAD_DIM + q * 4, &sh.xbar[0], (unsigned)tgt,
+                        *reinterpret_cast<const uint4*>(ystage + n * GSV_HEAD_DIM + q * 4));
         }
-        __syncwarp();
-        {
-          const int tgt = lane & 15;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = (lane >> 4) * 4 + i;
-            if (tgt < H && ((livemask >> n) & 1u))
-              st_async_v2(inA + n * D + (int)rank * GSV_HEAD_DIM + warp * 2, &sh.xbar[0], (unsigned)tgt,
-                          __float_as_uint(sh.stage[warp][n][0]), __float_as_uint(sh.stage[warp][n][1]));
-          }
-        }
-        __syncwarp();
       }
       mark(p, 55);
     }
@@ -511,24 +544,17 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
       stage_ln(true, &sh.xres[0][0]);                    // (residual copy unused here)
       __syncthreads();
       if (tid == 0) mbar_expect_tx(&sh.xbar[0], (unsigned)na * (D * 4u + 4u));        // re-arm inA for the next inputs (+ alive flags)
-      uint4 w[NCH], wn[NCH];
-      int j = warp;
-      if ((int)rank + j * H < V) load_vec<T, NCH>(Wh + (size_t)((int)rank + j * H) * D, lane, w);
+      const bool epi = warp < NB8 && ((livemask >> warp) & 1u);
 #pragma unroll 1
-      for (; (int)rank + j * H < V; j += NWARP) {
-        const int gg = (int)rank + j * H, gn = gg + NWARP * H;
-        if (gn < V) load_vec<T, NCH>(Wh + (size_t)gn * D, lane, wn);
-#pragma unroll 1
-        for (int n = 0; n < NB8; ++n) {
-          if (!((livemask >> n) & 1u)) continue;
-          float xv[NCH * 8];
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) unpack8<T>(*reinterpret_cast<const uint4*>(xa + n * LDX + c * 256 + lane * 8), &xv[c * 8]);
-          const float a = warp_allsum(dot_regs<T, NCH>(w, xv));
-          if (lane == 0) st_async(samp + gg, &sh.xbar[3], (unsigned)n, a);
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) w[c] = wn[c];
+      for (int j = 0; j < HC; ++j) {                     // 32 vocabulary rows per chunk
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_chunk(chunk_wait(), xa, LDX, 0, acc);
+        red_write(acc);
+        __syncthreads();
+        chunk_release();
+        const int gg = ((int)rank + j * H) * 32 + lane;
+        if (epi && gg < V) st_async(samp + gg, &sh.xbar[3], (unsigned)warp, red_read());
+        rsel ^= 1;
       }
     }
     mark(p, 20);
@@ -576,9 +602,9 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
     mark(p, 21);
     if (na == 0) break;
   }
-  for (int i = 0; i < RING8; ++i) {
-    mbar_wait(&sh.wbar[warp][use_i], use_par);
-    if (++use_i == RING8) { use_i = 0; use_par ^= 1u; }
+  for (int i = 0; i < NSLOT; ++i) {                       // requests that ran ahead of the last token
+    mbar_wait(&sh.cbar[ck_slot], ck_par);
+    if (++ck_slot == NSLOT) { ck_slot = 0; ck_par ^= 1u; }
   }
   cluster_sync_all();
 }
@@ -590,9 +616,26 @@ int launch_cl8(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
   if (nd == 2) fn = (void*)gpt_decode_cl8_kernel<T, 2>;
   else if (nd == 1) fn = (void*)gpt_decode_cl8_kernel<T, 1>;
   else return GSV_ERR_ARG;
-  const int D = ctx->p.d, F = ctx->p.F, H = ctx->p.H;
+  const int D = ctx->p.d, F = ctx->p.F, H = ctx->p.H, L = ctx->p.L, V = ctx->p.V;
+  const size_t chunk_bytes = (size_t)64 * D;
+  const int n_hchunks = (V + 31) / 32;
+  if (!ctx->cl8_pack) {
+    // one-time re-tiling of the block and head weights into chunk / fragment order (as large as the weights themselves)
+    void *pk = nullptr, *hp = nullptr;
+    GSV_CUDA(cudaMalloc(&pk, (size_t)L * H * CHUNKS * chunk_bytes));
+    GSV_CUDA(cudaMalloc(&hp, (size_t)n_hchunks * chunk_bytes));
+    cl8_pack_layers_kernel<T><<<ctx->num_sms * 4, 256, 0, st>>>(
+        reinterpret_cast<const T*>(ctx->p.w_qkv), reinterpret_cast<const T*>(ctx->p.w_o), reinterpret_cast<const T*>(ctx->p.w_1),
+        reinterpret_cast<const T*>(ctx->p.w_2), reinterpret_cast<uint4*>(pk), L, H, D);
+    cl8_pack_head_kernel<T><<<ctx->num_sms, 256, 0, st>>>(reinterpret_cast<const T*>(ctx->p.w_head), reinterpret_cast<uint4*>(hp), n_hchunks, V, D);
+    GSV_CUDA(cudaGetLastError());
+    ctx->cl8_pack = pk;
+    ctx->cl8_head_pack = hp;
+    ctx->launches += 2;
+  }
   const size_t bytes = (size_t)NB8 * D * 4 + (size_t)2 * NB8 * (D + XPAD) * 2 + (size_t)NB8 * (F + XPAD) * 2 + (size_t)D * 4 +
-                       (size_t)((GSV_SAMPLE_SMEM_FLOATS + 3) & ~3) * 4 + (size_t)NWARP * RING8 * (D * 2 + 16);
+                       (size_t)((GSV_SAMPLE_SMEM_FLOATS + 3) & ~3) * 4 + (size_t)2 * NWARP * RW * 4 + (size_t)NB8 * GSV_HEAD_DIM * 4 +
+                       (size_t)NB8 * 4 * GSV_HEAD_DIM * 2 + (size_t)NSLOT * chunk_bytes;
   GSV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   GSV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   const int n_clusters = (live + NB8 - 1) / NB8;
@@ -605,7 +648,9 @@ int launch_cl8(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   GptParams p = ctx->p;
   int ns = n_steps;
-  void* args[] = {&p, &ns};
+  const unsigned char* pk = reinterpret_cast<const unsigned char*>(ctx->cl8_pack);
+  const unsigned char* hp = reinterpret_cast<const unsigned char*>(ctx->cl8_head_pack);
+  void* args[] = {&p, &ns, &pk, &hp};
   GSV_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches += 1;
   return GSV_OK;

@@ -70,6 +70,8 @@ struct gsv_gpt_ctx {
   void* step_graph_exec;          // cudaGraphExec_t of one batched decode step
   int force_gemm;                 // GSV_DECODE_IMPL=gemm: multi-kernel tensor-core step for any live count
   int use_cl;                     // GSV_DECODE_IMPL=cl: cluster-per-sequence kernel
+  void* cl8_pack;                 // gpt_decode_cl8.cu: block weights re-tiled into chunk / mma-fragment order (first launch)
+  void* cl8_head_pack;            // ... and the head rows
   int use_cln;                    // GSV_DECODE_IMPL=cl2 / cl4: clusters serving 2 / 4 sequences each
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
