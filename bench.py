@@ -348,7 +348,7 @@ def extras(gpt, voc, dev, dtype, lib, N, syn):
         m.load_state_dict(syn.gpt_state_dict(syn.GPT_CONFIG, 0))
         m.initialize_runtime(dtype, dev, [(32, 512)])
         g = torch.Generator().manual_seed(7)
-        for B in (4, 8, 14, 28, 32):
+        for B in (4, 8, 16, 32):
             m._release_all()
             for s in range(B):
                 samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0,

@@ -152,21 +152,23 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
   // 1..4 live sequences: latency-optimised flag-in-data kernel; otherwise the barrier kernel
   // Measured on B200 (tools/decode_speed.py, bf16, kv 164..289), us per step (tokens per second):
-  //   live   ll     ll2    cl (1 seq/cluster)   cl2 (2/cluster)   cl4 (4/cluster)   gemm (multi-kernel, tcgen05 linears)
-  //    1     299    309    355                                                        1760
+  //   live   ll     ll2    cl (1 seq/cluster)   cl2 (2/cluster)   cl4 (4/cluster)   cl8 (8/cluster, mma)   gemm (multi-kernel, tcgen05 linears)
+  //    1     299    309    355                                                                               1760
   //    2     381    375    359  ( 5.6k)
   //    4     595    523    355  (11.3k)
   //    6      -      -     357  (16.8k)   <- at most 7 sixteen-CTA clusters are co-resident; more run in waves
-  //    8      -      -     712  (11.2k)          657 (12.2k)      1027 ( 7.8k)        1567 ( 5.1k)
+  //    8      -      -     712  (11.2k)          657 (12.2k)      1027 ( 7.8k)        427 (18.7k)           1567 ( 5.1k)
   //   14      -      -      -                    656 (21.3k)      1018 (13.8k)
-  //   28      -      -      -                   1308 (21.4k)      1016 (27.6k)        1580 (17.7k)
-  //   32      -      -    ~2140 (14.9k)         1962 (16.3k)      2062 (15.5k)        1583 (20.2k)
-  // -> 1: ll; 2..7: one cluster per sequence; 8..14: two per cluster; 15..28: four per cluster; more: the
-  //    multi-kernel step (GSV_DECODE_IMPL overrides).
+  //   16      -      -      -                     -                 -                 423 (37.9k)
+  //   28      -      -      -                   1308 (21.4k)      1016 (27.6k)                              1580 (17.7k)
+  //   32      -      -    ~2140 (14.9k)         1962 (16.3k)      2062 (15.5k)        432 (74.1k)           1583 (20.2k)
+  // -> 1: ll; 2..7: one cluster per sequence; 8 and more: eight per cluster on the tensor cores; the multi-kernel step
+  //    where clusters of H CTAs cannot be launched (GSV_DECODE_IMPL overrides).
   const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_ll2 || ctx->force_gemm;
   if (ctx->use_cln == 8 && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (ctx->use_cln && gsv_gpt_cl_supported(ctx, live)) return gsv_gpt_decode_cln_launch(ctx, live, ctx->use_cln, n_steps, (cudaStream_t)stream);
   if (!explicit_impl && !ctx->use_cl && gsv_gpt_cl_supported(ctx, live)) {
+    if (live >= 8 && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
     if (live >= 8 && live <= 14) return gsv_gpt_decode_cln_launch(ctx, live, 2, n_steps, (cudaStream_t)stream);
     if (live >= 15 && live <= 28) return gsv_gpt_decode_cln_launch(ctx, live, 4, n_steps, (cudaStream_t)stream);
   }

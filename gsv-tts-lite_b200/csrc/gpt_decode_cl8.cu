@@ -30,6 +30,7 @@ constexpr int NB8 = 8;                   // sequences per cluster
 constexpr int NSLOT = 3;                 // chunk ring slots
 constexpr int CHUNKS = 12;               // chunks per layer
 constexpr int XPAD = 8;                  // padding elements per staged activation row
+constexpr int PF = 3;                    // attention: passes (8 cached positions each) of K/V loads in flight per warp
 constexpr int RW = 176;                  // floats per warp in the partial-accumulator buffer: [8 sequences][20] (+16: bank shift between M-tiles)
 
 template <typename T> struct Mma16816;
@@ -46,13 +47,7 @@ template <> struct Mma16816<__half> {
   }
 };
 
-// 8 / 16 bytes into the same shared-memory location of CTA `rank`, completing that many bytes on its copy of `bar`
-__device__ __forceinline__ void st_async_v2(void* local_ptr, uint64_t* local_bar, unsigned rank, unsigned x, unsigned y) {
-  unsigned ra, rb;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(ra), "r"(x), "r"(y), "r"(rb) : "memory");
-}
+// 16 bytes into the same shared-memory location of CTA `rank`, completing that many bytes on its copy of `bar`
 __device__ __forceinline__ void st_async_v4(void* local_ptr, uint64_t* local_bar, unsigned rank, uint4 v) {
   unsigned ra, rb;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
@@ -324,6 +319,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
         stage_ln(l > 0, &sh.xres[0][0]);
         __syncthreads();                                // xa staged by the LayerNorm warps; inA fully read
         if (l > 0 && tid == 0) mbar_expect_tx(&sh.xbar[0], (unsigned)na * D * 4u);     // re-arm inA for this layer's y1
+        mark(p, 49);
         // chunks q, k, v: the 32 rows of this head
 #pragma unroll 1
         for (int u = 0; u < 3; ++u) {
@@ -367,24 +363,24 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
             float q[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) q[j] = sh.qs[n][sub * 8 + j];
-            // three passes of K/V rows in flight (L2 latency >> the arithmetic of a pass)
-            uint4 kq3[3], vq3[3];
+            // PF passes of K/V rows in flight (L2 latency >> the arithmetic of a pass)
+            uint4 kq3[PF], vq3[PF];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < PF; ++i) {
               kq3[i] = make_uint4(0, 0, 0, 0); vq3[i] = kq3[i];
               const int pp = pb + i * 8 + pg;
               if (pp < pe) { kq3[i] = ld_cg16(kb + (size_t)pp * GSV_HEAD_DIM); vq3[i] = ld_cg16(vb + (size_t)pp * GSV_HEAD_DIM); }
             }
 #pragma unroll 1
-            for (int base = pb; base < pe; base += 24) {
+            for (int base = pb; base < pe; base += 8 * PF) {
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
+              for (int i = 0; i < PF; ++i) {
                 const int pos = base + i * 8 + pg;
                 const bool ok = pos < pe;
                 const uint4 kr = kq3[i], vr = vq3[i];
-                if (pos + 24 < pe) {
-                  kq3[i] = ld_cg16(kb + (size_t)(pos + 24) * GSV_HEAD_DIM);
-                  vq3[i] = ld_cg16(vb + (size_t)(pos + 24) * GSV_HEAD_DIM);
+                if (pos + 8 * PF < pe) {
+                  kq3[i] = ld_cg16(kb + (size_t)(pos + 8 * PF) * GSV_HEAD_DIM);
+                  vq3[i] = ld_cg16(vb + (size_t)(pos + 8 * PF) * GSV_HEAD_DIM);
                 }
                 float kf[8], vf[8], sc_ = 0.f;
                 unpack8<T>(kr, kf);
@@ -464,6 +460,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
         if (epi) ystage[warp * GSV_HEAD_DIM + lane] = red_read() + o_bias + sh.xres[warp][lane];
         rsel ^= 1;
         __syncthreads();
+        mark(p, 31);
         // y1 rows of this CTA to every CTA: 16 bytes per store, (target, sequence, quad)
         for (int i = tid; i < H * 64; i += NT) {
           const int tgt = i >> 6, n = (i >> 3) & 7, q4 = i & 7;
@@ -484,6 +481,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
         stage_ln(true, &sh.xres1[0][0]);
         __syncthreads();                                // xa staged; inA fully read
         if (tid == 0) mbar_expect_tx(&sh.xbar[0], (unsigned)na * D * 4u);             // re-arm inA for y2
+        mark(p, 41);
 #pragma unroll 1
         for (int u = 0; u < 4; ++u) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -498,6 +496,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
           rsel ^= 1;
         }
         __syncthreads();
+        mark(p, 42);
         // h rows of this CTA (128 per sequence, storage type) to every CTA
         for (int i = tid; i < H * 128; i += NT) {
           const int tgt = i >> 7, n = (i >> 4) & 7, q8 = i & 15;
@@ -528,6 +527,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
         if (epi) ystage[warp * GSV_HEAD_DIM + lane] = red_read() + m_bias + sh.xres1[warp][lane];
         rsel ^= 1;
         __syncthreads();
+        mark(p, 51);
         for (int i = tid; i < H * 64; i += NT) {
           const int tgt = i >> 6, n = (i >> 3) & 7, q = i & 7;
           if ((livemask >> n) & 1u)

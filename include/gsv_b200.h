@@ -98,8 +98,8 @@ typedef struct gsv_gpt_ctx gsv_gpt_ctx;
 
 /* Allocates KV cache [L][slots][H][S][32] x2 and all step buffers (initialize_runtime,
  * t2s_model.py:210-298: one K root, one V root, static step I/O).  Nothing is captured here: decode is one
- * persistent launch per call for up to 24 live sequences, and one CUDA graph per step (captured on first
- * use) above that. */
+ * persistent launch per call.  The first decode with 8 or more live sequences re-tiles the block weights into
+ * the tensor-core kernel's chunk order (one extra copy of the weights, kept until destroy). */
 int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w, gsv_gpt_ctx** out);
 int gsv_gpt_destroy(gsv_gpt_ctx* ctx);
 
@@ -113,9 +113,9 @@ int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, co
 /* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
  * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
  * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).
- * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..28 -> thread-block
- * clusters serving 1, 2 or 4 sequences each, more -> tcgen05 linears + small kernels replayed from a CUDA graph.
- * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | cl2 | cl4 | gemm | barrier; GSV_GPT_GEMM = cuda. */
+ * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..7 -> one thread-block
+ * cluster per sequence, 8 and more -> clusters serving eight sequences each on tensor-core tiles.
+ * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | cl2 | cl4 | cl8 | gemm | barrier; GSV_GPT_GEMM = cuda. */
 int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream);
 
 /* Copy slot state to host memory (asynchronously on `stream`; caller synchronises):

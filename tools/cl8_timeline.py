@@ -1,10 +1,13 @@
 #!/usr/bin/env python
-"""In-kernel timeline of the 8-sequence cluster kernel (build with make EXTRA=-DGSV_TIMELINE; GSV_DECODE_IMPL=cl8)."""
+"""In-kernel timeline of the 8-sequence cluster kernel (needs a -DGSV_TIMELINE build: either `make EXTRA=-DGSV_TIMELINE`,
+or objects built into csrc/build_tl and linked as gsv_tts/libgsv_b200_tl.so; GSV_DECODE_IMPL=cl8)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gsv-tts-lite_b200"))
 import numpy as np, torch
 from gsv_tts import _native as N, _synthetic as syn
+if os.path.exists(os.path.join(os.path.dirname(N.LIB_PATH), 'libgsv_b200_tl.so')):
+    N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), 'libgsv_b200_tl.so')     # local -DGSV_TIMELINE build (see docstring)
 from tests import gpu_harness as H
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
@@ -21,7 +24,7 @@ rec = torch.zeros(G * 2 * MAXR, dtype=torch.int64, device=dev)
 N.check(N.lib().gsv_gpt_set_timeline(m._ctx, rec.data_ptr(), MAXR, 0))
 m._decode(3); torch.cuda.synchronize()
 r = rec.cpu().numpy().reshape(G, MAXR, 2)[:16]
-names = {1: "A.start", 50: " qkv done", 52: "A.end (att pushed)", 3: "O.start (att arrived)", 53: "O.end", 4: "M1.start (y1 arrived)", 54: "M1.end",
+names = {1: "A.start", 49: " ln staged", 41: " ln1 staged", 31: " O mma+epi done", 42: " M1 mma+epi done", 51: " M2 mma+epi done", 50: " qkv done", 52: "A.end (att pushed)", 3: "O.start (att arrived)", 53: "O.end", 4: "M1.start (y1 arrived)", 54: "M1.end",
          5: "M2.start (h arrived)", 55: "M2.end", 6: "HEAD.start", 20: "S.start", 21: "S.done"}
 n = int(r[0, 0, 0])
 ids = r[0, 1:n + 1, 0]

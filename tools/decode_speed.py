@@ -5,6 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gsv-tts-lite_b200"))
 import torch
 from gsv_tts import _native as N, _synthetic as syn
+if os.environ.get('GSV_B200_LIB'):      # A/B builds of the library (tools only)
+    N.LIB_PATH = os.path.join(os.path.dirname(N.LIB_PATH), os.environ['GSV_B200_LIB'])
 from tests import gpu_harness as H
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")
