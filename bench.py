@@ -17,6 +17,7 @@ Arms:
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -31,6 +32,7 @@ for p in (ROOT, os.path.join(ROOT, "gsv-tts-lite_b200")):
 import torch  # noqa: E402
 
 NX, NY, N_TOK, CHUNK = 64, 100, 200, 25
+DECODE_SMS = 128                           # SMs of the single-sequence decode kernel when the vocoder overlaps it
 FRAMES_FIRST, FRAMES_NEXT = 50, 55        # sovits_cache=[50,55] (reference README_EN.md:214)
 WORKLOAD = "V2Pro batch=1 streaming: prefill 64+100, 200 tokens in 8 chunks of 25, flow+HiFi-GAN 50/55 frames per chunk"
 METRIC = "AR tokens/sec (V2Pro, batch=1 streaming, end-to-end incl. prefill + vocoder)"
@@ -145,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="vocoder chunks on the decode stream (reference order) instead of a second stream")
     ap.add_argument("--no-extra", action="store_true", help="skip the batch 8/32 decode and vocoder-only extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -202,6 +205,10 @@ def main():
 
     gpt.debug_seed = 99
     stream = torch.cuda.current_stream(dev)
+    overlap = not args.no_overlap
+    side = torch.cuda.Stream(dev)
+    if overlap:
+        gpt.set_decode_sms(DECODE_SMS)
     dec_ms = []         # per decode launch (25 tokens), CUDA events on the launching stream
 
     ttft_marks = None
@@ -216,7 +223,9 @@ def main():
             gz = [z.to(dev, non_blocking=True) for z in zsh]
             gg = geh.to(dev, non_blocking=True)
         gpt._single_setup(gx, gy, gb, 15, 1.0, 1.0, 1.35, 10, N_TOK)
-        for c in range(N_TOK // CHUNK):
+        n_chunks = N_TOK // CHUNK
+
+        def decode_chunk():
             if time_decode:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
@@ -224,14 +233,32 @@ def main():
             if time_decode:
                 e1.record(stream)
                 dec_ms.append((e0, e1))
-            gpt._read(1)                                   # tokens of the chunk on the host (stream sync)
-            audio = voc.flow_dec(gz[c], masks[c], gg)
-            if not device_resident:
-                audio_host[c, : audio.shape[-1]].copy_(audio[0, 0], non_blocking=True)
-                if c == 0 and ttft_marks is not None:
-                    # time to first audio: host call -> first 1.6 s chunk of samples in host memory
-                    stream.synchronize()
-                    ttft_marks.append(time.perf_counter())
+
+        if overlap:
+            side.wait_stream(stream)                       # the host->device copies above
+        decode_chunk()
+        for c in range(n_chunks):
+            gpt._read(1)                                   # tokens of chunk c on the host (stream sync)
+            if overlap:
+                # gsv_tts.TTS.infer_features_stream: chunk c+1 decodes (on 128 SMs) while the vocoder of chunk c runs
+                # on a second stream; the first chunk's vocoder is enqueued BEFORE the next decode
+                if c + 1 < n_chunks and c > 0:
+                    decode_chunk()
+                ctx_mgr = torch.cuda.stream(side)
+            else:
+                ctx_mgr = contextlib.nullcontext()
+            with ctx_mgr:
+                audio = voc.flow_dec(gz[c], masks[c], gg)
+                if not device_resident:
+                    audio_host[c, : audio.shape[-1]].copy_(audio[0, 0], non_blocking=True)
+                    if c == 0 and ttft_marks is not None:
+                        # time to first audio: host call -> first 1.6 s chunk of samples in host memory
+                        torch.cuda.current_stream(dev).synchronize()
+                        ttft_marks.append(time.perf_counter())
+            if (not overlap or c == 0) and c + 1 < n_chunks:
+                decode_chunk()                             # behind the first chunk's vocoder: it gets the whole GPU (time to first audio)
+        if overlap:
+            stream.wait_stream(side)                       # the step ends when the last chunk of audio exists
         if not device_resident:
             stream.synchronize()
         return int(gpt._h_ngen[0]) - 1
@@ -326,7 +353,9 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "256 MB flush between timed steps; 152 MB of weights (> L2) streamed per token",
-                       "parallelism": f"{world} independent utterance streams, NCCL weight broadcast at load only"},
+                       "parallelism": f"{world} independent utterance streams, NCCL weight broadcast at load only",
+                       "overlap": (f"vocoder of chunk c on a second stream while chunk c+1 decodes on {DECODE_SMS} SMs" if overlap
+                                   else "none: decode and vocoder chunks back to back on one stream")},
             "rtf": (ms_total / 1e3 / args.steps) / audio_s, "ttft_ms": ttft_ms,
             "roofline": roofline, "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -248,6 +248,12 @@ extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int m
 
 extern "C" int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int gsv_gpt_set_decode_sms(gsv_gpt_ctx* ctx, int n_sms) {
+  GSV_ARG(ctx && n_sms >= 0);
+  ctx->decode_sms = n_sms;
+  return GSV_OK;
+}
+
 extern "C" int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta) {
   GSV_ARG(ctx);
   invalidate_step_graph(ctx);

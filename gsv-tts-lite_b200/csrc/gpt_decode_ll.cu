@@ -745,6 +745,7 @@ int launch_ll_nb(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   uint2* buf = reinterpret_cast<uint2*>(ctx->ll_buf);
   void* args[] = {&p, &ns, &tag_base, &buf};
   int grid = ctx->num_sms;
+  if (ctx->decode_sms >= ctx->p.H * NB && ctx->decode_sms < ctx->num_sms) grid = ctx->decode_sms;   // the rest stay free for a concurrent stream
   {
     // tuning hook: fewer CTAs = fewer pollers per exchange, more rows per CTA
     static int env_grid = -1;

@@ -70,6 +70,7 @@ struct gsv_gpt_ctx {
   void* step_graph_exec;          // cudaGraphExec_t of one batched decode step
   int force_gemm;                 // GSV_DECODE_IMPL=gemm: multi-kernel tensor-core step for any live count
   int use_cl;                     // GSV_DECODE_IMPL=cl: cluster-per-sequence kernel
+  int decode_sms;                 // gsv_gpt_set_decode_sms: CTAs of the single-sequence decode kernel (0 = every SM)
   void* cl8_pack;                 // gpt_decode_cl8.cu: block weights re-tiled into chunk / mma-fragment order (first launch)
   void* cl8_head_pack;            // ... and the head rows
   int use_cln;                    // GSV_DECODE_IMPL=cl2 / cl4: clusters serving 2 / 4 sequences each

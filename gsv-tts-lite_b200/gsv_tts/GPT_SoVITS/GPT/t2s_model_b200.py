@@ -182,6 +182,11 @@ class Text2SemanticDecoder(nn.Module):
         N.check(N.lib().gsv_gpt_prefill(self._ctx, slot, x.data_ptr(), x.numel(), y.data_ptr(), y.numel(),
                                         bert.data_ptr(), C.byref(samp), self._stream()))
 
+    def set_decode_sms(self, n_sms: int):
+        """Leave ``num_sms - n_sms`` SMs free while one sequence decodes (0 = use all): room for the vocoder of the
+        previous chunk on another stream (``TTS.infer_features_stream``)."""
+        N.check(N.lib().gsv_gpt_set_decode_sms(self._ctx, int(n_sms)))
+
     def _decode(self, n_steps: int):
         N.check(N.lib().gsv_gpt_decode(self._ctx, n_steps, self._stream()))
 
@@ -250,13 +255,19 @@ class Text2SemanticDecoder(nn.Module):
         self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
                            initial_suppression_steps, force_steps)
         first, pre_chunk, idx = True, None, 0
-        while True:
+        self.chunk_ready = torch.cuda.Event()      # recorded after the copy of every chunk handed out
+
+        def launch(done: int) -> bool:
             n = stream_chunk
             if force_steps is not None:
-                n = min(n, force_steps - idx)
-                if n <= 0:
-                    break
+                n = min(n, force_steps - done)
+            if n <= 0:
+                return False
             self._decode(n)
+            return True
+
+        more = launch(0)
+        while more:
             self._read(1)
             n_gen = int(self._h_ngen[0])            # s0 + decode steps so far
             active = int(self._h_active[0])
@@ -264,24 +275,37 @@ class Text2SemanticDecoder(nn.Module):
             steps = n_gen - 1
             if not active and int(toks[-1]) == self.EOS:
                 # EOS sampled at decode step `steps`: loop broke before the append (:534-535)
-                final = toks[0:steps]
-                yield final.to(self._device).view(1, 1, -1), True
+                final = toks[0:steps].to(self._device).view(1, 1, -1)
+                self.chunk_ready.record(torch.cuda.current_stream(self._device))
+                yield final, True
                 return
             idx = steps
+            chunk = None
             if idx % stream_chunk == 0 and idx > 0:
+                chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
+                self.chunk_ready.record(torch.cuda.current_stream(self._device))
+            # the next chunk is launched BEFORE this one is handed out: whatever the caller does with it (the
+            # vocoder, on its own stream after `chunk_ready`) overlaps the decode instead of delaying it
+            # ... except behind the very first chunk handed out, whose vocoder gets the whole GPU (time to first audio)
+            defer = chunk is not None and boost_first_chunk and first
+            if not defer:
+                more = bool(active) and launch(idx)
+            if chunk is not None:
                 if pre_chunk is not None:
                     yield pre_chunk, False
-                pre_chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
+                pre_chunk = chunk
                 if boost_first_chunk and first:
                     first = False
                     yield pre_chunk, False
                     pre_chunk = None
-            if not active:
-                break
+            if defer:
+                more = bool(active) and launch(idx)
         self._read(1)
         n_gen = int(self._h_ngen[0])
         toks = self._h_tokens[0, :n_gen].to(torch.int64)
-        yield toks[1:].to(self._device).view(1, 1, -1), True
+        out = toks[1:].to(self._device).view(1, 1, -1)
+        self.chunk_ready.record(torch.cuda.current_stream(self._device))
+        yield out, True
 
     @torch.inference_mode()
     def infer_batched(self, x: List[torch.Tensor], y: List[torch.Tensor], bert_feature: List[torch.Tensor],

@@ -120,6 +120,38 @@ class TTS:
         audio = voc.flow_dec(z_p, y_mask, ge)[0, 0].float().cpu().numpy()
         return tokens, self._clip(audio)
 
+    def infer_features_stream(self, phoneme_ids, bert, prompt_tokens, features_of_chunk, gpt_model: Optional[str] = None,
+                              sovits_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0,
+                              repetition_penalty=1.35, stream_chunk: int = 25, decode_sms: int = 128):
+        """Streaming counterpart of ``infer_features`` (the GPT / vocoder part of ``infer_stream``, TTS.py:402-470):
+        yields one ``AudioClip`` per chunk of ``stream_chunk`` semantic tokens.  ``features_of_chunk(tokens, final)``
+        stands for ``enc_p`` (out of scope): it returns ``(z_p, y_mask, ge)`` for the frames of that chunk.
+        The reference runs chunk c's vocoder and chunk c+1's decode back to back; here the decode of chunk c+1 is
+        already in flight (``Text2SemanticDecoder.infer_stream`` launches ahead, on ``decode_sms`` SMs) while the
+        vocoder of chunk c runs on a second stream."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev = gpt._device
+        side = torch.cuda.Stream(dev)
+        gpt.set_decode_sms(decode_sms)
+        try:
+            it = gpt.infer_stream(phoneme_ids, prompt_tokens, bert, top_k=top_k, top_p=top_p, temperature=temperature,
+                                  repetition_penalty=repetition_penalty, stream_chunk=stream_chunk)
+            while True:
+                with torch.inference_mode():
+                    try:
+                        tokens, final = next(it)          # host-synchronised: the tokens exist, the next chunk is decoding
+                    except StopIteration:
+                        break
+                    with torch.cuda.stream(side):
+                        side.wait_event(gpt.chunk_ready)                     # the token copy, not the decode behind it
+                        tokens.record_stream(side)
+                        z_p, y_mask, ge = features_of_chunk(tokens, final)
+                        audio = voc.flow_dec(z_p, y_mask, ge)[0, 0].float().cpu()        # waits for `side` only
+                yield self._clip(audio.numpy())
+        finally:
+            gpt.set_decode_sms(0)
+
     @torch.inference_mode()
     def infer_features_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence,
                                gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0):

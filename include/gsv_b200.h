@@ -138,6 +138,12 @@ int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n);
 int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows);
 /* Number of kernel launches issued by this context so far (bench "gpu_launches"). */
 int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx);
+
+/* Number of SMs the single-sequence decode kernel occupies (0 = all).  No reference counterpart: the reference
+ * runs the GPT chunk and the vocoder chunk of infer_stream back to back on one stream (TTS.py:402-470); here the
+ * vocoder of chunk c runs on a second stream, on the SMs left free, while the GPT decodes chunk c+1.  The step
+ * time of the decode kernel is the same from 128 SMs up. */
+int gsv_gpt_set_decode_sms(gsv_gpt_ctx* ctx, int n_sms);
 /* Tuning hook: CTA `cta` of the decode kernel appends {marker id, SM clock} pairs (2 x int64 per
  * record, record 0 holds the count) to dev_records; NULL disables. */
 int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta);
