@@ -187,6 +187,12 @@ class Text2SemanticDecoder(nn.Module):
         previous chunk on another stream (``TTS.infer_features_stream``)."""
         N.check(N.lib().gsv_gpt_set_decode_sms(self._ctx, int(n_sms)))
 
+    def _mark_chunk_ready(self):
+        """Event behind the host->device copy of the chunk about to be handed out: a consumer on another stream waits
+        for this, not for the decode launched after it."""
+        self.chunk_ready = torch.cuda.Event()
+        self.chunk_ready.record(torch.cuda.current_stream(self._device))
+
     def _decode(self, n_steps: int):
         N.check(N.lib().gsv_gpt_decode(self._ctx, n_steps, self._stream()))
 
@@ -255,7 +261,6 @@ class Text2SemanticDecoder(nn.Module):
         self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
                            initial_suppression_steps, force_steps)
         first, pre_chunk, idx = True, None, 0
-        self.chunk_ready = torch.cuda.Event()      # recorded after the copy of every chunk handed out
 
         def launch(done: int) -> bool:
             n = stream_chunk
@@ -276,14 +281,14 @@ class Text2SemanticDecoder(nn.Module):
             if not active and int(toks[-1]) == self.EOS:
                 # EOS sampled at decode step `steps`: loop broke before the append (:534-535)
                 final = toks[0:steps].to(self._device).view(1, 1, -1)
-                self.chunk_ready.record(torch.cuda.current_stream(self._device))
+                self._mark_chunk_ready()
                 yield final, True
                 return
             idx = steps
             chunk = None
             if idx % stream_chunk == 0 and idx > 0:
                 chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
-                self.chunk_ready.record(torch.cuda.current_stream(self._device))
+                self._mark_chunk_ready()
             # the next chunk is launched BEFORE this one is handed out: whatever the caller does with it (the
             # vocoder, on its own stream after `chunk_ready`) overlaps the decode instead of delaying it
             # ... except behind the very first chunk handed out, whose vocoder gets the whole GPU (time to first audio)
@@ -304,7 +309,7 @@ class Text2SemanticDecoder(nn.Module):
         n_gen = int(self._h_ngen[0])
         toks = self._h_tokens[0, :n_gen].to(torch.int64)
         out = toks[1:].to(self._device).view(1, 1, -1)
-        self.chunk_ready.record(torch.cuda.current_stream(self._device))
+        self._mark_chunk_ready()
         yield out, True
 
     @torch.inference_mode()
