@@ -95,6 +95,7 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(ctx->pf_attn, S * d * 2, false);
   A(ctx->pf_h, S * F * 2, false);
   A(ctx->pf_tmp, S * d * 2, false);
+  A(ctx->pf_last, B * d * 2, true);
   A(ctx->ll_buf, gsv_gpt_ll_buffer_bytes(ctx), true);
   A(ctx->dx, B * d * 2, true);
   A(ctx->dqkv, B * 3 * d * 2, true);
@@ -130,19 +131,51 @@ extern "C" int gsv_gpt_destroy(gsv_gpt_ctx* ctx) {
   return GSV_OK;
 }
 
-extern "C" int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
-                               const void* dev_bert, const gsv_gpt_sampling* samp, void* stream) {
-  GSV_ARG(ctx && dev_x && dev_y && dev_bert && samp);
-  GSV_ARG(slot >= 0 && slot < ctx->p.slots);
-  GSV_ARG(nx >= 1 && ny >= 1);
+static int check_prompt(gsv_gpt_ctx* ctx, int nx, int ny) {
   if (nx + ny >= ctx->p.S) {
     // the reference does not validate this and fails with a shape error inside process_prompt
     // (t2s_model.py:49; SURVEY.md 8b "Errors"); here it is an argument error
     gsv_set_error("prompt length %d+%d does not fit the KV cache (max_seq %d)", nx, ny, ctx->p.S);
     return GSV_ERR_ARG;
   }
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
+                               const void* dev_bert, const gsv_gpt_sampling* samp, void* stream) {
+  GSV_ARG(ctx && dev_x && dev_y && dev_bert && samp);
+  GSV_ARG(slot >= 0 && slot < ctx->p.slots);
+  GSV_ARG(nx >= 1 && ny >= 1);
+  int rc = check_prompt(ctx, nx, ny);
+  if (rc) return rc;
+  if ((rc = gsv_gpt_prefill_body(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, (cudaStream_t)stream))) return rc;
   ctx->slot_live[slot] = 1;
-  return gsv_gpt_prefill_impl(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, samp, (cudaStream_t)stream);
+  rc = gsv_gpt_prefill_tail(ctx, slot, dev_y, ny, samp, (cudaStream_t)stream);
+  ctx->pf_n[slot] = 0;
+  return rc;
+}
+
+extern "C" int gsv_gpt_prefill_begin(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
+                                     const void* dev_bert, void* stream) {
+  GSV_ARG(ctx && dev_x && dev_y && dev_bert);
+  GSV_ARG(slot >= 0 && slot < ctx->p.slots);
+  GSV_ARG(nx >= 1 && ny >= 1);
+  int rc = check_prompt(ctx, nx, ny);
+  if (rc) return rc;
+  // caller's contract: the slot's previous sequence has finished (its `active` flag read back as 0) or was released
+  return gsv_gpt_prefill_body(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, (cudaStream_t)stream);
+}
+
+extern "C" int gsv_gpt_prefill_finish(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_y, int ny, const gsv_gpt_sampling* samp,
+                                      void* stream) {
+  GSV_ARG(ctx && dev_y && samp);
+  GSV_ARG(slot >= 0 && slot < ctx->p.slots);
+  if (ctx->pf_n[slot] <= 0) { gsv_set_error("gsv_gpt_prefill_finish: no gsv_gpt_prefill_begin pending for slot %d", slot); return GSV_ERR_STATE; }
+  GSV_ARG(ny >= 1 && ny < ctx->pf_n[slot]);
+  ctx->slot_live[slot] = 1;
+  const int rc = gsv_gpt_prefill_tail(ctx, slot, dev_y, ny, samp, (cudaStream_t)stream);
+  ctx->pf_n[slot] = 0;
+  return rc;
 }
 
 extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {

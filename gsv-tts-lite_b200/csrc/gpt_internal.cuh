@@ -58,6 +58,8 @@ struct gsv_gpt_ctx {
   long long launches;
   // prefill scratch (T unless noted), sized for max_seq rows
   void *pf_x, *pf_qkv, *pf_attn, *pf_h, *pf_tmp;
+  void* pf_last;                  // [slots][d] T: last prompt row of a prefill body, read by its tail
+  int pf_nx[GSV_MAX_SLOTS], pf_n[GSV_MAX_SLOTS];   // text / total prompt length of the body waiting for its tail (0 = none)
   float* pf_f32;
   void* all_allocs[64];
   int n_allocs;
@@ -90,8 +92,8 @@ int gsv_umma_linear(gsv_umma_cache* c, size_t op, int dtype, const void* X, int 
 
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
 int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
-int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny,
-                         const void* bert, const gsv_gpt_sampling* samp, cudaStream_t st);
+int gsv_gpt_prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st);
+int gsv_gpt_prefill_tail(gsv_gpt_ctx* ctx, int slot, const int64_t* y, int ny, const gsv_gpt_sampling* samp, cudaStream_t st);
 int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);
 size_t gsv_gpt_ll_buffer_bytes(const gsv_gpt_ctx* ctx);
 bool gsv_gpt_ll_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);

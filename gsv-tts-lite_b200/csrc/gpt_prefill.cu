@@ -270,9 +270,11 @@ int gemm(const T* A, int lda, const T* W, const T* bias, T* C, int ldc, int M, i
   return GSV_OK;
 }
 
+// Body of a prefill: everything that does not touch the slot's decode state (embeddings, the L layers, the K/V rows of
+// the slot).  It may run on another stream than the decode launches: decode kernels never look at an inactive slot.
+// The last prompt row is parked in pf_last[slot] for prefill_tail().
 template <typename T>
-int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert,
-                 const gsv_gpt_sampling& samp, cudaStream_t st) {
+int prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st) {
   const GptParams& p = ctx->p;
   const int d = p.d, F = p.F, L = p.L, n = nx + ny;
   T* X = reinterpret_cast<T*>(ctx->pf_x);        // [n][d]
@@ -317,8 +319,20 @@ int prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int
     ctx->launches += 1;
     GSV_CHECK_LAUNCH();
   }
-  slot_reset_kernel<<<1, 256, 0, st>>>(p, slot, nx, n, y, ny, samp);
-  head_row_kernel<T><<<(p.V + 7) / 8, 256, 0, st>>>(p, slot, X + (size_t)(n - 1) * d);
+  GSV_CUDA(cudaMemcpyAsync(reinterpret_cast<T*>(ctx->pf_last) + (size_t)slot * d, X + (size_t)(n - 1) * d, (size_t)d * sizeof(T),
+                           cudaMemcpyDeviceToDevice, st));
+  ctx->pf_nx[slot] = nx;
+  ctx->pf_n[slot] = n;
+  return GSV_OK;
+}
+
+// Tail of a prefill: slot state reset (this is what makes the slot live), logits of the last prompt row, first sample.
+// Must be ordered after the body of the same slot and must not overlap a decode launch (same stream as the decodes).
+template <typename T>
+int prefill_tail(gsv_gpt_ctx* ctx, int slot, const int64_t* y, int ny, const gsv_gpt_sampling& samp, cudaStream_t st) {
+  const GptParams& p = ctx->p;
+  slot_reset_kernel<<<1, 256, 0, st>>>(p, slot, ctx->pf_nx[slot], ctx->pf_n[slot], y, ny, samp);
+  head_row_kernel<T><<<(p.V + 7) / 8, 256, 0, st>>>(p, slot, reinterpret_cast<const T*>(ctx->pf_last) + (size_t)slot * p.d);
   const size_t smem = GSV_SAMPLE_SMEM_FLOATS * sizeof(float);
   first_token_kernel<T><<<1, GSV_DECODE_THREADS, smem, st>>>(p, slot);
   ctx->launches += 3;
@@ -553,8 +567,12 @@ int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   return decode_gemm_impl<__nv_bfloat16>(ctx, n_steps, st);
 }
 
-int gsv_gpt_prefill_impl(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert,
-                         const gsv_gpt_sampling* samp, cudaStream_t st) {
-  if (ctx->dims.dtype == GSV_F16) return prefill_impl<__half>(ctx, slot, x, nx, y, ny, bert, *samp, st);
-  return prefill_impl<__nv_bfloat16>(ctx, slot, x, nx, y, ny, bert, *samp, st);
+int gsv_gpt_prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return prefill_body<__half>(ctx, slot, x, nx, y, ny, bert, st);
+  return prefill_body<__nv_bfloat16>(ctx, slot, x, nx, y, ny, bert, st);
+}
+
+int gsv_gpt_prefill_tail(gsv_gpt_ctx* ctx, int slot, const int64_t* y, int ny, const gsv_gpt_sampling* samp, cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return prefill_tail<__half>(ctx, slot, y, ny, *samp, st);
+  return prefill_tail<__nv_bfloat16>(ctx, slot, y, ny, *samp, st);
 }

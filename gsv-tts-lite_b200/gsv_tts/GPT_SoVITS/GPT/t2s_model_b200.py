@@ -99,6 +99,8 @@ class Text2SemanticDecoder(nn.Module):
         self._buckets = {}            # batch size -> sorted list of lengths (gpt_cache)
         self._parity_noise = None     # test hook: [rows][V] fp32 Exp(1) noise for slot 0
         self.debug_seed: Optional[int] = None
+        self.overlap_refill = True          # infer_batched: prompts of refills on a second stream (False: reference order)
+        self._refill_stream = None
 
     # ------------------------------------------------------------------ runtime set-up
     @torch.inference_mode()
@@ -181,6 +183,19 @@ class Text2SemanticDecoder(nn.Module):
         bert = bert.to(device=self._device, dtype=self._dtype).contiguous().view(x.numel(), -1)
         N.check(N.lib().gsv_gpt_prefill(self._ctx, slot, x.data_ptr(), x.numel(), y.data_ptr(), y.numel(),
                                         bert.data_ptr(), C.byref(samp), self._stream()))
+
+    def _prefill_begin(self, slot, x, y, bert):
+        """First half of a prefill on the CURRENT stream (``gsv_gpt_prefill_begin``); returns the tensors the second
+        half needs alive."""
+        x = x.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+        y = y.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+        bert = bert.to(device=self._device, dtype=self._dtype).contiguous().view(x.numel(), -1)
+        N.check(N.lib().gsv_gpt_prefill_begin(self._ctx, slot, x.data_ptr(), x.numel(), y.data_ptr(), y.numel(),
+                                              bert.data_ptr(), self._stream()))
+        return x, y, bert
+
+    def _prefill_finish(self, slot, y, samp: N.GptSampling):
+        N.check(N.lib().gsv_gpt_prefill_finish(self._ctx, slot, y.data_ptr(), y.numel(), C.byref(samp), self._stream()))
 
     def set_decode_sms(self, n_sms: int):
         """Leave ``num_sms - n_sms`` SMs free while one sequence decodes (0 = use all): room for the vocoder of the
@@ -331,14 +346,17 @@ class Text2SemanticDecoder(nn.Module):
         N.check(N.lib().gsv_gpt_set_noise(self._ctx, None, 0))
         base_seed = self._next_seed()
 
-        def start(slot, r):
-            samp = N.GptSampling(top_k=top_k if top_k is not None else 0, top_p=top_p if top_p is not None else 1.0,
+        def sampling(r):
+            return N.GptSampling(top_k=top_k if top_k is not None else 0, top_p=top_p if top_p is not None else 1.0,
                                  temperature=temperature, repetition_penalty=1.0, suppress_steps=0,
                                  max_new_tokens=(max_new[r] if max_new is not None else 0), mask_eos=0,
                                  max_kv=max_kv, seed=(base_seed + 0x9E3779B97F4A7C15 * (r + 1)) & (2 ** 64 - 1))
-            self._prefill(slot, x[r], y[r], bert_feature[r], samp)
 
-        owner = [-1] * slots
+        def start(slot, r):
+            self._prefill(slot, x[r], y[r], bert_feature[r], sampling(r))
+
+        FREE, REFILLING = -1, -2
+        owner = [FREE] * slots
         nxt = 0
         for s in range(min(slots, B)):
             start(s, nxt)
@@ -346,9 +364,23 @@ class Text2SemanticDecoder(nn.Module):
             nxt += 1
         results, order = [], []
         interval = max(int(check_interval), self.BATCH_INTERVAL)
-        while any(o >= 0 for o in owner):
-            self._decode(interval)
+        main = torch.cuda.current_stream(self._device)
+        side = self._refill_stream if self.overlap_refill else None
+        if self.overlap_refill and side is None:
+            side = self._refill_stream = torch.cuda.Stream(self._device)
+        pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
+        while any(o >= 0 for o in owner) or pending:
+            if any(o >= 0 for o in owner):
+                self._decode(interval)
+            # second half of the refills started after the previous read: behind the decode launch just enqueued, so
+            # the prompt was computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
+            for slot, r, keep, ev in pending:
+                main.wait_event(ev)
+                self._prefill_finish(slot, keep[1], sampling(r))
+                owner[slot] = r
+            done_refills, pending = pending, []
             self._read(slots)
+            del done_refills              # their prompt tensors were needed until the second half had run
             for s in range(slots):
                 if owner[s] >= 0 and not int(self._h_active[s]):
                     n_gen = int(self._h_ngen[s])
@@ -357,9 +389,17 @@ class Text2SemanticDecoder(nn.Module):
                         toks = toks[:-1]
                     results.append(toks.to(self._device))
                     order.append(owner[s])
-                    owner[s] = -1
+                    owner[s] = FREE
                     if nxt < B:
-                        start(s, nxt)
-                        owner[s] = nxt
+                        if side is None:
+                            start(s, nxt)
+                            owner[s] = nxt
+                        else:
+                            with torch.cuda.stream(side):
+                                keep = self._prefill_begin(s, x[nxt], y[nxt], bert_feature[nxt])
+                                ev = torch.cuda.Event()
+                                ev.record(side)
+                            pending.append((s, nxt, keep, ev))
+                            owner[s] = REFILLING
                         nxt += 1
         return results, torch.tensor(order, device=self._device)

@@ -52,6 +52,8 @@ SYMBOLS = [
     ("gsv_gpt_create", C.c_int, [C.POINTER(GptDims), C.POINTER(GptWeights), C.POINTER(_P)]),
     ("gsv_gpt_destroy", C.c_int, [_P]),
     ("gsv_gpt_prefill", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.POINTER(GptSampling), _P]),
+    ("gsv_gpt_prefill_begin", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
+    ("gsv_gpt_prefill_finish", C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(GptSampling), _P]),
     ("gsv_gpt_decode", C.c_int, [_P, C.c_int, _P]),
     ("gsv_gpt_read", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     ("gsv_gpt_state_ptrs", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),

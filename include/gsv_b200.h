@@ -110,6 +110,18 @@ int gsv_gpt_destroy(gsv_gpt_ctx* ctx);
 int gsv_gpt_prefill(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
                     const void* dev_bert, const gsv_gpt_sampling* samp, void* stream);
 
+/* The same prefill in two halves, for refilling a slot of a running batch without stalling the other slots (the
+ * reference prefills a finished slot's successor eagerly between two decode steps, t2s_model.py:696-722, and every
+ * live slot waits for it).  `begin` computes the prompt (embeddings, all layers, the slot's K/V rows) and may be
+ * enqueued on ANOTHER stream while gsv_gpt_decode launches run: decode kernels never touch an inactive slot.
+ * `finish` samples the first token and makes the slot live; enqueue it on the stream of the decode launches, after
+ * the caller has ordered it behind `begin` (event).  The slot must be idle (its previous sequence finished or
+ * released); dev_y must stay valid until `finish` has run. */
+int gsv_gpt_prefill_begin(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int nx, const int64_t* dev_y, int ny,
+                          const void* dev_bert, void* stream);
+int gsv_gpt_prefill_finish(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_y, int ny, const gsv_gpt_sampling* samp,
+                           void* stream);
+
 /* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
  * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
  * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).

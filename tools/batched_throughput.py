@@ -21,11 +21,15 @@ xs = [t.to(dev) for t in xs]; ys = [t.to(dev) for t in ys]; bs = [t.to(dev, torc
 m.debug_seed = 5
 m.infer_batched(xs[:40], ys[:40], bs[:40], max_new=[20] * 40)          # warm-up (kernel selection, weight re-tiling)
 torch.cuda.synchronize()
-l0 = int(N.lib().gsv_gpt_launch_count(m._ctx))
-t0 = time.perf_counter()
-outs, order = m.infer_batched(xs, ys, bs, max_new=mx)
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-tok = sum(int(o.numel()) for o in outs)
-print(f"{R} requests, 32 slots: {tok} tokens in {dt*1e3:.1f} ms -> {tok/dt:.0f} tok/s, {tok*0.04/dt:.0f} audio-s/s (GPT stage), "
-      f"{int(N.lib().gsv_gpt_launch_count(m._ctx)) - l0} launches; mean length {tok/R:.1f}")
+for overlap in (True, False):
+    m.overlap_refill = overlap
+    m.debug_seed = 5
+    l0 = int(N.lib().gsv_gpt_launch_count(m._ctx))
+    t0 = time.perf_counter()
+    outs, order = m.infer_batched(xs, ys, bs, max_new=mx)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tok = sum(int(o.numel()) for o in outs)
+    print(f"{R} requests, 32 slots, refill prompts {'on a second stream' if overlap else 'between decode launches'}: {tok} tokens in "
+          f"{dt*1e3:.1f} ms -> {tok/dt:.0f} tok/s, {tok*0.04/dt:.0f} audio-s/s (GPT stage), "
+          f"{int(N.lib().gsv_gpt_launch_count(m._ctx)) - l0} launches; mean length {tok/R:.1f}")
