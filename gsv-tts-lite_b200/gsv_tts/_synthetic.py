@@ -178,3 +178,48 @@ def sovits_flow_dec_state_dict(model: dict, seed: int = 0) -> Dict[str, torch.Te
                 sd[rp + f"convs2.{c}.bias"] = _randn(g, ch, std=0.05)
     sd["dec.conv_post.weight"] = _randn(g, 1, ch, 7, std=0.6 / math.sqrt(ch * 7))
     return sd
+
+
+def sovits_encp_state_dict(model: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 tensors with the key set and shapes of the reference's ``enc_p.*``, ``quantizer`` codebook and ``ge_to512``
+    (SoVITS/models.py:141-194, 305-317; probed from the reference module, checked by oracle/make_golden.py).  Scales are
+    chosen so that activations stay O(1) through the 12 encoder layers; LayerNorm gains / biases are randomised."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    C, Fc, H, L = model["hidden_channels"], model["filter_channels"], model["n_heads"], model["n_layers"]
+    k = model["kernel_size"]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_c, in_c, kk=1):
+        sd[name + ".weight"] = _randn(g, out_c, in_c, kk, std=(in_c * kk) ** -0.5)
+        sd[name + ".bias"] = _randn(g, out_c, std=0.05)
+
+    def enc(pre, n):
+        for i in range(n):
+            a = f"{pre}.attn_layers.{i}"
+            sd[a + ".emb_rel_k"] = _randn(g, 1, 9, C // H, std=(C // H) ** -0.5)
+            sd[a + ".emb_rel_v"] = _randn(g, 1, 9, C // H, std=(C // H) ** -0.5)
+            for nm in ("conv_q", "conv_k", "conv_v", "conv_o"):
+                lin(f"{a}.{nm}", C, C)
+            for j in (1, 2):
+                sd[f"{pre}.norm_layers_{j}.{i}.gamma"] = 1.0 + _randn(g, C, std=0.1)
+                sd[f"{pre}.norm_layers_{j}.{i}.beta"] = _randn(g, C, std=0.1)
+            lin(f"{pre}.ffn_layers.{i}.conv_1", Fc, C, k)
+            lin(f"{pre}.ffn_layers.{i}.conv_2", C, Fc, k)
+
+    lin("enc_p.ssl_proj", C, 768)
+    enc("enc_p.encoder_ssl", L // 2)
+    enc("enc_p.encoder_text", L)
+    sd["enc_p.text_embedding.weight"] = _randn(g, 732, C, std=1.0)
+    for nm in ("conv_q", "conv_k", "conv_v", "conv_o"):
+        lin(f"enc_p.mrte.cross_attention.{nm}", 512, 512)
+    lin("enc_p.mrte.c_pre", 512, C)
+    lin("enc_p.mrte.text_pre", 512, C)
+    lin("enc_p.mrte.c_post", C, 512)
+    enc("enc_p.encoder2", L // 2)
+    lin("enc_p.proj", 2 * model["inter_channels"], C)
+    sd["enc_p.proj.bias"][model["inter_channels"]:] -= 1.0          # logs around -1: exp(logs) stays tame
+    sd["quantizer.vq.layers.0._codebook.embed"] = _randn(g, 1024, 768, std=1.0)
+    if model.get("version") in ("v2Pro", "v2ProPlus"):
+        lin("ge_to512", 512, model["gin_channels"])
+        sd["ge_to512.weight"] = sd["ge_to512.weight"][:, :, 0].contiguous()
+    return sd

@@ -149,14 +149,56 @@ def make_vocoder(name, key, B, T, masked_tail, ge_per_frame=False, with16=True):
     print(msg)
 
 
+def make_encp(name, key):
+    """Row f-1: outputs of the reference's own quantizer / ge_to512 / TextEncoder on synthetic weights:
+    plain call, speed != 1, two streaming chunks with the cross-fade state, and a slice_indices call (MRTE window)."""
+    import torch.nn.functional as F
+    model = dict(syn.SOVITS_MODEL[key])
+    M = ref_shim.sovits_models()
+    net = M.SynthesizerTrn(1025, 32, n_speakers=300, **model).eval()
+    sd = syn.sovits_encp_state_dict(model, 0)
+    ref = net.state_dict()
+    want = {k for k in ref if k.startswith(("enc_p.", "ge_to512."))} | {"quantizer.vq.layers.0._codebook.embed"}
+    assert set(sd) == want, set(sd) ^ want                       # the synthetic writer follows the reference's key set ...
+    assert all(sd[k].shape == ref[k].shape for k in sd)           # ... and shapes
+    net.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(4321)
+    n, nt = 13, 9
+    codes = torch.randint(0, 1024, (1, 1, n), generator=g)
+    text = torch.randint(0, 732, (1, nt), generator=g)
+    ge = torch.randn(1, model["gin_channels"], 1, generator=g)
+    noise = torch.randn(1, model["inter_channels"], 2 * n, generator=g)
+    q = F.interpolate(net.quantizer.decode(codes), size=2 * n, mode="nearest")
+    gin = net.ge_to512(ge.transpose(2, 1)).transpose(2, 1) if net.is_v2pro else ge
+    out = dict(codes=codes.numpy(), text=text.numpy(), ge=ge.numpy(), noise=noise.numpy(), quantized=q.numpy())
+    m, logs, mask = net.enc_p.infer(q, text, gin, 1)
+    out.update(m_p=m.numpy(), logs_p=logs.numpy(), z_p=(m + noise * torch.exp(logs) * 0.5).numpy())
+    m, logs, mask = net.enc_p.infer(q, text, gin, 1.3)
+    out.update(m_p_speed=m.numpy(), logs_p_speed=logs.numpy(), speed=np.float32(1.3))
+    sl = torch.tensor([[2, 7]])
+    m, logs, mask = net.enc_p.infer(q, text, gin, 1, slice_indices=sl)
+    out.update(m_p_slice=m.numpy(), slice_indices=sl.numpy())
+    net.enc_p.y_overlap = None
+    chunks = [(8, 0), (13, 5)]                                   # (codes so far, valid_start_idx), overlap_len 5
+    for i, (nn_, vs) in enumerate(chunks):
+        m, logs, mask = net.enc_p.infer(q[:, :, : 2 * nn_], text, gin, 1, True, vs, 5)
+        out[f"m_p_stream{i}"] = m.numpy()
+    out["stream_chunks"] = np.array(chunks)
+    np.savez_compressed(os.path.join(OUT, f"encp_{name}.npz"), **out)
+    print(f"encp {name}: m_p std {float(out['m_p'].std()):.3f} logs mean {float(out['logs_p'].mean()):.3f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["gpt", "batched", "voc"]
+    which = sys.argv[1:] or ["gpt", "batched", "voc", "encp"]
     if "gpt" in which:
         make_gpt("tiny", syn.GPT_CONFIG_TINY, nx=40, ny=30, n_forced=12, max_seq=256, eos_boost=6.0, infer_seed=7, with_bf16=True)
         make_gpt("full", syn.GPT_CONFIG, nx=48, ny=60, n_forced=8, max_seq=512, eos_boost=6.0, infer_seed=11, with_bf16=True)
     if "batched" in which:
         make_gpt_batched("tiny_batched", syn.GPT_CONFIG_TINY, n_req=7, slots=4, max_seq=256, eos_boost=6.0)
+    if "encp" in which:
+        make_encp("v2pro", "v2Pro")
+        make_encp("v2", "v2")
     if "voc" in which:
         make_vocoder("tiny", "tiny", B=2, T=20, masked_tail=5)
         make_vocoder("tiny_ge_t", "tiny", B=1, T=16, masked_tail=0, ge_per_frame=True)
