@@ -297,8 +297,8 @@ def test_eight_slots_batched_matches_two_slots(dev):
 
 
 def test_thirty_two_slots_continuous_batch(dev):
-    """BASELINE config 3 in miniature: 44 ragged requests through 32 slots (more than 24 live sequences run the
-    multi-kernel tcgen05 step, the tail drains through the cluster kernel, slots are refilled from the queue) and
+    """BASELINE config 3 in miniature: 44 ragged requests through 32 slots (eight sequences per cluster on the
+    tensor-core cluster kernel, slots refilled from the queue with their prompts computed on a second stream) and
     through 2 slots: every request completes exactly once, tokens are in range and cut at EOS / max_new, and
     per-request tokens agree for (nearly) every request -- the kernels sum in different orders and round
     activations at different points, so a rare near-tie may flip."""
