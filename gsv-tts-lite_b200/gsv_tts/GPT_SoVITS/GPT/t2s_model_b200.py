@@ -202,6 +202,23 @@ class Text2SemanticDecoder(nn.Module):
         previous chunk on another stream (``TTS.infer_features_stream``)."""
         N.check(N.lib().gsv_gpt_set_decode_sms(self._ctx, int(n_sms)))
 
+    # second-stream plumbing of infer_batched (separate methods so that the CPU tests can script them)
+    def _side_stream(self):
+        if self._refill_stream is None:
+            self._refill_stream = torch.cuda.Stream(self._device)
+        return self._refill_stream
+
+    def _on_stream(self, stream):
+        return torch.cuda.stream(stream)
+
+    def _record_event(self, stream):
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def _wait_on_current_stream(self, ev):
+        torch.cuda.current_stream(self._device).wait_event(ev)
+
     def _mark_chunk_ready(self):
         """Event behind the host->device copy of the chunk about to be handed out: a consumer on another stream waits
         for this, not for the decode launched after it."""
@@ -364,10 +381,7 @@ class Text2SemanticDecoder(nn.Module):
             nxt += 1
         results, order = [], []
         interval = max(int(check_interval), self.BATCH_INTERVAL)
-        main = torch.cuda.current_stream(self._device)
-        side = self._refill_stream if self.overlap_refill else None
-        if self.overlap_refill and side is None:
-            side = self._refill_stream = torch.cuda.Stream(self._device)
+        side = self._side_stream() if self.overlap_refill else None
         pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
         while any(o >= 0 for o in owner) or pending:
             if any(o >= 0 for o in owner):
@@ -375,7 +389,7 @@ class Text2SemanticDecoder(nn.Module):
             # second half of the refills started after the previous read: behind the decode launch just enqueued, so
             # the prompt was computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
             for slot, r, keep, ev in pending:
-                main.wait_event(ev)
+                self._wait_on_current_stream(ev)
                 self._prefill_finish(slot, keep[1], sampling(r))
                 owner[slot] = r
             done_refills, pending = pending, []
@@ -395,10 +409,9 @@ class Text2SemanticDecoder(nn.Module):
                             start(s, nxt)
                             owner[s] = nxt
                         else:
-                            with torch.cuda.stream(side):
+                            with self._on_stream(side):
                                 keep = self._prefill_begin(s, x[nxt], y[nxt], bert_feature[nxt])
-                                ev = torch.cuda.Event()
-                                ev.record(side)
+                                ev = self._record_event(side)
                             pending.append((s, nxt, keep, ev))
                             owner[s] = REFILLING
                         nxt += 1
