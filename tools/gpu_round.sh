@@ -12,4 +12,6 @@ tail -2 gpurun_out/ncu_full.log | cut -c1-300
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gpt_decode_cl8 -s 1 -c 1 -o gpurun_out/prof_cl8 -f \
     python tools/decode_speed.py 32 > gpurun_out/ncu_cl8.log 2>&1
 tail -2 gpurun_out/ncu_cl8.log | cut -c1-300
+# continuous batching (GPT stage), both refill modes
+timeout 120 python tools/batched_throughput.py 128 > gpurun_out/batched.log 2>&1; tail -2 gpurun_out/batched.log
 ls -la gpurun_out
