@@ -426,6 +426,35 @@ def extras(gpt, voc, dev, dtype, lib, N, syn):
         out["vocoder_b16_500f_audio_s_per_s"] = 16 * 10.0 / (ms / 1e3)
     except Exception as e:      # extras must never break the headline line
         out["error"] = f"{type(e).__name__}: {e}"
+    try:
+        # SURVEY.md 8d config 3 (GPT stage): 128 mixed requests through 32 slots of infer_batched (continuous batching;
+        # Nx ~ U{40..120}, Ny ~ U{75..250}, length ~ U{50..250} via max_new), wall clock, both refill modes
+        import time as _t
+        m = Text2SemanticDecoder(syn.GPT_CONFIG)
+        m.load_state_dict(syn.gpt_state_dict(syn.GPT_CONFIG, 0))
+        m.initialize_runtime(dtype, dev, [(32, 1024)])
+        g = torch.Generator().manual_seed(1234)
+        xs, ys, bs, mx = [], [], [], []
+        for _ in range(128):
+            nx = int(torch.randint(40, 121, (1,), generator=g))
+            ny = int(torch.randint(75, 251, (1,), generator=g))
+            xs.append(torch.randint(0, 732, (nx,), generator=g).to(dev))
+            ys.append(torch.randint(0, 1024, (ny,), generator=g).to(dev))
+            bs.append(torch.zeros(nx, 1024, device=dev, dtype=dtype))
+            mx.append(int(torch.randint(50, 251, (1,), generator=g)))
+        m.debug_seed = 5
+        m.infer_batched(xs[:40], ys[:40], bs[:40], max_new=[20] * 40)        # warm-up (weight re-tiling, kernel attributes)
+        for overlap, tag in ((True, "batched128_tok_s"), (False, "batched128_serial_refill_tok_s")):
+            m.overlap_refill = overlap
+            m.debug_seed = 5
+            torch.cuda.synchronize()
+            t0 = _t.perf_counter()
+            outs, _ = m.infer_batched(xs, ys, bs, max_new=mx)
+            torch.cuda.synchronize()
+            out[tag] = sum(int(o.numel()) for o in outs) / (_t.perf_counter() - t0)
+        del m
+    except Exception as e:
+        out["error_batched"] = f"{type(e).__name__}: {e}"
     return out
 
 
