@@ -61,7 +61,7 @@ struct Cl8Shared {
   float apart[NWARP][GSV_HEAD_DIM + 2];     // attention partials per warp: m, l, o[32]
   float xres[NB8][GSV_HEAD_DIM];            // residual rows of this CTA for the out-proj (layer input x)
   float xres1[NB8][GSV_HEAD_DIM];           // ... and for the MLP-down (x1)
-  __align__(16) float stage[NWARP][NB8][4]; // per-warp staging of a phase's results before they are pushed (16 B per sequence)
+  __align__(16) float stage[NWARP][NB8][4]; // per-warp staging of the attention output (32 values in the storage type) before it is pushed
   float alive[NB8];                         // pushed by the sampler CTAs together with the next inputs
   int alive_i;
   int slot[NB8], kv[NB8];
