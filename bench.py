@@ -380,7 +380,7 @@ def extras(gpt, voc, dev, dtype, lib, N, syn):
         for B in (4, 8, 16, 32):
             m._release_all()
             for s in range(B):
-                samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0,
+                samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0, suppress_first=0,
                                      max_new_tokens=0, mask_eos=1, max_kv=512, seed=s + 1)
                 m._prefill(s, torch.randint(0, 732, (NX,), generator=g), torch.randint(0, 1024, (NY + 100,), generator=g),
                            torch.zeros(NX, 1024), samp)

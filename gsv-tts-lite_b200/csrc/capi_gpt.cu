@@ -88,8 +88,7 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(p.y2, B * d * sizeof(float), true);
   A(p.logits, B * GSV_VOCAB_MAX * sizeof(float), true);
   A(p.barrier, 64, true);
-  A(p.forced_pos, 64, true);
-  A(p.trace_pos, 64, true);
+  A(ctx->hooks_dev, GSV_MAX_SLOTS * sizeof(GptSlotHooks), true);
   A(ctx->pf_x, S * d * 2, false);
   A(ctx->pf_qkv, S * 3 * d * 2, false);
   A(ctx->pf_attn, S * d * 2, false);
@@ -255,28 +254,56 @@ static void invalidate_step_graph(gsv_gpt_ctx* ctx) {
   }
 }
 
+// Parity hooks live in a device array indexed by slot; the kernels see it only while at least one hook is set.
+static int push_slot_hooks(gsv_gpt_ctx* ctx, int slot, const GptSlotHooks& h, cudaStream_t st, bool device_sync) {
+  GptSlotHooks& cur = ctx->hooks_host[slot];
+  if (cur.noise == h.noise && cur.noise_rows == h.noise_rows && cur.forced == h.forced && cur.n_forced == h.n_forced &&
+      cur.trace == h.trace && cur.trace_max == h.trace_max && !(h.noise || h.forced || h.trace))
+    return GSV_OK;                                  // off -> off: nothing to do (the product path never pays for a hook)
+  cur = h;
+  if (device_sync) {
+    GSV_CUDA(cudaDeviceSynchronize());
+    GSV_CUDA(cudaMemcpy(ctx->hooks_dev + slot, &cur, sizeof(cur), cudaMemcpyHostToDevice));
+  } else {
+    GSV_CUDA(cudaMemcpyAsync(ctx->hooks_dev + slot, &cur, sizeof(cur), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  }
+  bool any = false;
+  for (int i = 0; i < ctx->p.slots; ++i) any = any || ctx->hooks_host[i].noise || ctx->hooks_host[i].forced || ctx->hooks_host[i].trace;
+  GptSlotHooks* want = any ? ctx->hooks_dev : nullptr;
+  if (want != ctx->p.hooks) { invalidate_step_graph(ctx); ctx->p.hooks = want; }
+  return GSV_OK;
+}
+
+extern "C" int gsv_gpt_set_slot_hooks(gsv_gpt_ctx* ctx, int slot, const float* dev_noise, int n_noise_rows, const int32_t* dev_forced,
+                                      int n_forced, float* dev_trace_rows, int max_trace_rows, void* stream) {
+  GSV_ARG(ctx && slot >= 0 && slot < ctx->p.slots);
+  GptSlotHooks h;
+  memset(&h, 0, sizeof(h));
+  h.noise = dev_noise; h.noise_rows = dev_noise ? n_noise_rows : 0;
+  h.forced = dev_forced; h.n_forced = dev_forced ? n_forced : 0;
+  h.trace = dev_trace_rows; h.trace_max = dev_trace_rows ? max_trace_rows : 0;
+  return push_slot_hooks(ctx, slot, h, (cudaStream_t)stream, false);
+}
+
 extern "C" int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows) {
   GSV_ARG(ctx);
-  if (ctx->p.noise != dev_noise || ctx->p.noise_rows != (dev_noise ? n_rows : 0)) invalidate_step_graph(ctx);
-  ctx->p.noise = dev_noise;
-  ctx->p.noise_rows = dev_noise ? n_rows : 0;
-  return GSV_OK;
+  GptSlotHooks h = ctx->hooks_host[0];
+  h.noise = dev_noise; h.noise_rows = dev_noise ? n_rows : 0; h.forced_pos = 0; h.trace_pos = 0;
+  return push_slot_hooks(ctx, 0, h, nullptr, true);
 }
 
 extern "C" int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n) {
   GSV_ARG(ctx);
-  if (ctx->p.forced != dev_forced || ctx->p.n_forced != (dev_forced ? n : 0)) invalidate_step_graph(ctx);
-  ctx->p.forced = dev_forced;
-  ctx->p.n_forced = dev_forced ? n : 0;
-  return GSV_OK;
+  GptSlotHooks h = ctx->hooks_host[0];
+  h.forced = dev_forced; h.n_forced = dev_forced ? n : 0; h.forced_pos = 0; h.trace_pos = 0;
+  return push_slot_hooks(ctx, 0, h, nullptr, true);
 }
 
 extern "C" int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows) {
   GSV_ARG(ctx);
-  if (ctx->p.trace != dev_rows || ctx->p.trace_max != (dev_rows ? max_rows : 0)) invalidate_step_graph(ctx);
-  ctx->p.trace = dev_rows;
-  ctx->p.trace_max = dev_rows ? max_rows : 0;
-  return GSV_OK;
+  GptSlotHooks h = ctx->hooks_host[0];
+  h.trace = dev_rows; h.trace_max = dev_rows ? max_rows : 0; h.forced_pos = 0; h.trace_pos = 0;
+  return push_slot_hooks(ctx, 0, h, nullptr, true);
 }
 
 extern "C" int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -741,7 +741,13 @@ int launch_ll_nb(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   int ns = n_steps;
   // tags never repeat between launches: launch sequence in the high 16 bits, phase counter below
   ctx->ll_seq += 1;
-  unsigned tag_base = (unsigned)(ctx->ll_seq << 16);
+  if ((ctx->ll_seq & 0xffffull) == 0) {
+    // the 16-bit launch sequence wraps every 65 536 launches: clear every cell (a rarely written one could still hold
+    // a tag of the previous lap) and skip sequence 0, whose tags equal the cleared value
+    GSV_CUDA(cudaMemsetAsync(ctx->ll_buf, 0, gsv_gpt_ll_buffer_bytes(ctx), st));
+    ctx->ll_seq += 1;
+  }
+  unsigned tag_base = (unsigned)(ctx->ll_seq << 16);      // tags never repeat between launches
   uint2* buf = reinterpret_cast<uint2*>(ctx->ll_buf);
   void* args[] = {&p, &ns, &tag_base, &buf};
   int grid = ctx->num_sms;

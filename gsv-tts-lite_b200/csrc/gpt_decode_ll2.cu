@@ -872,6 +872,12 @@ int launch_ll2_nb(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   GptParams p = ctx->p;
   int ns = n_steps;
   ctx->ll_seq += 1;
+  if ((ctx->ll_seq & 0xffffull) == 0) {
+    // the 16-bit launch sequence wraps every 65 536 launches: clear every cell (a rarely written one could still hold
+    // a tag of the previous lap) and skip sequence 0, whose tags equal the cleared value
+    GSV_CUDA(cudaMemsetAsync(ctx->ll_buf, 0, gsv_gpt_ll_buffer_bytes(ctx), st));
+    ctx->ll_seq += 1;
+  }
   unsigned tag_base = (unsigned)(ctx->ll_seq << 16);      // tags never repeat between launches
   uint2* buf = reinterpret_cast<uint2*>(ctx->ll_buf);
   void* args[] = {&p, &ns, &tag_base, &buf};

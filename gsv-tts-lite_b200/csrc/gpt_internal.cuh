@@ -10,6 +10,16 @@
 #define GSV_DECODE_THREADS 512
 #define GSV_VOCAB_MAX 2048       // sampling scratch is sized for this
 
+// Parity hooks of one slot (tests only; they do not change the arithmetic).  Device-resident so that a refill can
+// re-point them between two launches without touching the kernels' parameter block.
+struct GptSlotHooks {
+  const float* noise;   // [noise_rows][V] Exp(1) rows consumed one per sample() call of the slot's current request
+  const int* forced;    // [n_forced] teacher forcing: the i-th sample() call returns forced[i]
+  float* trace;         // [trace_max][V] raw logits appended per sample() call (row 0 = prefill)
+  int noise_rows, n_forced, trace_max;
+  int forced_pos, trace_pos, pad;
+};
+
 struct GptParams {
   int d, H, L, F, V, eos, S, slots, n_pos, d_bert, n_phoneme;
   // weights (element type T)
@@ -38,10 +48,8 @@ struct GptParams {
   float* y2;      // [slots][d] pre-LN2
   float* logits;  // [slots][GSV_VOCAB_MAX]
   unsigned* barrier;
-  // parity hooks
-  const float* noise; int noise_rows;
-  const int* forced; int n_forced; int* forced_pos;
-  float* trace; int trace_max; int* trace_pos;
+  // parity hooks: [slots], or nullptr while none is set (the product path)
+  GptSlotHooks* hooks;
   // in-kernel timeline (tools/decode_timeline.py): {id, clock64} records written by one CTA
   long long* prof; int prof_max; int prof_cta;
 };
@@ -67,6 +75,8 @@ struct gsv_gpt_ctx {
   void* ll_buf;
   unsigned long long ll_seq;
   int slot_live[GSV_MAX_SLOTS];   // host-side view: prefilled and not yet released
+  GptSlotHooks* hooks_dev;        // [slots] device copy of the parity hooks
+  GptSlotHooks hooks_host[GSV_MAX_SLOTS];
   gsv_umma_cache* umma;           // tensor-map cache of the prefill / batched-decode linears
   void *dx, *dqkv, *datt, *dh, *dtmp;   // batched decode step rows [slots][.] (T)
   void* step_graph_exec;          // cudaGraphExec_t of one batched decode step

@@ -240,10 +240,7 @@ __global__ void slot_reset_kernel(const GptParams p, int slot, int nx, int n, co
     p.samp_count[slot] = 0ull;
     p.active[slot] = 1;
     p.samp[slot] = samp;
-    if (slot == 0) {
-      if (p.forced_pos) *p.forced_pos = 0;
-      if (p.trace_pos) *p.trace_pos = 0;
-    }
+    if (p.hooks) { p.hooks[slot].forced_pos = 0; p.hooks[slot].trace_pos = 0; }
   }
 }
 
@@ -523,11 +520,11 @@ int decode_step_launches(gsv_gpt_ctx* ctx, cudaStream_t st) {
 template <typename T>
 int decode_gemm_impl(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   const GptParams& p = ctx->p;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0ull;        // one bit per device
+  if (!((attr_set >> (ctx->device & 63)) & 1ull)) {
     GSV_CUDA(cudaFuncSetAttribute(sample_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(GSV_SAMPLE_SMEM_FLOATS * sizeof(float))));
-    attr_set = true;
+    attr_set |= 1ull << (ctx->device & 63);
   }
   xin_to_x_kernel<T><<<p.slots, 128, 0, st>>>(p, reinterpret_cast<T*>(ctx->dx));
   ctx->launches += 1;

@@ -92,26 +92,36 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   const unsigned long long cnt = __ldcg(p.samp_count + slot);
   __syncthreads();
 
-  // raw logits (+ optional trace of slot 0 for the teacher-forced parity test)
+  // raw logits (+ optional trace of the slot for the teacher-forced / audited parity tests)
+  GptSlotHooks* const hk = p.hooks ? p.hooks + slot : nullptr;     // CTA-uniform
+  const float* hk_noise = nullptr; const int* hk_forced = nullptr; float* hk_trace = nullptr;
+  int hk_noise_rows = 0, hk_n_forced = 0;
   int trow = -1;
-  if (slot == 0 && p.trace != nullptr) {
-    trow = ld_cg(p.trace_pos);
-    if (trow >= p.trace_max) trow = -1;
+  if (hk) {
+    hk_noise = hk->noise; hk_noise_rows = hk->noise_rows;
+    hk_forced = hk->forced; hk_n_forced = hk->n_forced;
+    hk_trace = hk->trace;
+    if (hk_trace) {
+      trow = ld_cg(&hk->trace_pos);
+      if (trow >= hk->trace_max) trow = -1;
+    }
   }
   const bool preloaded = ll != nullptr && ll->preloaded;
   for (int v = tid; v < GSV_VOCAB_MAX; v += NT) {
     float l = GSV_NEG_INF;
     if (v < p.V) {
       l = preloaded ? lg[v] : ld_cg(p.logits + (size_t)slot * GSV_VOCAB_MAX + v);
-      if (trow >= 0) p.trace[(size_t)trow * p.V + v] = l;
+      if (trow >= 0) hk_trace[(size_t)trow * p.V + v] = l;
       if (v >= Vv) l = GSV_NEG_INF;
     }
     lg[v] = l;
   }
   __syncthreads();
-  const bool suppress = first ? (sp.suppress_steps > 0) : (ngen < sp.suppress_steps);
+  // the first sample of infer / infer_stream masks the suppressed tokens whatever initial_suppression_steps is
+  // (t2s_model.py:415); infer_batched never does (:613)
+  const bool suppress = first ? (sp.suppress_first != 0) : (ngen < sp.suppress_steps);
   if (tid == 0) {
-    if (trow >= 0) st_cg(p.trace_pos, trow + 1);
+    if (trow >= 0) st_cg(&hk->trace_pos, trow + 1);
     if (suppress) {                                       // suppressed_tokens = [280, 486, EOS] (:170)
       if (280 < Vv) lg[280] = GSV_NEG_INF;
       if (486 < Vv) lg[486] = GSV_NEG_INF;
@@ -276,12 +286,12 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   // (6) token = argmax(p / q), q ~ Exp(1) i.i.d. per column (utils.py:5-9)
   ArgMax best;
   best.v = -1.0f; best.i = 0x7fffffff;
-  const bool ext = p.noise != nullptr && slot == 0 && cnt < (unsigned long long)p.noise_rows;
+  const bool ext = hk_noise != nullptr && cnt < (unsigned long long)hk_noise_rows;
   const uint2 key = make_uint2((uint32_t)sp.seed, (uint32_t)(sp.seed >> 32));
   for (int v = tid; v < Vv; v += NT) {
     float q;
     if (ext) {
-      q = p.noise[(size_t)cnt * p.V + v];
+      q = hk_noise[(size_t)cnt * p.V + v];
     } else {
       uint4 r = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)(v >> 2), 0u), key);   // slot-independent: the seed names the request
       uint32_t bits = (v & 3) == 0 ? r.x : (v & 3) == 1 ? r.y : (v & 3) == 2 ? r.z : r.w;
@@ -298,12 +308,12 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   // bookkeeping by one thread; every value other CTAs read later goes through st.cg
   const int kvl = ll ? ll->kv_len : ld_cg(p.kv_len + slot);
   if (sp.max_new_tokens > 0 && ngen > sp.max_new_tokens) tok = p.eos;    // ngen counts s0 too
-  if (slot == 0 && p.forced != nullptr) {        // CTA-uniform branch
-    int fp = ld_cg(p.forced_pos);
+  if (hk_forced != nullptr) {                    // CTA-uniform branch
+    int fp = ld_cg(&hk->forced_pos);
     __syncthreads();                              // every thread has read the cursor before thread 0 moves it
-    if (fp < p.n_forced) {
-      tok = p.forced[fp];
-      if (tid == 0) st_cg(p.forced_pos, fp + 1);
+    if (fp < hk_n_forced) {
+      tok = hk_forced[fp];
+      if (tid == 0) st_cg(&hk->forced_pos, fp + 1);
     }
   }
   const int kv_cap = (sp.max_kv > 0 && sp.max_kv < p.S) ? sp.max_kv : p.S;

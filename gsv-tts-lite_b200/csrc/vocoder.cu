@@ -448,11 +448,13 @@ bool umma_eligible(const ConvArgs<T>& a) {
 
 template <typename T, int BN, int BK>
 int launch_umma_inst(const umma::Params<T>& P, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0ull;        // one bit per device: the attribute is per device, not per process
+  int dev = 0;
+  GSV_CUDA(cudaGetDevice(&dev));
+  if (!((attr_set >> (dev & 63)) & 1ull)) {
     GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_kernel<T, BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   umma::kSmemBudget + 2048));
-    attr_set = true;
+    attr_set |= 1ull << (dev & 63);
   }
   static int use_pdl = -1;
   if (use_pdl < 0) { const char* e = getenv("GSV_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }

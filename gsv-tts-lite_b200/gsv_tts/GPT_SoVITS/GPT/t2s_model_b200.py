@@ -73,6 +73,8 @@ class Text2SemanticDecoder(nn.Module):
     N_POS = 4000                      # t2s_model.py:212-213
     DECODE_CHUNK = 32                 # decode steps per persistent launch in infer()
     BATCH_INTERVAL = 8                # decode steps between harvest/refill points in infer_batched()
+    _slot_audit = None                # test hook: callable(slot, request) -> (noise, forced, trace) device tensors or None
+                                      # each; attached to the slot right before the request's first sample (infer_batched)
 
     def __init__(self, config):
         super().__init__()
@@ -246,7 +248,7 @@ class Text2SemanticDecoder(nn.Module):
                              temperature=temperature, repetition_penalty=repetition_penalty,
                              suppress_steps=suppress_steps, max_new_tokens=0,
                              mask_eos=1 if force_steps is not None else 0, max_kv=self._buckets[1][-1],
-                             seed=self._next_seed())
+                             suppress_first=1, seed=self._next_seed())
         if self._parity_noise is not None:
             N.check(N.lib().gsv_gpt_set_noise(self._ctx, self._parity_noise.data_ptr(), self._parity_noise.shape[0]))
         else:
@@ -367,9 +369,19 @@ class Text2SemanticDecoder(nn.Module):
             return N.GptSampling(top_k=top_k if top_k is not None else 0, top_p=top_p if top_p is not None else 1.0,
                                  temperature=temperature, repetition_penalty=1.0, suppress_steps=0,
                                  max_new_tokens=(max_new[r] if max_new is not None else 0), mask_eos=0,
-                                 max_kv=max_kv, seed=(base_seed + 0x9E3779B97F4A7C15 * (r + 1)) & (2 ** 64 - 1))
+                                 max_kv=max_kv, suppress_first=0,
+                                 seed=(base_seed + 0x9E3779B97F4A7C15 * (r + 1)) & (2 ** 64 - 1))
+
+        def audit(slot, r):
+            if self._slot_audit is not None:
+                noise, forced, trace = self._slot_audit(slot, r)
+                N.check(N.lib().gsv_gpt_set_slot_hooks(
+                    self._ctx, slot, noise.data_ptr() if noise is not None else None, noise.shape[0] if noise is not None else 0,
+                    forced.data_ptr() if forced is not None else None, forced.numel() if forced is not None else 0,
+                    trace.data_ptr() if trace is not None else None, trace.shape[0] if trace is not None else 0, self._stream()))
 
         def start(slot, r):
+            audit(slot, r)
             self._prefill(slot, x[r], y[r], bert_feature[r], sampling(r))
 
         FREE, REFILLING = -1, -2
@@ -390,6 +402,7 @@ class Text2SemanticDecoder(nn.Module):
             # the prompt was computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
             for slot, r, keep, ev in pending:
                 self._wait_on_current_stream(ev)
+                audit(slot, r)
                 self._prefill_finish(slot, keep[1], sampling(r))
                 owner[slot] = r
             done_refills, pending = pending, []

@@ -21,6 +21,9 @@ import io
 import json
 import os
 import re
+import sys
+import types
+import contextlib
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -74,8 +77,39 @@ def read_gpt_checkpoint(path: str) -> Tuple[dict, Dict[str, torch.Tensor]]:
         with open(os.path.join(path, "config.json")) as f:
             config = json.load(f)
         return config, load_file(os.path.join(path, "model.safetensors"))
-    blob = torch.load(path, map_location="cpu", weights_only=False)
-    return blob["config"], remap_gpt_keys(blob["weight"])
+    with _upstream_pickle_modules():
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+    return _to_plain(blob["config"]), remap_gpt_keys(blob["weight"])
+
+
+class _AttrBag:
+    """Stand-in for the classes upstream checkpoints pickle their ``config`` with (``utils.HParams``,
+    ``utils.DictToAttrRecursive``): unpickling only needs ``__new__`` + ``__dict__`` / ``__setstate__``."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {})
+
+    def __setitem__(self, key, value):          # DictToAttrRecursive is a dict subclass: items arrive through SETITEMS
+        self.__dict__[key] = value
+
+
+@contextlib.contextmanager
+def _upstream_pickle_modules():
+    """Upstream ``.pth`` files pickle ``config`` as ``utils.HParams`` (top-level module ``utils``); the reference
+    registers its own ``GPT_SoVITS/utils.py`` under that name before ``torch.load`` (Loader.py:13-14).  Do the same
+    with a minimal shim for the duration of the load and put ``sys.modules`` back afterwards."""
+    shim = types.ModuleType("utils")
+    shim.HParams = type("HParams", (_AttrBag,), {})
+    shim.DictToAttrRecursive = type("DictToAttrRecursive", (_AttrBag,), {})
+    prev = sys.modules.get("utils")
+    sys.modules["utils"] = shim
+    try:
+        yield
+    finally:
+        if prev is None:
+            sys.modules.pop("utils", None)
+        else:
+            sys.modules["utils"] = prev
 
 
 def _to_plain(obj):
@@ -110,7 +144,8 @@ def read_sovits_checkpoint(path: str) -> Tuple[dict, Dict[str, torch.Tensor], st
         version = hps.get("model", {}).get("version")
     else:
         version, data = sniff_sovits_version(path)
-        blob = torch.load(io.BytesIO(data), map_location="cpu", weights_only=False)
+        with _upstream_pickle_modules():
+            blob = torch.load(io.BytesIO(data), map_location="cpu", weights_only=False)
         hps = _to_plain(blob["config"])
         sd = blob["weight"]
         if version is None:

@@ -31,7 +31,7 @@ class GptSampling(C.Structure):
     _fields_ = [("top_k", C.c_int32), ("top_p", C.c_float), ("temperature", C.c_float),
                 ("repetition_penalty", C.c_float), ("suppress_steps", C.c_int32),
                 ("max_new_tokens", C.c_int32), ("mask_eos", C.c_int32), ("max_kv", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("suppress_first", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
 
 
 class VocDims(C.Structure):
@@ -61,6 +61,7 @@ SYMBOLS = [
     ("gsv_gpt_set_noise", C.c_int, [_P, _P, C.c_int]),
     ("gsv_gpt_set_forced", C.c_int, [_P, _P, C.c_int]),
     ("gsv_gpt_set_logits_trace", C.c_int, [_P, _P, C.c_int]),
+    ("gsv_gpt_set_slot_hooks", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     ("gsv_gpt_launch_count", C.c_int64, [_P]),
     ("gsv_gpt_set_decode_sms", C.c_int, [_P, C.c_int]),
     ("gsv_gpt_set_timeline", C.c_int, [_P, _P, C.c_int, C.c_int]),

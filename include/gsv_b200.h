@@ -86,11 +86,14 @@ typedef struct {
   float top_p;                /* >=1: disabled                                   */
   float temperature;
   float repetition_penalty;   /* 1.0: disabled (batched mode, t2s_model.py:651)  */
-  int32_t suppress_steps;     /* tokens {280,486,EOS} masked while idx < this (10 single, 0 batched) */
+  int32_t suppress_steps;     /* tokens {280,486,EOS} masked while idx < this (initial_suppression_steps; 0 batched) */
   int32_t max_new_tokens;     /* <=0: until the cache is full; else EOS is forced after this many   */
   int32_t mask_eos;           /* bench hook: never sample EOS              */
   int32_t max_kv;             /* <=0: dims.max_seq; else the slot stops when kv_len reaches this (the
                                  largest bucket length of its batch size, t2s_model.py:425, :656)     */
+  int32_t suppress_first;     /* 1: the FIRST sample masks {280,486,EOS} whatever suppress_steps is (infer and
+                                 infer_stream, t2s_model.py:415); 0: it does not (infer_batched, :613) */
+  int32_t reserved;
   uint64_t seed;              /* Philox key for the slot's Exp(1) noise          */
 } gsv_gpt_sampling;
 
@@ -148,6 +151,12 @@ int gsv_gpt_set_noise(gsv_gpt_ctx* ctx, const float* dev_noise, int n_rows);
 int gsv_gpt_set_forced(gsv_gpt_ctx* ctx, const int32_t* dev_forced, int n);
 /* Raw logits of slot 0 are appended as rows [vocab] fp32 (row 0 = prefill). */
 int gsv_gpt_set_logits_trace(gsv_gpt_ctx* ctx, float* dev_rows, int max_rows);
+/* The same three hooks for ANY slot, set together (NULL = off), for the request the slot is about to be given: the
+ * row / forcing cursors restart at the slot's next prefill.  The update is enqueued on `stream`; order it before the
+ * gsv_gpt_prefill / gsv_gpt_prefill_finish of that request (the three calls above are this one for slot 0 after a
+ * device synchronisation).  With these the multi-sequence kernels are held to the oracle slot by slot. */
+int gsv_gpt_set_slot_hooks(gsv_gpt_ctx* ctx, int slot, const float* dev_noise, int n_noise_rows, const int32_t* dev_forced,
+                           int n_forced, float* dev_trace_rows, int max_trace_rows, void* stream);
 /* Number of kernel launches issued by this context so far (bench "gpu_launches"). */
 int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx);
 

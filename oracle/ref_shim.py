@@ -13,7 +13,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("GSV_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """/root/reference in the build container; on the GPU box the unmodified copy of the hot-path files that
+    ``baseline/install_ref.py`` placed under the git-ignored ``baseline/_ref`` (same-box GPU baseline only)."""
+    cands = [os.environ.get("GSV_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "gsv_tts", "GPT_SoVITS")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -34,8 +34,8 @@ def test_library_exports_every_symbol():
 
 
 def test_struct_layouts():
-    # gsv_gpt_sampling: 8 x 4-byte fields then a uint64 seed at offset 32
-    assert C.sizeof(N.GptSampling) == 40 and N.GptSampling.seed.offset == 32
+    # gsv_gpt_sampling: 10 x 4-byte fields then a uint64 seed at offset 40
+    assert C.sizeof(N.GptSampling) == 48 and N.GptSampling.seed.offset == 40
     assert C.sizeof(N.GptDims) == 48
     assert C.sizeof(N.GptWeights) == 19 * 8
     assert C.sizeof(N.VocDims) == 4 * (8 + 8 + 8 + 1 + 4 + 12 + 1)

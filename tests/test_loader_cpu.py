@@ -86,3 +86,38 @@ def test_public_surface_imports_and_refuses_cpu():
     assert clip.audio_len_s == 1.0 and clip.audio_data.dtype.name == "float32"
     with pytest.raises(RuntimeError):
         TTS(device="cpu")
+
+
+def test_sovits_pth_with_config_pickled_from_module_utils(tmp_path):
+    """Real upstream .pth files pickle ``config`` as ``utils.HParams`` (a top-level module named ``utils``; the reference
+    registers its own under that name before torch.load, Loader.py:13-14).  Write such a file from a throw-away module
+    of that name, make sure the name is gone again, and load it."""
+    import subprocess
+    import sys
+    import textwrap
+    model = dict(syn.SOVITS_MODEL["tiny"], version="v2")
+    pth = tmp_path / "hp.pth"
+    writer = tmp_path / "write_it.py"
+    (tmp_path / "utils.py").write_text(textwrap.dedent("""
+        class HParams:
+            def __init__(self, **kwargs):
+                for k, v in kwargs.items():
+                    if type(v) == dict:
+                        v = HParams(**v)
+                    setattr(self, k, v)
+    """))
+    writer.write_text(textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, {str(tmp_path)!r})
+        import utils
+        hps = utils.HParams(data=dict(hop_length=640), train=dict(segment_size=20480), model={model!r})
+        torch.save({{"config": hps, "weight": {{"dec.conv_post.weight": torch.ones(1, 4, 7)}}}}, {str(pth)!r})
+    """))
+    subprocess.run([sys.executable, str(writer)], check=True)
+    assert "utils" not in sys.modules or not hasattr(sys.modules["utils"], "HParams")
+    before = sys.modules.get("utils")
+    hps, sd, version = Loader.read_sovits_checkpoint(str(pth))
+    assert sys.modules.get("utils") is before                 # the shim does not leak
+    assert version == "v2" and hps["model"]["upsample_rates"] == model["upsample_rates"]
+    assert hps["data"]["hop_length"] == 640 and isinstance(hps["model"], dict)
+    assert torch.equal(sd["dec.conv_post.weight"], torch.ones(1, 4, 7))

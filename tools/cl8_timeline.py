@@ -16,7 +16,7 @@ m = H.build_gpt(cfg, syn.gpt_state_dict(cfg, 0), torch.bfloat16, dev, [(B, 512)]
 g = torch.Generator().manual_seed(1)
 m._release_all()
 for s in range(B):
-    samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, suppress_steps=10, max_new_tokens=0, mask_eos=1, max_kv=512, seed=s + 1)
+    samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.35, suppress_steps=10, suppress_first=1, max_new_tokens=0, mask_eos=1, max_kv=512, seed=s + 1)
     m._prefill(s, torch.randint(0, 732, (64,), generator=g), torch.randint(0, 1024, (100,), generator=g), torch.zeros(64, 1024), samp)
 m._decode(25); torch.cuda.synchronize()
 G, MAXR = 148, 1024
