@@ -107,6 +107,7 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
     ctx->force_barrier_kernel = (e && strcmp(e, "barrier") == 0) ? 1 : 0;
     ctx->force_ll1 = (e && strcmp(e, "ll1") == 0) ? 1 : 0;
     ctx->force_ll2 = (e && strcmp(e, "ll2") == 0) ? 1 : 0;
+    ctx->force_hx = (e && strcmp(e, "hx") == 0) ? 1 : 0;
     ctx->force_gemm = (e && strcmp(e, "gemm") == 0) ? 1 : 0;
     ctx->use_cl = (e && strcmp(e, "cl") == 0) ? 1 : 0;
     ctx->use_cln = (e && strcmp(e, "cl2") == 0) ? 2 : ((e && strcmp(e, "cl4") == 0) ? 4 : ((e && strcmp(e, "cl8") == 0) ? 8 : 0));
@@ -124,6 +125,8 @@ extern "C" int gsv_gpt_destroy(gsv_gpt_ctx* ctx) {
   for (int i = 0; i < ctx->n_allocs; ++i) cudaFree(ctx->all_allocs[i]);
   if (ctx->step_graph_exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(ctx->step_graph_exec));
   gsv_umma_cache_destroy(ctx->umma);
+  if (ctx->hx_pack) cudaFree(ctx->hx_pack);
+  if (ctx->hx_head_pack) cudaFree(ctx->hx_head_pack);
   if (ctx->cl8_pack) cudaFree(ctx->cl8_pack);
   if (ctx->cl8_head_pack) cudaFree(ctx->cl8_head_pack);
   delete ctx;
@@ -197,6 +200,11 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   // -> 1: ll; 2..7: one cluster per sequence; 8 and more: eight per cluster on the tensor cores; the multi-kernel step
   //    where clusters of H CTAs cannot be launched (GSV_DECODE_IMPL overrides).
   const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_ll2 || ctx->force_gemm;
+  // one live sequence: head-cluster kernel (2 grid-wide exchanges per layer instead of 5)
+  if ((ctx->force_hx || (live == 1 && !explicit_impl && !ctx->use_cl && !ctx->use_cln)) && gsv_gpt_hx_supported(ctx, live, n_steps)) {
+    const int rc = gsv_gpt_decode_hx_launch(ctx, n_steps, (cudaStream_t)stream);
+    if (rc != GSV_ERR_STATE || ctx->force_hx) return rc;      // GSV_ERR_STATE: clusters not co-resident here -> grid-wide kernel below
+  }
   if (ctx->use_cln == 8 && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (ctx->use_cln && gsv_gpt_cl_supported(ctx, live)) return gsv_gpt_decode_cln_launch(ctx, live, ctx->use_cln, n_steps, (cudaStream_t)stream);
   if (!explicit_impl && !ctx->use_cl && gsv_gpt_cl_supported(ctx, live)) {

@@ -775,6 +775,8 @@ int launch_ll(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
 size_t gsv_gpt_ll_buffer_bytes(const gsv_gpt_ctx* ctx) {
   const GptParams& p = ctx->p;
   size_t words = (size_t)p.slots * (6 * (size_t)p.d + p.F + (size_t)p.H * NSMAX * GSV_PART_STRIDE + GSV_VOCAB_MAX + 1);
+  const size_t hx = gsv_gpt_hx_buffer_words(ctx);            // the head-cluster kernel lays its own areas over the same buffer
+  if (hx > words) words = hx;
   return words * sizeof(uint2) + 256;
 }
 

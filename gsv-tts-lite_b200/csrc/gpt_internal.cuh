@@ -86,6 +86,10 @@ struct gsv_gpt_ctx {
   void* cl8_pack;                 // gpt_decode_cl8.cu: block weights re-tiled into chunk / mma-fragment order (first launch)
   void* cl8_head_pack;            // ... and the head rows
   int use_cln;                    // GSV_DECODE_IMPL=cl2 / cl4: clusters serving 2 / 4 sequences each
+  void* hx_pack;                  // gpt_decode_hx.cu: per-(layer, CTA) weight blobs (first launch)
+  void* hx_head_pack;             // ... and the per-CTA head rows
+  int hx_clusters_ok;             // 0 not asked yet, 1 every cluster of the kernel is co-resident, -1 not
+  int force_hx;                   // GSV_DECODE_IMPL=hx
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
   int force_ll1;                  // GSV_DECODE_IMPL=ll1: first-generation small-batch kernel (A/B checks)
@@ -115,3 +119,6 @@ bool gsv_gpt_cl_supported(const gsv_gpt_ctx* ctx, int live_slots);
 int gsv_gpt_decode_cl_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
 int gsv_gpt_decode_cln_launch(gsv_gpt_ctx* ctx, int live_slots, int nb, int n_steps, cudaStream_t st);
 int gsv_gpt_decode_cl8_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
+size_t gsv_gpt_hx_buffer_words(const gsv_gpt_ctx* ctx);
+bool gsv_gpt_hx_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
+int gsv_gpt_decode_hx_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);

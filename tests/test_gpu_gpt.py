@@ -207,7 +207,7 @@ def test_infer_batched_contract_and_scheduling_independence(dev):
     assert 0 < np.mean([len(v) for v in outs[4].values()]) < int(g["max_seq"])
 
 
-@pytest.mark.parametrize("impl", ["ll1", "ll2", "cl", "cl2", "cl4", "cl8", "gemm", "barrier"])
+@pytest.mark.parametrize("impl", ["hx", "ll1", "ll2", "cl", "cl2", "cl4", "cl8", "gemm", "barrier"])
 @pytest.mark.parametrize("name,cfg", [("tiny", syn.GPT_CONFIG_TINY), ("full", syn.GPT_CONFIG)])
 def test_every_decode_kernel_teacher_forced_logits(dev, monkeypatch, impl, name, cfg):
     """Every decode implementation behind gsv_gpt_decode (flag-in-data ll / ll2, cluster-per-sequence,
@@ -376,3 +376,36 @@ def test_infer_batched_audited_full_size(dev):
     """The reference-size model (24 layers, d 512, 16 heads), 8 slots, 12 requests, overlapped refill."""
     byreq, audit, orc, _, worst = _audited_batched(dev, syn.GPT_CONFIG, 8, 12, 160, True, (4, 12), 91, nx=(20, 50), ny=(20, 60))
     print("full size worst logit error", worst)
+
+
+@pytest.mark.parametrize("nx,ny,max_seq", [(30, 35, 160), (100, 300, 512), (250, 351, 700), (500, 561, 1100)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_single_sequence_head_cluster_kernel_context_lengths(dev, nx, ny, max_seq, dtype):
+    """One live sequence (the head-cluster kernel): cached lengths that exercise one, two and three attention passes per
+    CTA (positions are dealt p mod 4 over the cluster's 4 CTAs, 128 per pass) and every owner rank of the newest position
+    (10 consecutive steps), logits against the oracle."""
+    from tests import gpu_harness as H
+    e = H.multi_sequence_teacher_forced_error(syn.GPT_CONFIG_TINY, dtype, dev, 1, 10, seed=nx, max_seq=max_seq,
+                                               nx=(nx, nx + 1), ny=(ny, ny + 1))
+    print("kv", nx + ny, dtype, "max", e["max"])
+    assert e["forced_ok"] and e["max"] < TOL[dtype]
+
+
+def test_single_sequence_decode_is_bit_deterministic_and_chunk_invariant(dev):
+    """The same 60 free-running tokens whether decoded in one launch, in chunks of 7 (launch boundaries: the input and
+    the K/V cache travel through global memory) or twice in a row."""
+    from tests import gpu_harness as H
+    cfg = syn.GPT_CONFIG
+    sd = syn.gpt_state_dict(cfg, 0, 0.0)
+    m = H.build_gpt(cfg, sd, torch.bfloat16, dev, [(1, 512)])
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 732, (1, 50), generator=g)
+    y = torch.randint(0, 1024, (1, 80), generator=g)
+    bert = torch.randn(1, 50, 1024, generator=g)
+    outs = []
+    for chunk in (32, 7, 32):
+        m.DECODE_CHUNK = chunk
+        m.debug_seed = 9
+        outs.append(m.infer(x, y, bert, force_steps=60)[0, 0].cpu().tolist())
+    assert len(outs[0]) == 60
+    assert outs[0] == outs[1] == outs[2]
