@@ -89,6 +89,7 @@ struct gsv_gpt_ctx {
   void* hx_pack;                  // gpt_decode_hx.cu: per-(layer, CTA) weight blobs (first launch)
   void* hx_head_pack;             // ... and the per-CTA head rows
   int hx_clusters_ok;             // 0 not asked yet, 1 every cluster of the kernel is co-resident, -1 not
+  int hx_cs;                      // CTAs per cluster of the head-cluster kernel (0: not chosen yet)
   int force_hx;                   // GSV_DECODE_IMPL=hx
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier

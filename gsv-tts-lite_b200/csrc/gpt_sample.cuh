@@ -71,6 +71,10 @@ __device__ __forceinline__ uint2 ll_peek(const uint2* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return make_uint2((unsigned)(w & 0xffffffffull), (unsigned)(w >> 32));
 }
+// Polls that need SEVERAL words per thread: issue every ll_peek first, then test every tag, and loop over the whole
+// group (see gpt_decode_hx.cu).  Testing a word right after its load makes ptxas wait for each L2 round trip in turn
+// (8 words = 8 x 0.24 us); and the loads must stay STRONG: with weak loads (ld.global.cg) ptxas may assume that a value
+// cannot change between two iterations, deletes the loop and the tag test, and the kernel sums whatever was there.
 __device__ __forceinline__ float ll_wait(const uint2* p, unsigned tag) {
   uint2 v;
   do { v = ll_peek(p); } while (v.y != tag);

@@ -23,7 +23,8 @@ rec = torch.zeros(G * 2 * MAXR, dtype=torch.int64, device=dev)
 N.check(N.lib().gsv_gpt_set_timeline(m._ctx, rec.data_ptr(), MAXR, 0))
 m._decode(3); torch.cuda.synchronize()
 r = rec.cpu().numpy().reshape(G, MAXR, 2)
-names = {30: " S0 landed", 31: " S2 landed", 1: "layer start", 2: " qkv rows done, pushed", 3: " q/k/v gathered", 4: " attention done, pushed", 5: " att merged",
+names = {40: "  (attn: warp partial in smem)", 41: "  (attn: barrier passed)", 42: "  (attn: CTA partial merged)", 43: "  (all-read: poll done)",
+         44: "  (all-read: barrier passed)", 45: "  (y1 inbox full)", 30: " S0 landed", 31: " S2 landed", 1: "layer start", 2: " qkv rows done, pushed", 3: " q/k/v gathered", 4: " attention done, pushed", 5: " att merged",
          6: " O partial published", 7: " all-read 1 done, pushed", 8: " y1 gathered, LN1 done", 9: " MLP-up done", 10: " MLP-down done, pushed",
          11: " reduce-scatter done, published", 12: " all-read 2 done, pushed", 13: "HEAD start (LN2 done)", 20: "head rows published", 21: "token done"}
 n = int(r[0, 0, 0])
