@@ -1,26 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the two hot paths (contract: see the task statement / DESIGN.md).
+"""bench.py -- headline benchmark of the two hot paths (contract: see the task statement / DESIGN.md section 6).
 
-Workload at every N (weak scaling, one process per GPU, independent utterances per rank):
+Headline workload at every N (weak scaling, one process per GPU, independent utterances per rank):
 BASELINE.json configs[1] -- V2Pro, batch=1 streaming, seq_len <= 512:
     prompt Nx=64 phonemes + Ny=100 prompt tokens -> prefill; 200 generated semantic tokens (EOS masked)
-    in 8 stream chunks of 25 (kv 164 -> 364, gpt_cache=[(1,512)]); after every chunk the SoVITS
+    in 8 stream chunks of 25 (kv 164 -> 364, gpt_cache (1,512)); after every chunk the SoVITS
     flow + HiFi-GAN vocoder turns 50 (first) / 55 (later) latent frames into 32 kHz audio.
-One "step" = one such utterance.  metric = generated AR tokens per second over the whole step
-(prefill + decode + vocoder), i.e. tokens / end-to-end time, with RTF = time / audio seconds.
+One "step" = one such utterance, driven through the PUBLIC entry ``gsv_tts.TTS.infer_features_stream`` (models loaded
+with ``TTS.load_gpt_model`` / ``load_sovits_model`` from checkpoint files in the reference's formats).
+    value  = generated AR tokens / device time of the step, inputs resident in HBM;
+    e2e    = the same call with HOST (pinned) inputs: host->device copies of the prompt, BERT features and latents and
+             the device->host read of tokens and audio are inside the timed region.
+The rest of BASELINE.json's metric rides in the same JSON line: ``batches`` (batch 1 / 8 / 32: decode-only roofline
+and GPT + vocoder end to end), ``config3`` (128 mixed requests through 32 slots), ``config4`` (32 utterances per GPU,
+dealt by length over the ranks, continuous batch + vocoder, audio-seconds per second of the whole job) and ``config5``
+(vocoder only, 10 s x batch 64, V2Pro and V2ProPlus, against the tensor peak).
 
 Arms:
     (default)          the CUDA path through libgsv_b200.so
     --impl reference   the reference algorithm's CPU path (oracle port; /root/reference cannot travel to
                        the GPU box and the reference forces fp32 on CPU, gsv_tts/TTS.py:74-76)
+The reference's own CUDA path (FlashAttention decoder, CUDA graphs) on the same B200 is timed by
+tools/ref_gpu_bench.py; its recorded numbers (profiles/r02_ref_gpu_baseline.json) are attached as ``ref_gpu``.
 """
 from __future__ import annotations
 
 import argparse
-import contextlib
 import json
 import os
 import sys
+import tempfile
 import threading
 import time
 
@@ -32,10 +41,13 @@ for p in (ROOT, os.path.join(ROOT, "gsv-tts-lite_b200")):
 import torch  # noqa: E402
 
 NX, NY, N_TOK, CHUNK = 64, 100, 200, 25
-DECODE_SMS = 128                           # SMs of the single-sequence decode kernel when the vocoder overlaps it
 FRAMES_FIRST, FRAMES_NEXT = 50, 55        # sovits_cache=[50,55] (reference README_EN.md:214)
 WORKLOAD = "V2Pro batch=1 streaming: prefill 64+100, 200 tokens in 8 chunks of 25, flow+HiFi-GAN 50/55 frames per chunk"
 METRIC = "AR tokens/sec (V2Pro, batch=1 streaming, end-to-end incl. prefill + vocoder)"
+REF_SAMPLE_TOKENS = 100                    # the CPU reference arm's bounded sample per step
+W_BYTES = (24 * (12 * 512 * 512 + 13 * 512) + 1025 * 512) * 2      # 152.4 MB of 16-bit weights per step
+KV_BYTES = 49152                                                   # per live position per sequence
+DEC_FLOP = {"v2Pro": 813.1e6 + 14.2e6, "v2ProPlus": 1828.4e6 + 14.2e6}   # flow + dec FLOPs per 50 Hz frame
 
 
 def synth_inputs(seed):
@@ -46,6 +58,20 @@ def synth_inputs(seed):
     zs = [torch.randn(1, 192, FRAMES_FIRST if i == 0 else FRAMES_NEXT, generator=g) for i in range(N_TOK // CHUNK)]
     ge = torch.randn(1, 1024, 1, generator=g)
     return x, y, bert, zs, ge
+
+
+def mixed_requests(n, seed, dev, dtype):
+    """SURVEY.md 8d config 3 / 4 generator: Nx ~ U{40..120}, Ny ~ U{75..250}, target length ~ U{50..250}."""
+    g = torch.Generator().manual_seed(seed)
+    xs, ys, bs, mx = [], [], [], []
+    for _ in range(n):
+        nx = int(torch.randint(40, 121, (1,), generator=g))
+        ny = int(torch.randint(75, 251, (1,), generator=g))
+        xs.append(torch.randint(0, 732, (nx,), generator=g).to(dev))
+        ys.append(torch.randint(0, 1024, (ny,), generator=g).to(dev))
+        bs.append(torch.zeros(nx, 1024, device=dev, dtype=dtype))
+        mx.append(int(torch.randint(50, 251, (1,), generator=g)))
+    return xs, ys, bs, mx
 
 
 def peaks():
@@ -93,6 +119,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port)
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step(n_tok=N_TOK, threads=None):
     """One bounded sample of the workload on the host cores with the oracle port of the reference
     algorithm (fp32, all cores).  Returns (seconds, tokens, description)."""
@@ -118,7 +147,7 @@ def cpu_reference_step(n_tok=N_TOK, threads=None):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n_tok = 100      # bounded sample: half an utterance per step keeps K steps within minutes
+    n_tok = REF_SAMPLE_TOKENS      # bounded sample: half an utterance per step keeps K steps within minutes
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(n_tok)
     times = []
@@ -131,12 +160,58 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": desc},
+        "config": {"workload": WORKLOAD, "sample": desc,
+                   "note": f"bounded sample of {n_tok} tokens / {n_tok // CHUNK} vocoder chunks per step (per-token rate; the shorter "
+                           "KV makes the CPU side if anything faster per token than the full 200-token step of the CUDA arm)"},
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------------------
+def write_checkpoints(tmp, sovits_keys=("v2Pro",)):
+    """Synthetic checkpoints in the reference's on-disk formats (GPT: {"config","weight"} .ckpt; SoVITS: {"config","weight"}
+    .pth), so that the bench loads its models the way a user does (TTS.load_gpt_model / load_sovits_model)."""
+    from gsv_tts import _synthetic as syn
+    gsd = syn.gpt_state_dict(syn.GPT_CONFIG, 0)
+    gsd["ar_predict_layer.weight"][syn.GPT_CONFIG["model"]["EOS"]] = 0.0      # EOS never in the top-k (config 3/4 stop by max_new)
+    gpath = os.path.join(tmp, "s1_synthetic.ckpt")
+    torch.save({"config": syn.GPT_CONFIG, "weight": gsd}, gpath)
+    spaths = {}
+    for key in sovits_keys:
+        model = dict(syn.SOVITS_MODEL[key])
+        hps = {"data": {"filter_length": 2048, "hop_length": 640, "n_speakers": 300}, "train": {"segment_size": 20480}, "model": model}
+        sp = os.path.join(tmp, f"s2_{key}_synthetic.pth")
+        torch.save({"config": hps, "weight": syn.sovits_flow_dec_state_dict(model, 0)}, sp)
+        spaths[key] = sp
+    return gpath, spaths
+
+
+class DecodeTimer:
+    """CUDA events around every decode launch of a Text2SemanticDecoder (on the launching stream)."""
+
+    def __init__(self, gpt):
+        self.gpt, self.orig, self.ev, self.on = gpt, gpt._decode, [], False
+        gpt._decode = self._decode
+
+    def _decode(self, n):
+        if not self.on:
+            return self.orig(n)
+        st = torch.cuda.current_stream(self.gpt._device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        self.orig(n)
+        e1.record(st)
+        self.ev.append((e0, e1, n))
+
+    def take(self):
+        out = [(a.elapsed_time(b), n) for a, b, n in self.ev]
+        self.ev = []
+        return out
 
 
 def main():
@@ -147,8 +222,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="vocoder chunks on the decode stream (reference order) instead of a second stream")
-    ap.add_argument("--no-extra", action="store_true", help="skip the batch 8/32 decode and vocoder-only extras")
+    ap.add_argument("--no-extra", action="store_true", help="headline only: skip batches / config3 / config4 / config5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -160,10 +234,9 @@ def main():
         return
 
     import torch.distributed as dist
+    from gsv_tts import TTS
     from gsv_tts import _native as N
-    from gsv_tts import _synthetic as syn
-    from gsv_tts.GPT_SoVITS.GPT.t2s_model_b200 import Text2SemanticDecoder
-    from gsv_tts.GPT_SoVITS.SoVITS.models_b200 import FlowDecoder
+    from gsv_tts import _shard
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
     torch.cuda.set_device(local)
@@ -171,97 +244,51 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-
-    # ---- weights: rank 0 materialises the synthetic checkpoint, NCCL broadcasts it ----
-    gsd = syn.gpt_state_dict(syn.GPT_CONFIG, 0)
-    model = syn.SOVITS_MODEL["v2Pro"]
-    vsd = syn.sovits_flow_dec_state_dict(model, 0)
-    if world > 1:
-        from gsv_tts import _shard
-        if rank != 0:       # only rank 0's copy counts: the others start from garbage and receive the broadcast
-            gsd = {k: torch.empty_like(v) for k, v in gsd.items()}
-            vsd = {k: torch.empty_like(v) for k, v in vsd.items()}
-        gsd = _shard.broadcast_state_dict(gsd, 0, dev)
-        vsd = _shard.broadcast_state_dict(vsd, 0, dev)
-    gpt = Text2SemanticDecoder(syn.GPT_CONFIG)
-    gpt.load_state_dict(gsd)
-    gpt.initialize_runtime(dtype, dev, [(1, 512)])
-    voc = FlowDecoder(**model)
-    voc.load_state_dict(vsd)
-    voc.initialize_runtime(dtype, dev, [FRAMES_FIRST, FRAMES_NEXT])
     lib = N.lib()
 
-    x, y, bert, zs, ge = synth_inputs(1234 + rank)
-    xd, yd, bertd = x.to(dev), y.to(dev), bert.to(dev, dtype)
-    zsd = [z.to(dev, dtype) for z in zs]
-    masks = [torch.ones(1, 1, z.shape[-1], device=dev, dtype=dtype) for z in zs]
-    ged = ge.to(dev, dtype)
-    # pinned host copies for the end-to-end arm
-    xh, yh, berth = x.pin_memory(), y.pin_memory(), bert.to(dtype).pin_memory()
-    zsh = [z.to(dtype).pin_memory() for z in zs]
-    geh = ge.to(dtype).pin_memory()
-    audio_host = torch.empty(N_TOK // CHUNK, FRAMES_NEXT * 640, dtype=dtype).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # ---- models through the public loaders; under torch.distributed only rank 0 reads the files and NCCL broadcasts the
+    #      tensors GPU to GPU (Loader.get_*_weights)
+    tmp = tempfile.mkdtemp(prefix="gsv_bench_")
+    if rank == 0:
+        gpath, spaths = write_checkpoints(tmp, ("v2Pro", "v2ProPlus") if not args.no_extra else ("v2Pro",))
+    else:
+        gpath, spaths = "s1_synthetic.ckpt", {"v2Pro": "s2_v2Pro_synthetic.pth", "v2ProPlus": "s2_v2ProPlus_synthetic.pth"}
+    tts = TTS(gpt_cache=[(1, 512), (8, 512), (32, 512), (32, 1024)], sovits_cache=[FRAMES_FIRST, FRAMES_NEXT], device=dev, dtype=dtype)
+    tts.load_gpt_model(gpath)
+    tts.load_sovits_model(spaths["v2Pro"])
+    gpt = tts.gpt_models[gpath].t2s_model
+    voc = tts.sovits_models[spaths["v2Pro"]].vq_model
+    timer = DecodeTimer(gpt)
 
+    x, y, bert, zs, ge = synth_inputs(1234 + rank)
+    dev_in = dict(x=x.to(dev), y=y.to(dev), bert=bert.to(dev, dtype), zs=[z.to(dev, dtype) for z in zs], ge=ge.to(dev, dtype))
+    host_in = dict(x=x.pin_memory(), y=y.pin_memory(), bert=bert.to(dtype).pin_memory(), zs=[z.to(dtype).pin_memory() for z in zs],
+                   ge=ge.to(dtype).pin_memory())
+    mask_first = torch.ones(1, 1, FRAMES_FIRST, device=dev, dtype=dtype)
+    mask_next = torch.ones(1, 1, FRAMES_NEXT, device=dev, dtype=dtype)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
     gpt.debug_seed = 99
     stream = torch.cuda.current_stream(dev)
-    overlap = not args.no_overlap
-    side = torch.cuda.Stream(dev)
-    if overlap:
-        gpt.set_decode_sms(DECODE_SMS)
-    dec_ms = []         # per decode launch (25 tokens), CUDA events on the launching stream
 
-    ttft_marks = None
+    def utterance(inp, first_clip_time=None):
+        """One streaming utterance through the public API: 8 chunks of 25 tokens, one AudioClip each."""
+        state = {"c": 0}
 
-    def utterance(device_resident: bool, time_decode: bool):
-        """prefill + 8 x (25-token persistent decode launch + vocoder chunk)."""
-        nonlocal ttft_marks
-        if device_resident:
-            gx, gy, gb, gz, gg = xd, yd, bertd, zsd, ged
-        else:
-            gx, gy, gb = xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True), berth.to(dev, non_blocking=True)
-            gz = [z.to(dev, non_blocking=True) for z in zsh]
-            gg = geh.to(dev, non_blocking=True)
-        gpt._single_setup(gx, gy, gb, 15, 1.0, 1.0, 1.35, 10, N_TOK)
-        n_chunks = N_TOK // CHUNK
+        def features_of_chunk(tokens, final):      # stands for enc_p (SURVEY.md 8 f-1): the chunk's latents
+            c = state["c"]
+            state["c"] += 1
+            z = inp["zs"][min(c, len(inp["zs"]) - 1)]
+            return z.to(dev, non_blocking=True), (mask_first if z.shape[-1] == FRAMES_FIRST else mask_next), inp["ge"].to(dev, non_blocking=True)
 
-        def decode_chunk():
-            if time_decode:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            gpt._decode(CHUNK)
-            if time_decode:
-                e1.record(stream)
-                dec_ms.append((e0, e1))
-
-        if overlap:
-            side.wait_stream(stream)                       # the host->device copies above
-        decode_chunk()
-        for c in range(n_chunks):
-            gpt._read(1)                                   # tokens of chunk c on the host (stream sync)
-            if overlap:
-                # gsv_tts.TTS.infer_features_stream: chunk c+1 decodes (on 128 SMs) while the vocoder of chunk c runs
-                # on a second stream; the first chunk's vocoder is enqueued BEFORE the next decode
-                if c + 1 < n_chunks and c > 0:
-                    decode_chunk()
-                ctx_mgr = torch.cuda.stream(side)
-            else:
-                ctx_mgr = contextlib.nullcontext()
-            with ctx_mgr:
-                audio = voc.flow_dec(gz[c], masks[c], gg)
-                if not device_resident:
-                    audio_host[c, : audio.shape[-1]].copy_(audio[0, 0], non_blocking=True)
-                    if c == 0 and ttft_marks is not None:
-                        # time to first audio: host call -> first 1.6 s chunk of samples in host memory
-                        torch.cuda.current_stream(dev).synchronize()
-                        ttft_marks.append(time.perf_counter())
-            if (not overlap or c == 0) and c + 1 < n_chunks:
-                decode_chunk()                             # behind the first chunk's vocoder: it gets the whole GPU (time to first audio)
-        if overlap:
-            stream.wait_stream(side)                       # the step ends when the last chunk of audio exists
-        if not device_resident:
-            stream.synchronize()
-        return int(gpt._h_ngen[0]) - 1
+        n_clips = 0
+        samples = 0
+        for clip in tts.infer_features_stream(inp["x"], inp["bert"], inp["y"], features_of_chunk, stream_chunk=CHUNK, force_steps=N_TOK):
+            if n_clips == 0 and first_clip_time is not None:
+                first_clip_time.append(time.perf_counter())
+            n_clips += 1
+            samples += clip.audio_data.shape[0]
+        assert n_clips == N_TOK // CHUNK, n_clips
+        return N_TOK, samples
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -269,21 +296,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(device_resident, steps, collect):
+    def timed(inp, steps, collect):
         evs = []
         l0 = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count()
+        timer.on = collect
         barrier()
         wall0 = time.perf_counter()
         for _ in range(steps):
             flush.zero_()                                    # evict L2 between timed steps (outside the events)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            n = utterance(device_resident, collect)
+            utterance(inp)
             b.record(stream)
             evs.append((a, b))
-            assert n == N_TOK, n
         barrier()
         wall = time.perf_counter() - wall0
+        timer.on = False
         ms = sum(a.elapsed_time(b) for a, b in evs)
         launches = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -292,24 +320,23 @@ def main():
         return float(t.item()), wall, launches
 
     for _ in range(args.warmup):
-        utterance(True, False)
+        utterance(dev_in)
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total, wall, launches = timed(True, args.steps, True)
-    decode_launch_ms = [a.elapsed_time(b) for a, b in dec_ms]
-    ms_e2e, wall_e2e, _ = timed(False, args.steps, False)
+    ms_total, wall, launches = timed(dev_in, args.steps, True)
+    decode_launches = timer.take()
+    ms_e2e, wall_e2e, _ = timed(host_in, args.steps, False)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # TTFT (BASELINE config 2): separate, untimed-region measurement so the extra sync does not perturb `e2e`
+    # TTFT (BASELINE config 2): host call -> first AudioClip in host memory, median of 5
     ttfts = []
     for _ in range(5):
         flush.zero_()
         torch.cuda.synchronize(dev)
-        ttft_marks = []
+        marks = []
         t_call = time.perf_counter()
-        utterance(False, False)
-        ttfts.append((ttft_marks[0] - t_call) * 1e3)
-    ttft_marks = None
+        utterance(host_in, marks)
+        ttfts.append((marks[0] - t_call) * 1e3)
     ttfts.sort()
     ttft_ms = ttfts[len(ttfts) // 2]
 
@@ -317,28 +344,32 @@ def main():
     value = tokens / (ms_total / 1e3)
     e2e_value = tokens / (ms_e2e / 1e3)
     audio_s = N_TOK * 0.04
-    # ---- roofline of the dominant kernel: the small-batch persistent decode kernel (HBM bound) ----
+    # ---- roofline of the dominant kernel: the single-sequence persistent decode kernel (HBM bound) ----
     pk, pk_kind = peaks()
-    w_bytes = (24 * (12 * 512 * 512 + 13 * 512) + 1025 * 512) * 2
     kv_mean = NX + NY + (N_TOK + 1) / 2.0
-    bytes_per_token = w_bytes + 49152 * kv_mean                 # weights once + 49 152 B per live position
-    mean_launch_ms = sum(decode_launch_ms) / len(decode_launch_ms)
+    bytes_per_token = W_BYTES + KV_BYTES * kv_mean              # weights once + 49 152 B per live position
+    mean_launch_ms = sum(ms for ms, _ in decode_launches) / len(decode_launches)
     achieved = bytes_per_token * CHUNK / (mean_launch_ms / 1e3) / 1e9
     traffic = None      # dram bytes per launch of the same kernel from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_decode_traffic.json")) as f:
-            tj = json.load(f)
-        traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * CHUNK / tj["tokens_per_launch"]
-    except Exception:
-        pass
-    roofline = {"kernel": "gpt_decode_ll_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+    for name in ("r02_decode_traffic.json", "r01_decode_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            traffic = (tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]) * CHUNK / tj["tokens_per_launch"]
+            break
+        except Exception:
+            pass
+    roofline = {"kernel": "gpt_decode_hx_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind,
                 "bytes_per_launch": bytes_per_token * CHUNK, "launch_ms": mean_launch_ms,
-                "decode_only_tok_s": CHUNK / (mean_launch_ms / 1e3)}
+                "decode_only_tok_s": CHUNK / (mean_launch_ms / 1e3), "us_per_token": mean_launch_ms * 1e3 / CHUNK}
 
-    extra = {}
-    if rank == 0 and not args.no_extra:
-        extra = extras(gpt, voc, dev, dtype, lib, N, syn)
+    blocks = {}
+    if not args.no_extra:
+        try:
+            blocks = metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dist, _shard, barrier)
+        except Exception as e:      # the extra blocks must never break the headline line
+            blocks = {"error": f"{type(e).__name__}: {e}"}
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -346,115 +377,162 @@ def main():
         cpu_base = {"value": ntok / dt, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
 
     if rank == 0:
-        h2d = sum(t.numel() * t.element_size() for t in [xh, yh, berth, geh] + zsh)
-        d2h = sum(z.shape[-1] * 640 * 2 for z in zs) + (N_TOK // CHUNK) * (512 * 4 + 8)
+        h2d = sum(t.numel() * t.element_size() for t in [host_in["x"], host_in["y"], host_in["bert"]]) + \
+            sum((z.numel() + host_in["ge"].numel()) * 2 for z in host_in["zs"])
+        d2h = sum(z.shape[-1] * 640 * 4 for z in zs) + (N_TOK // CHUNK) * (512 * 4 + 8)
+        ref_gpu = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_ref_gpu_baseline.json")) as f:
+                rg = json.load(f)
+            ref_gpu = {"source": "profiles/r02_ref_gpu_baseline.json (tools/ref_gpu_bench.py on this pool's B200, recorded, not re-run here)",
+                       "flash_b1_tok_s": rg["flash_b1_infer"]["tok_s"], "flash_b8_tok_s": rg["flash_b8_infer_batched"]["tok_s"],
+                       "flash_b32_tok_s": rg["flash_b32_infer_batched"]["tok_s"], "flash_first_chunk_ms": rg["flash_b1_stream"]["first_chunk_ms"],
+                       "voc_v2Pro_B1_T50_graph_ms": rg["voc_v2Pro_B1_T50"]["graph_ms"], "voc_v2Pro_B64_T500_ms": rg["voc_v2Pro_B64_T500"]["eager_ms"]}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "256 MB flush between timed steps; 152 MB of weights (> L2) streamed per token",
-                       "parallelism": f"{world} independent utterance streams, NCCL weight broadcast at load only",
-                       "overlap": (f"vocoder of chunk c on a second stream while chunk c+1 decodes on {DECODE_SMS} SMs" if overlap
-                                   else "none: decode and vocoder chunks back to back on one stream")},
+                       "api": "gsv_tts.TTS.infer_features_stream (models from TTS.load_gpt_model / load_sovits_model)",
+                       "parallelism": f"{world} independent utterance streams, rank 0 reads the checkpoints, NCCL broadcast GPU to GPU at load only",
+                       "overlap": "vocoder of chunk c on a second stream while chunk c+1 decodes on 64 SMs",
+                       "reference_arm_sample": f"{REF_SAMPLE_TOKENS} tokens / {REF_SAMPLE_TOKENS // CHUNK} vocoder chunks per step (per-token rate)"},
             "rtf": (ms_total / 1e3 / args.steps) / audio_s, "ttft_ms": ttft_ms,
             "roofline": roofline, "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "rtf": (ms_e2e / 1e3 / args.steps) / audio_s},
-            "gpu_launches": launches, "clocks": sampler.summary(), "wall_s": wall + wall_e2e, "extra": extra,
+            "gpu_launches": launches, "clocks": sampler.summary(), "wall_s": wall + wall_e2e, "ref_gpu": ref_gpu,
         }
+        line.update(blocks)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def extras(gpt, voc, dev, dtype, lib, N, syn):
-    """Secondary numbers (not the headline): decode tok/s at batch 8 / 32 and vocoder-only throughput."""
-    import ctypes as C
-    from gsv_tts.GPT_SoVITS.GPT.t2s_model_b200 import Text2SemanticDecoder
+def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dist, _shard, barrier):
+    """The rest of BASELINE.json's metric.  Every block times device work with CUDA events (GPT decode launches) or the
+    wall clock around a public call bracketed by synchronisations, after one warm-up call."""
     out = {}
-    try:
-        m = Text2SemanticDecoder(syn.GPT_CONFIG)
-        m.load_state_dict(syn.gpt_state_dict(syn.GPT_CONFIG, 0))
-        m.initialize_runtime(dtype, dev, [(32, 512)])
-        g = torch.Generator().manual_seed(7)
-        for B in (4, 8, 16, 32):
-            m._release_all()
-            for s in range(B):
-                samp = N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0, suppress_first=0,
-                                     max_new_tokens=0, mask_eos=1, max_kv=512, seed=s + 1)
-                m._prefill(s, torch.randint(0, 732, (NX,), generator=g), torch.randint(0, 1024, (NY + 100,), generator=g),
-                           torch.zeros(NX, 1024), samp)
-            m._decode(8)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            m._decode(64)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            out[f"decode_batch{B}_tok_s"] = B * 64 / (ms / 1e3)
-            out[f"decode_batch{B}_us_per_step"] = ms * 1e3 / 64
-        del m
-        # vocoder only: 2 s of audio (100 frames) x batch 8
-        z = torch.randn(8, 192, 100, device=dev, dtype=dtype)
-        mk = torch.ones(8, 1, 100, device=dev, dtype=dtype)
-        ge = torch.randn(8, 1024, 1, device=dev, dtype=dtype)
-        voc.flow_dec(z, mk, ge)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        voc.flow_dec(z, mk, ge)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        out["vocoder_b8_100f_ms"] = ms
-        out["vocoder_audio_s_per_s"] = 8 * 2.0 / (ms / 1e3)
-        out["vocoder_tflops"] = 8 * 100 * (813.1e6 + 14.2e6) / (ms / 1e3) / 1e12
-        # a quarter of BASELINE config 5 (10 s of tokens, batch 64): batch 16 x 500 frames
-        z = torch.randn(16, 192, 500, device=dev, dtype=dtype)
-        mk = torch.ones(16, 1, 500, device=dev, dtype=dtype)
-        ge = torch.randn(16, 1024, 1, device=dev, dtype=dtype)
-        voc.flow_dec(z, mk, ge)
-        torch.cuda.synchronize()
-        e0.record()
-        voc.flow_dec(z, mk, ge)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        out["vocoder_b16_500f_ms"] = ms
-        out["vocoder_b16_500f_tflops"] = 16 * 500 * (813.1e6 + 14.2e6) / (ms / 1e3) / 1e12
-        out["vocoder_b16_500f_audio_s_per_s"] = 16 * 10.0 / (ms / 1e3)
-    except Exception as e:      # extras must never break the headline line
-        out["error"] = f"{type(e).__name__}: {e}"
-    try:
-        # SURVEY.md 8d config 3 (GPT stage): 128 mixed requests through 32 slots of infer_batched (continuous batching;
-        # Nx ~ U{40..120}, Ny ~ U{75..250}, length ~ U{50..250} via max_new), wall clock, both refill modes
-        import time as _t
-        m = Text2SemanticDecoder(syn.GPT_CONFIG)
-        m.load_state_dict(syn.gpt_state_dict(syn.GPT_CONFIG, 0))
-        m.initialize_runtime(dtype, dev, [(32, 1024)])
-        g = torch.Generator().manual_seed(1234)
-        xs, ys, bs, mx = [], [], [], []
-        for _ in range(128):
-            nx = int(torch.randint(40, 121, (1,), generator=g))
-            ny = int(torch.randint(75, 251, (1,), generator=g))
-            xs.append(torch.randint(0, 732, (nx,), generator=g).to(dev))
-            ys.append(torch.randint(0, 1024, (ny,), generator=g).to(dev))
-            bs.append(torch.zeros(nx, 1024, device=dev, dtype=dtype))
-            mx.append(int(torch.randint(50, 251, (1,), generator=g)))
-        m.debug_seed = 5
-        m.infer_batched(xs[:40], ys[:40], bs[:40], max_new=[20] * 40)        # warm-up (weight re-tiling, kernel attributes)
-        for overlap, tag in ((True, "batched128_tok_s"), (False, "batched128_serial_refill_tok_s")):
-            m.overlap_refill = overlap
-            m.debug_seed = 5
-            torch.cuda.synchronize()
-            t0 = _t.perf_counter()
-            outs, _ = m.infer_batched(xs, ys, bs, max_new=mx)
-            torch.cuda.synchronize()
-            out[tag] = sum(int(o.numel()) for o in outs) / (_t.perf_counter() - t0)
-        del m
-    except Exception as e:
-        out["error_batched"] = f"{type(e).__name__}: {e}"
+    g = torch.Generator().manual_seed(7)
+
+    def sync_time(fn):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, r
+
+    # ---- batches 1 / 8 / 32: B identical-length requests through B slots, 200 tokens each (EOS never sampled), then the
+    #      vocoder over the B utterances (400 frames each); decode launches timed for the roofline of the batch kernel
+    batches = {}
+    for B in (1, 8, 32):
+        xs = [torch.randint(0, 732, (NX,), generator=g).to(dev) for _ in range(B)]
+        ys = [torch.randint(0, 1024, (NY,), generator=g).to(dev) for _ in range(B)]
+        bs = [torch.zeros(NX, 1024, device=dev, dtype=dtype) for _ in range(B)]
+        zs = [torch.randn(192, 2 * N_TOK, generator=g).to(dev, dtype) for _ in range(B)]
+        ges = [torch.randn(1024, 1, generator=g).to(dev, dtype) for _ in range(B)]
+        gpt.debug_seed = 11
+        tts.infer_features_batched(xs, bs, ys, max_new=[16] * B)             # warm-up (kernel choice, weight re-tiling)
+        tts.vocode_features_batched(zs, ges)                                  # same shapes as the timed call (tensor maps, scratch)
+        timer.on = True
+        gpt.debug_seed = 11
+        t_gpt, toks = sync_time(lambda: tts.infer_features_batched(xs, bs, ys, max_new=[N_TOK] * B))
+        launches = timer.take()
+        timer.on = False
+        t_voc, clips = sync_time(lambda: tts.vocode_features_batched(zs, ges))
+        n_tok = sum(int(t.numel()) for t in toks)
+        steps = min(sum(n for _, n in launches), N_TOK + 1)      # the last launch stops early once every sequence is done
+        ms_dec = sum(ms for ms, _ in launches)
+        us_step = ms_dec * 1e3 / max(steps, 1)
+        kv_mean = NX + NY + (N_TOK + 1) / 2.0
+        bytes_step = W_BYTES + B * KV_BYTES * kv_mean
+        ach = bytes_step / (us_step * 1e-6) / 1e9
+        audio_s = n_tok * 0.04
+        batches[str(B)] = {
+            "decode_us_per_step": us_step, "decode_tok_s": B * 1e6 / us_step,
+            "roofline": {"kernel": "gpt_decode_hx_kernel" if B == 1 else "gpt_decode_cl8_kernel", "bound": "hbm", "achieved": ach,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "bytes_per_step": bytes_step},
+            "gpt_stage_tok_s": n_tok / t_gpt, "gpt_stage_ms": t_gpt * 1e3, "vocoder_ms": t_voc * 1e3,
+            "e2e_tok_s": n_tok / (t_gpt + t_voc), "e2e_rtf": (t_gpt + t_voc) / audio_s, "audio_s_per_s": audio_s / (t_gpt + t_voc),
+            "tokens": n_tok,
+        }
+    out["batches"] = batches
+
+    # ---- config 3 (GPT stage): 128 mixed requests through 32 slots of infer_batched, refill prompts on a second stream
+    xs, ys, bs, mx = mixed_requests(128, 1234, dev, dtype)
+    gpt.debug_seed = 5
+    tts.infer_features_batched(xs[:40], bs[:40], ys[:40], max_new=[20] * 40)
+    gpt.debug_seed = 5
+    t3, toks = sync_time(lambda: tts.infer_features_batched(xs, bs, ys, max_new=mx))
+    n3 = sum(int(t.numel()) for t in toks)
+    out["config3"] = {"workload": "128 mixed requests (Nx U{40..120}, Ny U{75..250}, length U{50..250}) through 32 slots, V2Pro-size GPT",
+                      "tokens": n3, "ms": t3 * 1e3, "tok_s": n3 / t3, "audio_s_per_s": n3 * 0.04 / t3}
+
+    # ---- config 4: 32 utterances per GPU, dealt over the ranks by predicted length, continuous batch + vocoder per rank
+    n4 = 32 * world
+    xs, ys, bs, mx = mixed_requests(n4, 4321, dev, dtype)
+    mine = _shard.shard_by_length([len(a) + m for a, m in zip(xs, mx)], world)[rank]
+    gz = torch.Generator().manual_seed(99 + rank)
+    lx, ly, lb, lm = [xs[i] for i in mine], [ys[i] for i in mine], [bs[i] for i in mine], [mx[i] for i in mine]
+    ges = [torch.randn(1024, 1, generator=gz).to(dev, dtype) for _ in mine]
+
+    def run4():
+        toks = tts.infer_features_batched(lx, lb, ly, max_new=lm)
+        zs = [torch.randn(192, 2 * int(t.numel()), device=dev, dtype=dtype) for t in toks]   # stands for enc_p (row f-1)
+        clips = tts.vocode_features_batched(zs, ges)
+        return sum(c.audio_data.shape[0] for c in clips) / 32000.0
+
+    gpt.debug_seed = 6
+    run4()
+    barrier()
+    gpt.debug_seed = 6
+    t4, audio4 = sync_time(run4)
+    stat = torch.tensor([t4, audio4], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = stat[:1].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        asum = stat[1:].clone()
+        dist.all_reduce(asum, op=dist.ReduceOp.SUM)
+        t4, audio4 = float(tmax.item()), float(asum.item())
+        got = _shard.gather_in_order({i: 1 for i in mine}, n4)                   # every request answered exactly once
+        assert len(got) == n4
+    out["config4"] = {"workload": f"{n4} utterances (32 per GPU) sharded by length over {world} rank(s); continuous batch + flow/HiFi-GAN per rank",
+                      "audio_s": audio4, "ms": t4 * 1e3, "audio_s_per_s": audio4 / t4, "rtf": t4 / audio4}
+
+    # ---- config 5: vocoder only, 10 s of latents x batch 64 (rank 0)
+    if rank == 0:
+        c5 = {}
+        for key in ("v2Pro", "v2ProPlus"):
+            try:
+                if key == "v2Pro":
+                    v = voc
+                else:
+                    tts.load_sovits_model(spaths[key]) if world == 1 else None
+                    v = tts.sovits_models[spaths[key]].vq_model if spaths[key] in tts.sovits_models else None
+                if v is None:
+                    continue
+                gin = v.gin_channels
+                z = torch.randn(64, 192, 500, device=dev, dtype=dtype)
+                mk = torch.ones(64, 1, 500, device=dev, dtype=dtype)
+                gg = torch.randn(64, gin, 1, device=dev, dtype=dtype)
+                v.flow_dec(z, mk, gg)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                v.flow_dec(z, mk, gg)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1)
+                tf = 64 * 500 * DEC_FLOP[key] / (ms / 1e3) / 1e12
+                c5[key] = {"ms": ms, "tflops": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops"], "audio_s_per_s": 64 * 10.0 / (ms / 1e3),
+                           "roofline": {"kernel": "conv_umma_kernel (flow + HiFi-GAN call)", "bound": "tensor", "achieved": tf,
+                                        "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"]}}
+                del z, mk, gg
+            except Exception as e:
+                c5[key] = {"error": f"{type(e).__name__}: {e}"}
+        out["config5"] = c5
     return out
 
 

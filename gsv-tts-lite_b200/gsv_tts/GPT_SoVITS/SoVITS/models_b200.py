@@ -57,7 +57,7 @@ class FlowDecoder(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = False):
         """Keeps every ``flow.*`` / ``dec.*`` tensor; other keys (enc_p, quantizer, training-only
         modules) are ignored like ``strict=False`` does in the reference (Loader.py:94)."""
-        self._raw = {k: v.detach().float().cpu() for k, v in state_dict.items()
+        self._raw = {k: v.detach().float() for k, v in state_dict.items()        # stay where they are (CPU file / GPU broadcast)
                      if k.startswith("flow.") or k.startswith("dec.")}
         return self
 

@@ -170,20 +170,30 @@ class Sovits:
 
 
 def get_gpt_weights(gpt_path: str, tts_config: Config) -> Gpt:
+    """Reference Loader.py:124-167.  Under ``torch.distributed`` only rank 0 reads the file; the tensors reach the other
+    ranks by NCCL broadcast, GPU to GPU (the one collective of the path)."""
+    from . import _shard
     from .GPT_SoVITS.GPT.t2s_model_b200 import Text2SemanticDecoder
-    config, sd = read_gpt_checkpoint(gpt_path)
-    model = Text2SemanticDecoder(config)
-    model.load_state_dict(sd)
+    config, sd = _shard.broadcast_checkpoint(lambda: read_gpt_checkpoint(gpt_path), 0, tts_config.device)
+    with torch.device("meta"):                 # parameter holders only: the tensors read / received above are assigned, not copied
+        model = Text2SemanticDecoder(config)
+    model.load_state_dict(sd, assign=True)
     model.eval()
     model.initialize_runtime(tts_config.dtype, tts_config.device, tts_config.gpt_cache)
     return Gpt(model, config)
 
 
 def get_sovits_weights(sovits_path: str, tts_config: Config) -> Sovits:
-    """Builds the native flow + HiFi-GAN context.  ``vq_model`` here is the ``FlowDecoder``; the reference's
-    ``enc_p`` / quantizer / ``get_ge`` are not part of this package."""
+    """Builds the native SoVITS half (flow + HiFi-GAN, and the prior encoder where the checkpoint carries it); same
+    rank-0-reads / NCCL-broadcast rule as ``get_gpt_weights``."""
+    from . import _shard
     from .GPT_SoVITS.SoVITS.models_b200 import FlowDecoder
-    hps, sd, _ = read_sovits_checkpoint(sovits_path)
+
+    def read():
+        hps, sd, _ = read_sovits_checkpoint(sovits_path)
+        return hps, sd
+
+    hps, sd = _shard.broadcast_checkpoint(read, 0, tts_config.device)
     model = FlowDecoder(**hps["model"])
     model.load_state_dict(sd)
     model.initialize_runtime(tts_config.dtype, tts_config.device, tts_config.sovits_cache)

@@ -122,7 +122,8 @@ class TTS:
 
     def infer_features_stream(self, phoneme_ids, bert, prompt_tokens, features_of_chunk, gpt_model: Optional[str] = None,
                               sovits_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0,
-                              repetition_penalty=1.35, stream_chunk: int = 25, decode_sms: int = 128):
+                              repetition_penalty=1.35, stream_chunk: int = 25, decode_sms: int = 128,
+                              force_steps: Optional[int] = None):
         """Streaming counterpart of ``infer_features`` (the GPT / vocoder part of ``infer_stream``, TTS.py:402-470):
         yields one ``AudioClip`` per chunk of ``stream_chunk`` semantic tokens.  ``features_of_chunk(tokens, final)``
         stands for ``enc_p`` (out of scope): it returns ``(z_p, y_mask, ge)`` for the frames of that chunk.
@@ -136,7 +137,7 @@ class TTS:
         gpt.set_decode_sms(decode_sms)
         try:
             it = gpt.infer_stream(phoneme_ids, prompt_tokens, bert, top_k=top_k, top_p=top_p, temperature=temperature,
-                                  repetition_penalty=repetition_penalty, stream_chunk=stream_chunk)
+                                  repetition_penalty=repetition_penalty, stream_chunk=stream_chunk, force_steps=force_steps)
             while True:
                 with torch.inference_mode():
                     try:
@@ -154,15 +155,45 @@ class TTS:
 
     @torch.inference_mode()
     def infer_features_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence,
-                               gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0):
+                               gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0, max_new=None):
         """Continuous-batched GPT stage of ``infer_batched`` (TTS.py:695-703): token lists in request order."""
         gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
         outs, order = gpt.infer_batched(list(phoneme_ids), list(prompt_tokens), list(bert), top_k=top_k, top_p=top_p,
-                                        temperature=temperature)
+                                        temperature=temperature, max_new=max_new)
         res = [None] * len(outs)
         for o, i in zip(outs, order.tolist()):
             res[i] = o
         return res
+
+    @torch.inference_mode()
+    def vocode_features_batched(self, z_p: Sequence[torch.Tensor], ge: Sequence[torch.Tensor], sovits_model: Optional[str] = None,
+                                max_frames: int = 8192) -> List[AudioClip]:
+        """Vocoder stage of ``infer_batched`` (TTS.py:705-764): utterances of different lengths ``z_p[i]`` [192, T_i] are
+        sorted by length and run through flow + HiFi-GAN in padded groups of at most ``max_frames`` frames (padded frames
+        are masked), so that a group is one native call; clips come back in request order."""
+        voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev, dt = voc._device, voc._dtype
+        order = sorted(range(len(z_p)), key=lambda i: -int(z_p[i].shape[-1]))
+        clips: List[Optional[AudioClip]] = [None] * len(z_p)
+        spf = voc.samples_per_frame
+        i = 0
+        while i < len(order):
+            tmax = int(z_p[order[i]].shape[-1])
+            n = max(1, min(len(order) - i, max_frames // max(tmax, 1)))
+            grp = order[i:i + n]
+            zb = torch.zeros(n, voc.inter_channels, tmax, device=dev, dtype=dt)
+            mb = torch.zeros(n, 1, tmax, device=dev, dtype=dt)
+            gb = torch.empty(n, voc.gin_channels, 1, device=dev, dtype=dt)
+            for r, k in enumerate(grp):
+                t = int(z_p[k].shape[-1])
+                zb[r, :, :t] = z_p[k].to(device=dev, dtype=dt, non_blocking=True)
+                mb[r, :, :t] = 1
+                gb[r] = ge[k].to(device=dev, dtype=dt, non_blocking=True).view(voc.gin_channels, 1)
+            audio = voc.flow_dec(zb, mb, gb).float().cpu().numpy()
+            for r, k in enumerate(grp):
+                clips[k] = self._clip(audio[r, 0, : int(z_p[k].shape[-1]) * spf])
+            i += n
+        return clips
 
     def _clip(self, audio: np.ndarray, text: str = "") -> AudioClip:
         peak = float(np.abs(audio).max()) if audio.size else 0.0

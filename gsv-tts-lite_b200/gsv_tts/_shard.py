@@ -30,8 +30,10 @@ def shard_by_length(lengths: Sequence[int], world: int) -> List[List[int]]:
 
 def broadcast_state_dict(sd: Dict[str, torch.Tensor], src: int = 0, device=None) -> Dict[str, torch.Tensor]:
     """Weight blobs from rank ``src`` to every rank (NCCL over NVLink on GPUs, gloo on CPU).  Every rank
-    passes a state dict with the same keys/shapes/dtypes (non-source ranks may pass uninitialised tensors);
-    returns CPU tensors.  This is the only collective of the whole path."""
+    passes a state dict with the same keys/shapes/dtypes (non-source ranks may pass uninitialised tensors).
+    With ``device`` the tensors are broadcast GPU to GPU and STAY on the device (no host bounce: the native
+    loaders take device tensors); without it they travel and return as CPU tensors.  This is the only
+    collective of the whole path."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return sd
     out = {}
@@ -39,8 +41,27 @@ def broadcast_state_dict(sd: Dict[str, torch.Tensor], src: int = 0, device=None)
         t = sd[k]
         buf = t.to(device) if device is not None else t.clone()
         dist.broadcast(buf, src)
-        out[k] = buf.cpu()
+        out[k] = buf
     return out
+
+
+def broadcast_checkpoint(read_fn, src: int = 0, device=None):
+    """Rank ``src`` calls ``read_fn() -> (meta, state_dict)`` (the only rank that touches the file system); ``meta`` (config /
+    hps: small python objects) and the tensors' names, shapes and dtypes go out as objects, the tensors themselves with
+    ``broadcast_state_dict``.  Returns ``(meta, state_dict)`` on every rank.  Single process: just ``read_fn()``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return read_fn()
+    rank = dist.get_rank()
+    if rank == src:
+        meta, sd = read_fn()
+        head = [meta, [(k, tuple(v.shape), v.dtype) for k, v in sorted(sd.items())]]
+    else:
+        sd, head = None, [None, None]
+    dist.broadcast_object_list(head, src)
+    meta, layout = head
+    if rank != src:
+        sd = {k: torch.empty(shape, dtype=dtype) for k, shape, dtype in layout}
+    return meta, broadcast_state_dict(sd, src, device)
 
 
 def gather_in_order(local_results: Dict[int, object], n_total: int) -> List[object]:

@@ -44,6 +44,12 @@ def _worker(rank, world, port, q):
         sd = ref if rank == 0 else {k: torch.full_like(v, float("nan")) for k, v in ref.items()}
         got = _shard.broadcast_state_dict(sd, 0)
         ok_bcast = all(torch.equal(got[k], ref[k]) for k in ref)
+        # checkpoint load under torch.distributed: only rank 0 touches the file system (Loader.get_*_weights)
+        def read():
+            assert rank == 0, "only the source rank may read the checkpoint"
+            return {"model": {"hidden_dim": 512}}, ref
+        meta, got2 = _shard.broadcast_checkpoint(read, 0)
+        ok_bcast = ok_bcast and meta == {"model": {"hidden_dim": 512}} and all(torch.equal(got2[k], ref[k]) for k in ref)
         # sharded "inference": every request's result is a function of the request only
         lengths = [50 + 7 * (i % 11) for i in range(23)]
         mine = _shard.shard_by_length(lengths, world)[rank]
