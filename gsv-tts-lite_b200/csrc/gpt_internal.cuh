@@ -105,6 +105,10 @@ void gsv_umma_cache_destroy(gsv_umma_cache* c);
 int gsv_umma_linear(gsv_umma_cache* c, size_t op, int dtype, const void* X, int rows, int rows_cap, int K, const void* W,
                     const void* bias, int N, void* out, int relu, cudaStream_t st);
 
+// Conv1d with KW taps ('same' padding, odd KW) on the same kernel: X [rows][K] T, W [KW][N][K] T, out [rows][N] T.
+int gsv_umma_conv(gsv_umma_cache* c, size_t op, int dtype, const void* X, int rows, int K, const void* W, const void* bias, int N, int KW,
+                  void* out, int relu, cudaStream_t st);
+
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
 int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
 int gsv_gpt_prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st);

@@ -998,3 +998,24 @@ int gsv_umma_linear(gsv_umma_cache* c, size_t op, int dtype, const void* X, int 
   if (dtype == GSV_F16) return umma_linear_t<__half>(c, op, X, rows, rows_cap, K, W, bias, N, out, relu, st);
   return umma_linear_t<__nv_bfloat16>(c, op, X, rows, rows_cap, K, W, bias, N, out, relu, st);
 }
+
+// Conv1d with KW taps ('same' zero padding, odd KW) over channels-last rows: out[t][n] = act(sum_k X[t + k - KW/2] . W[k][n] + bias[n]),
+// X [rows][K] T, W [KW][N][K] T.  The FFN convolutions of the prior encoder (encp.cu; attentions.py:244-271).
+template <typename T>
+static int umma_conv_t(gsv_umma_cache* c, size_t op, const void* X, int rows, int K, const void* W, const void* bias, int N, int KW,
+                       void* out, int relu, cudaStream_t st) {
+  ConvArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.in = reinterpret_cast<const T*>(X); a.in_ld = K; a.B = 1; a.Tin = rows; a.Tout = rows; a.Cin = K; a.Cout = N;
+  a.KW = KW; a.dil = 1; a.stride = 1; a.res_sign = 1.f; a.acc_scale = 1.f;
+  a.w = reinterpret_cast<const T*>(W); a.w_tap = (long long)N * K; a.bias = reinterpret_cast<const T*>(bias);
+  a.outT = reinterpret_cast<T*>(out); a.o_ld = N; a.act = relu ? ACT_RELU : ACT_NONE;
+  if (!umma_eligible<T>(a) || (KW & 1) == 0) { gsv_set_error("umma conv: unsupported shape K=%d N=%d KW=%d", K, N, KW); return GSV_ERR_ARG; }
+  return launch_conv_umma<T>(c->maps, c->num_sms, a, op, st);
+}
+
+int gsv_umma_conv(gsv_umma_cache* c, size_t op, int dtype, const void* X, int rows, int K, const void* W, const void* bias, int N, int KW,
+                  void* out, int relu, cudaStream_t st) {
+  if (dtype == GSV_F16) return umma_conv_t<__half>(c, op, X, rows, K, W, bias, N, KW, out, relu, st);
+  return umma_conv_t<__nv_bfloat16>(c, op, X, rows, K, W, bias, N, KW, out, relu, st);
+}

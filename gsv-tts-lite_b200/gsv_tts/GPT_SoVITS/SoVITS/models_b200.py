@@ -159,3 +159,171 @@ class FlowDecoder(nn.Module):
 
     def launch_count(self) -> int:
         return int(N.lib().gsv_voc_launch_count(self._ctx))
+
+
+class _PriorEncoderState:
+    """What callers touch on ``vq_model.enc_p``: the cross-chunk state of streaming decode (reference models.py:194,
+    213-215; ``TTS.infer_stream`` resets it with ``enc_p.y_overlap = None``, TTS.py:498).  The tensor itself lives in the
+    native context; here it can only be forgotten."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.latent_channels = owner.inter_channels
+
+    @property
+    def y_overlap(self):
+        return None
+
+    @y_overlap.setter
+    def y_overlap(self, value):
+        if value is not None:
+            raise ValueError("enc_p.y_overlap can only be reset to None on the B200 backend")
+        if self._owner._enc_ctx is not None:
+            N.check(N.lib().gsv_encp_reset_stream(self._owner._enc_ctx))
+
+
+class SynthesizerTrn(FlowDecoder):
+    """``SynthesizerTrn`` as ``Loader.get_sovits_weights`` builds it (reference SoVITS/models.py:235-429), inference half:
+    ``decode`` (codes -> waveform: quantizer lookup, prior encoder ``enc_p``, prior sample, reverse flow, HiFi-GAN),
+    ``flow_dec``, ``initialize_runtime``, ``samples_per_frame``, ``enc_p.y_overlap``.  Everything between the semantic
+    tokens and the waveform runs in ``libgsv_b200.so`` (csrc/encp.cu, csrc/vocoder.cu).  ``get_ge`` / ``extract_latent``
+    (reference-audio featurisers run once per cached prompt, TTS.py:1374, 1567) are not part of the hot path and not here."""
+
+    def __init__(self, spec_channels=1025, segment_size=32, inter_channels=192, hidden_channels=192, filter_channels=768, n_heads=2,
+                 n_layers=6, kernel_size=3, p_dropout=0.0, n_speakers=0, gin_channels=512, semantic_frame_rate="25hz", version="v2",
+                 **kw):
+        super().__init__(inter_channels=inter_channels, hidden_channels=hidden_channels, gin_channels=gin_channels, version=version, **kw)
+        self.filter_channels, self.n_heads, self.n_layers, self.kernel_size = filter_channels, n_heads, n_layers, kernel_size
+        self.is_v2pro = version in ("v2Pro", "v2ProPlus")
+        self._enc_raw: Dict[str, torch.Tensor] = {}
+        self._enc_dev: Dict[str, torch.Tensor] = {}
+        self._enc_ctx = None
+        self.enc_p = _PriorEncoderState(self)
+        self.debug_seed: Optional[int] = None
+        self._noise = None          # test hook: [inter, T'] fp32 tensor standing for randn_like(m_p)
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        super().load_state_dict(state_dict, strict)
+        keep = ("enc_p.", "ge_to512.", "quantizer.vq.layers.0._codebook.embed")
+        self._enc_raw = {k: v.detach().float() for k, v in state_dict.items() if k.startswith(keep)}
+        return self
+
+    def state_dict(self, *a, **k):
+        sd = super().state_dict()
+        sd.update(self._enc_raw)
+        return sd
+
+    @torch.inference_mode()
+    def initialize_runtime(self, dtype, device, sovits_cache=None):
+        super().initialize_runtime(dtype, device, sovits_cache)
+        raw = self._enc_raw
+        if "enc_p.proj.weight" not in raw:
+            return                      # a flow + HiFi-GAN only checkpoint: decode() is unavailable, flow_dec works
+        d = N.EncpDims(hidden_channels=self.hidden_channels, filter_channels=self.filter_channels, inter_channels=self.inter_channels,
+                       n_heads=self.n_heads, n_layers=self.n_layers, kernel_size=self.kernel_size,
+                       ssl_dim=raw["quantizer.vq.layers.0._codebook.embed"].shape[1],
+                       n_codes=raw["quantizer.vq.layers.0._codebook.embed"].shape[0],
+                       n_symbols=raw["enc_p.text_embedding.weight"].shape[0], mrte_channels=raw["enc_p.mrte.c_pre.weight"].shape[0],
+                       mrte_heads=4, gin_channels=self.gin_channels, dtype=N.dtype_code(dtype))
+        ctx = C.c_void_p()
+        with torch.cuda.device(self._device):
+            N.check(N.lib().gsv_encp_create(C.byref(d), C.byref(ctx)))
+        self._enc_ctx = ctx
+
+        def put(name, w, b=None):
+            wd = w.to(device=self._device, dtype=dtype).contiguous()
+            bd = b.to(device=self._device, dtype=dtype).contiguous() if b is not None else None
+            self._enc_dev[name] = wd
+            if bd is not None:
+                self._enc_dev[name + "#b"] = bd
+            N.check(N.lib().gsv_encp_set_weight(ctx, name.encode(), wd.data_ptr(), bd.data_ptr() if bd is not None else None))
+
+        def lin(name):                  # Conv1d k=1 [out][in][1] -> [out][in]
+            put(name, raw[name + ".weight"][:, :, 0], raw[name + ".bias"])
+
+        put("quantizer.codebook", raw["quantizer.vq.layers.0._codebook.embed"])
+        put("enc_p.text_embedding", raw["enc_p.text_embedding.weight"])
+        lin("enc_p.ssl_proj")
+        lin("enc_p.proj")
+        for nm in ("c_pre", "text_pre", "c_post"):
+            lin("enc_p.mrte." + nm)
+        ca = "enc_p.mrte.cross_attention."
+        lin(ca + "conv_q")
+        lin(ca + "conv_o")
+        put(ca + "kv", torch.cat([raw[ca + "conv_k.weight"][:, :, 0], raw[ca + "conv_v.weight"][:, :, 0]], 0),
+            torch.cat([raw[ca + "conv_k.bias"], raw[ca + "conv_v.bias"]], 0))
+        for enc, n in (("encoder_ssl", self.n_layers // 2), ("encoder_text", self.n_layers), ("encoder2", self.n_layers // 2)):
+            for i in range(n):
+                a = f"enc_p.{enc}.attn_layers.{i}."
+                put(a + "qkv", torch.cat([raw[a + f"conv_{c}.weight"][:, :, 0] for c in "qkv"], 0),
+                    torch.cat([raw[a + f"conv_{c}.bias"] for c in "qkv"], 0))
+                lin(a + "conv_o")
+                put(a + "emb_rel_k", raw[a + "emb_rel_k"][0])
+                put(a + "emb_rel_v", raw[a + "emb_rel_v"][0])
+                for j in (1, 2):
+                    put(f"enc_p.{enc}.norm_layers_{j}.{i}", raw[f"enc_p.{enc}.norm_layers_{j}.{i}.gamma"],
+                        raw[f"enc_p.{enc}.norm_layers_{j}.{i}.beta"])
+                    f = f"enc_p.{enc}.ffn_layers.{i}.conv_{j}"
+                    put(f, raw[f + ".weight"].permute(2, 0, 1), raw[f + ".bias"])      # [out][in][k] -> [k][out][in]
+        if self.is_v2pro and "ge_to512.weight" in raw:
+            put("ge_to512", raw["ge_to512.weight"], raw["ge_to512.bias"])
+
+    def __del__(self):
+        try:
+            if self._enc_ctx is not None:
+                N.lib().gsv_encp_destroy(self._enc_ctx)
+                self._enc_ctx = None
+        except Exception:
+            pass
+        super().__del__()
+
+    @torch.inference_mode()
+    def prior(self, codes, text, ge, noise_scale=0.5, speed=1, stream_mode=False, valid_start_idx=None, overlap_len=None,
+              slice_indices=None, return_stats=False):
+        """The front of ``decode`` (models.py:387-404): -> (z_p [1,inter,T'], y_mask [1,1,T'], ge for flow_dec, attn [4,T,Nt]
+        [, m_p, logs_p])."""
+        if self._enc_ctx is None:
+            raise N.NativeError("this SoVITS checkpoint carries no enc_p weights: decode() needs them")
+        dev, dt = self._device, self._dtype
+        codes = codes.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        text = text.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        n, nt = codes.numel(), text.numel()
+        ge = ge.to(device=dev, dtype=dt)
+        if ge.shape[-1] != 1:                                        # models.py:389
+            ge = torch.nn.functional.interpolate(ge.float(), size=ge.shape[-1] * 2, mode="nearest").to(dt)
+        ge_c = ge[0].contiguous()
+        tg = ge_c.shape[-1]
+        lib = N.lib()
+        speed = float(speed)
+        vs = int(valid_start_idx) if stream_mode else 0
+        ov = int(overlap_len) if stream_mode else 0
+        tp = lib.gsv_encp_output_frames(self._enc_ctx, n, speed, 1 if stream_mode else 0, vs)
+        z_p = torch.empty(1, self.inter_channels, tp, device=dev, dtype=dt)
+        attn = torch.empty(4, 2 * n, nt, device=dev, dtype=torch.float32)
+        m_p = torch.empty(self.inter_channels, tp, device=dev, dtype=torch.float32) if return_stats else None
+        logs_p = torch.empty_like(m_p) if return_stats else None
+        lo, hi = (-1, -1) if slice_indices is None else (int(slice_indices[0, 0]), int(slice_indices[0, 1]))
+        noise = self._noise.to(device=dev, dtype=torch.float32).contiguous() if self._noise is not None else None
+        if noise is not None and tuple(noise.shape[-2:]) != (self.inter_channels, tp):
+            raise ValueError(f"injected noise has shape {tuple(noise.shape)}, expected [{self.inter_channels}, {tp}]")
+        seed = self.debug_seed if self.debug_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        frames = C.c_int(0)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N.check(lib.gsv_encp_forward(self._enc_ctx, codes.data_ptr(), n, text.data_ptr(), nt, ge_c.data_ptr(), tg, speed,
+                                     1 if stream_mode else 0, vs, ov, lo, hi, noise.data_ptr() if noise is not None else None,
+                                     float(noise_scale), seed, z_p.data_ptr(), m_p.data_ptr() if return_stats else None,
+                                     logs_p.data_ptr() if return_stats else None, attn.data_ptr(), C.byref(frames), st))
+        assert frames.value == tp
+        y_mask = torch.ones(1, 1, tp, device=dev, dtype=dt)
+        if speed != 1 and ge.shape[-1] != 1:                         # models.py:402
+            ge = torch.nn.functional.interpolate(ge.float(), size=tp, mode="nearest").to(dt)
+        out = (z_p, y_mask, ge, attn)
+        return out + (m_p, logs_p) if return_stats else out
+
+    @torch.inference_mode()
+    def decode(self, codes, text, ge, noise_scale=0.5, speed=1, cuda_graph=True, stream_mode=False, valid_start_idx=None,
+               overlap_len=None, slice_indices=None):
+        """models.py:385-429: codes [1,1,N] int64, text [1,Nt] int64, ge [1,gin,1|N] -> (audio [1,1,640 T'], attn [4,T,Nt]).
+        ``cuda_graph`` is accepted for signature compatibility (the native path takes any length)."""
+        z_p, y_mask, ge2, attn = self.prior(codes, text, ge, noise_scale, speed, stream_mode, valid_start_idx, overlap_len, slice_indices)
+        return self.flow_dec(z_p, y_mask, ge2), attn

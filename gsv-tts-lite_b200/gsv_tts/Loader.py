@@ -187,14 +187,16 @@ def get_sovits_weights(sovits_path: str, tts_config: Config) -> Sovits:
     """Builds the native SoVITS half (flow + HiFi-GAN, and the prior encoder where the checkpoint carries it); same
     rank-0-reads / NCCL-broadcast rule as ``get_gpt_weights``."""
     from . import _shard
-    from .GPT_SoVITS.SoVITS.models_b200 import FlowDecoder
+    from .GPT_SoVITS.SoVITS.models_b200 import SynthesizerTrn
 
     def read():
         hps, sd, _ = read_sovits_checkpoint(sovits_path)
         return hps, sd
 
     hps, sd = _shard.broadcast_checkpoint(read, 0, tts_config.device)
-    model = FlowDecoder(**hps["model"])
+    data = hps.get("data", {})
+    model = SynthesizerTrn(data.get("filter_length", 2048) // 2 + 1, hps.get("train", {}).get("segment_size", 20480) // data.get("hop_length", 640),
+                           n_speakers=data.get("n_speakers", 0), **hps["model"])       # reference Loader.py:66-71, 87-92
     model.load_state_dict(sd)
     model.initialize_runtime(tts_config.dtype, tts_config.device, tts_config.sovits_cache)
     return Sovits(model, hps)

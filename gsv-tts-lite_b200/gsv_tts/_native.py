@@ -43,6 +43,12 @@ class VocDims(C.Structure):
                 ("resblock_dilations", (C.c_int32 * 3) * 4), ("dtype", C.c_int32)]
 
 
+class EncpDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "hidden_channels", "filter_channels", "inter_channels", "n_heads", "n_layers", "kernel_size", "ssl_dim", "n_codes",
+        "n_symbols", "mrte_channels", "mrte_heads", "gin_channels", "dtype")]
+
+
 # every symbol include/gsv_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = [
@@ -71,6 +77,14 @@ SYMBOLS = [
     ("gsv_voc_flow_dec", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     ("gsv_voc_set_debug_z", C.c_int, [_P, _P]),
     ("gsv_voc_launch_count", C.c_int64, [_P]),
+    ("gsv_encp_create", C.c_int, [C.POINTER(EncpDims), C.POINTER(_P)]),
+    ("gsv_encp_set_weight", C.c_int, [_P, C.c_char_p, _P, _P]),
+    ("gsv_encp_destroy", C.c_int, [_P]),
+    ("gsv_encp_output_frames", C.c_int, [_P, C.c_int, C.c_float, C.c_int, C.c_int]),
+    ("gsv_encp_forward", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   _P, C.c_float, C.c_uint64, _P, _P, _P, _P, C.POINTER(C.c_int), _P]),
+    ("gsv_encp_reset_stream", C.c_int, [_P]),
+    ("gsv_encp_launch_count", C.c_int64, [_P]),
 ]
 
 _lib = None

@@ -219,6 +219,56 @@ int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const void* dev_mask
 int gsv_voc_set_debug_z(gsv_voc_ctx* ctx, void* dev_z);
 int64_t gsv_voc_launch_count(gsv_voc_ctx* ctx);
 
+/* ======================================================================================
+ * SoVITS prior encoder: semantic tokens -> z_p (the stage between the two hot paths)
+ * replaces the front of SynthesizerTrn.decode (reference SoVITS/models.py:385-404): quantizer.decode
+ * (module/core_vq.py:133-135, 222-226) + x2 nearest interpolation, ge_to512 (:396), TextEncoder.infer
+ * (models.py:196-224; module/attentions.py:10-278; module/mrte_model.py:19-38) and the prior sample (:404).
+ * ====================================================================================== */
+
+typedef struct {
+  int32_t hidden_channels;   /* 192 */
+  int32_t filter_channels;   /* 768 */
+  int32_t inter_channels;    /* 192: m_p / logs_p channels */
+  int32_t n_heads;           /* 2   */
+  int32_t n_layers;          /* 6: encoder_text; encoder_ssl and encoder2 have n_layers / 2 */
+  int32_t kernel_size;       /* 3 (FFN convolutions) */
+  int32_t ssl_dim;           /* 768: codebook width */
+  int32_t n_codes;           /* 1024 codebook entries */
+  int32_t n_symbols;         /* 732 phoneme symbols */
+  int32_t mrte_channels;     /* 512 */
+  int32_t mrte_heads;        /* 4   */
+  int32_t gin_channels;      /* 512 (v2) / 1024 (v2Pro, v2ProPlus: ge goes through ge_to512 first) */
+  int32_t dtype;
+} gsv_encp_dims;
+
+typedef struct gsv_encp_ctx gsv_encp_ctx;
+
+int gsv_encp_create(const gsv_encp_dims* dims, gsv_encp_ctx** out);
+/* Weights by name, already in T: linear / 1x1 convolution [out][in]; FFN convolution [k][out][in]; tables as stored.
+ * Names: "quantizer.codebook" [n_codes][ssl_dim]; "enc_p.ssl_proj"; "enc_p.text_embedding" [n_symbols][C];
+ * "enc_p.{encoder_ssl,encoder_text,encoder2}.attn_layers.{i}.qkv" (conv_q | conv_k | conv_v stacked on the output axis),
+ * "...attn_layers.{i}.conv_o", "...attn_layers.{i}.emb_rel_k" / "emb_rel_v" [9][96], "...norm_layers_{1,2}.{i}" (weight =
+ * gamma, bias = beta), "...ffn_layers.{i}.conv_{1,2}"; "enc_p.mrte.{c_pre,text_pre,c_post}",
+ * "enc_p.mrte.cross_attention.{conv_q,kv,conv_o}" (kv = conv_k | conv_v stacked); "enc_p.proj"; optional "ge_to512". */
+int gsv_encp_set_weight(gsv_encp_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias);
+int gsv_encp_destroy(gsv_encp_ctx* ctx);
+/* Frames of z_p a call produces: 2 * n_codes, minus valid_start in stream mode, then int(T / speed) + 1 if speed != 1. */
+int gsv_encp_output_frames(gsv_encp_ctx* ctx, int n_codes, float speed, int stream_mode, int valid_start);
+/* dev_codes [n_codes] int64, dev_text [n_text] int64, dev_ge [gin][Tg] T (torch layout; Tg == 1 or 2 * n_codes; NULL: none).
+ * stream_mode / valid_start / overlap_len: the cross-fade with the previous chunk's tail, kept in the context
+ * (enc_p.y_overlap, models.py:208-215; gsv_encp_reset_stream forgets it, TTS.py:498).  slice_lo < 0: every text position is
+ * attended; else [slice_lo, slice_hi) plus the last one (mrte_model.py:26-32).  dev_noise [inter][T'] fp32 stands for
+ * randn_like(m_p) (NULL: in-kernel Philox normal keyed by `seed`).  Outputs: dev_z_p [inter][T'] T (what flow_dec takes);
+ * optional dev_m_p / dev_logs_p [inter][T'] fp32; optional dev_attn [mrte_heads][2 n_codes][n_text] fp32 (what decode()
+ * returns as attn, models.py:427-429); *out_frames = T'. */
+int gsv_encp_forward(gsv_encp_ctx* ctx, const int64_t* dev_codes, int n_codes, const int64_t* dev_text, int n_text, const void* dev_ge,
+                     int Tg, float speed, int stream_mode, int valid_start, int overlap_len, int slice_lo, int slice_hi,
+                     const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p, float* dev_logs_p,
+                     float* dev_attn, int* out_frames, void* stream);
+int gsv_encp_reset_stream(gsv_encp_ctx* ctx);
+int64_t gsv_encp_launch_count(gsv_encp_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif
