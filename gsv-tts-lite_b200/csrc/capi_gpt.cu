@@ -106,11 +106,10 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
     const char* e = getenv("GSV_DECODE_IMPL");
     ctx->force_barrier_kernel = (e && strcmp(e, "barrier") == 0) ? 1 : 0;
     ctx->force_ll1 = (e && strcmp(e, "ll1") == 0) ? 1 : 0;
-    ctx->force_ll2 = (e && strcmp(e, "ll2") == 0) ? 1 : 0;
     ctx->force_hx = (e && strcmp(e, "hx") == 0) ? 1 : 0;
     ctx->force_gemm = (e && strcmp(e, "gemm") == 0) ? 1 : 0;
     ctx->use_cl = (e && strcmp(e, "cl") == 0) ? 1 : 0;
-    ctx->use_cln = (e && strcmp(e, "cl2") == 0) ? 2 : ((e && strcmp(e, "cl4") == 0) ? 4 : ((e && strcmp(e, "cl8") == 0) ? 8 : 0));
+    ctx->use_cl8 = (e && strcmp(e, "cl8") == 0) ? 1 : 0;
     const char* g = getenv("GSV_GPT_GEMM");
     ctx->use_umma_linear = (g && strcmp(g, "cuda") == 0) ? 0 : 1;
     ctx->umma = gsv_umma_cache_create(ctx->num_sms);
@@ -185,41 +184,30 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   int live = 0;
   for (int i = 0; i < ctx->p.slots; ++i) live += ctx->slot_live[i];
   if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
-  // 1..4 live sequences: latency-optimised flag-in-data kernel; otherwise the barrier kernel
-  // Measured on B200 (tools/decode_speed.py, bf16, kv 164..289), us per step (tokens per second):
-  //   live   ll     ll2    cl (1 seq/cluster)   cl2 (2/cluster)   cl4 (4/cluster)   cl8 (8/cluster, mma)   gemm (multi-kernel, tcgen05 linears)
-  //    1     299    309    355                                                                               1760
-  //    2     381    375    359  ( 5.6k)
-  //    4     595    523    355  (11.3k)
-  //    6      -      -     357  (16.8k)   <- at most 7 sixteen-CTA clusters are co-resident; more run in waves
-  //    8      -      -     712  (11.2k)          657 (12.2k)      1027 ( 7.8k)        427 (18.7k)           1567 ( 5.1k)
-  //   14      -      -      -                    656 (21.3k)      1018 (13.8k)
-  //   16      -      -      -                     -                 -                 423 (37.9k)
-  //   28      -      -      -                   1308 (21.4k)      1016 (27.6k)                              1580 (17.7k)
-  //   32      -      -    ~2140 (14.9k)         1962 (16.3k)      2062 (15.5k)        432 (74.1k)           1583 (20.2k)
-  // -> 1: ll; 2..7: one cluster per sequence; 8 and more: eight per cluster on the tensor cores; the multi-kernel step
-  //    where clusters of H CTAs cannot be launched (GSV_DECODE_IMPL overrides).
-  const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_ll2 || ctx->force_gemm;
+  // Measured on B200 (tools/decode_speed.py / bench.py, bf16, kv 164..364), us per step (tokens per second):
+  //   live   hx (head clusters)   ll (grid-wide LL)   cl (1 seq/cluster)   cl8 (8/cluster, mma)   gemm (multi-kernel, tcgen05 linears)
+  //    1     168 ( 5.9k)          293                 355                                         1760
+  //    2      -                   381                 359 ( 5.6k)
+  //    4      -                   595                 355 (11.3k)
+  //    6      -                    -                  357 (16.8k)   <- at most 7 sixteen-CTA clusters are co-resident; more run in waves
+  //    8      -                    -                  712 (11.2k)          430 (18.6k)            1567 ( 5.1k)
+  //   16      -                    -                   -                   423 (37.9k)
+  //   32      -                    -                ~2140 (14.9k)          444 (72.1k)            1583 (20.2k)
+  // -> 1: head-cluster kernel (grid-wide LL kernel where its clusters are not co-resident); 2..7: one cluster per sequence;
+  //    8 and more: eight per cluster on the tensor cores; the multi-kernel step where clusters of H CTAs cannot be
+  //    launched; the grid-barrier kernel for shapes none of them takes (GSV_DECODE_IMPL overrides).
+  const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_gemm;
   // one live sequence: head-cluster kernel (2 grid-wide exchanges per layer instead of 5)
-  if ((ctx->force_hx || (live == 1 && !explicit_impl && !ctx->use_cl && !ctx->use_cln)) && gsv_gpt_hx_supported(ctx, live, n_steps)) {
+  if ((ctx->force_hx || (live == 1 && !explicit_impl && !ctx->use_cl && !ctx->use_cl8)) && gsv_gpt_hx_supported(ctx, live, n_steps)) {
     const int rc = gsv_gpt_decode_hx_launch(ctx, n_steps, (cudaStream_t)stream);
     if (rc != GSV_ERR_STATE || ctx->force_hx) return rc;      // GSV_ERR_STATE: clusters not co-resident here -> grid-wide kernel below
   }
-  if (ctx->use_cln == 8 && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
-  if (ctx->use_cln && gsv_gpt_cl_supported(ctx, live)) return gsv_gpt_decode_cln_launch(ctx, live, ctx->use_cln, n_steps, (cudaStream_t)stream);
-  if (!explicit_impl && !ctx->use_cl && gsv_gpt_cl_supported(ctx, live)) {
-    if (live >= 8 && ctx->p.H >= 8) return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
-    if (live >= 8 && live <= 14) return gsv_gpt_decode_cln_launch(ctx, live, 2, n_steps, (cudaStream_t)stream);
-    if (live >= 15 && live <= 28) return gsv_gpt_decode_cln_launch(ctx, live, 4, n_steps, (cudaStream_t)stream);
-  }
+  if ((ctx->use_cl8 || (!explicit_impl && !ctx->use_cl && live >= 8)) && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8)
+    return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if ((ctx->use_cl || (!explicit_impl && live >= 2 && live <= 7)) && gsv_gpt_cl_supported(ctx, live))
     return gsv_gpt_decode_cl_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (ctx->force_gemm || (live > 4 && !ctx->force_barrier_kernel && ctx->use_umma_linear))
     return gsv_gpt_decode_gemm_launch(ctx, n_steps, (cudaStream_t)stream);
-  // measured on B200 (tools/decode_speed.py, bf16, kv 164..289): 1 live sequence 299 us/token (ll) vs 317 (ll2);
-  // 2 live 381 vs 375; 4 live 595 vs 560 -> ll2 from two live sequences up, ll for one (GSV_DECODE_IMPL overrides)
-  if (!ctx->force_barrier_kernel && !ctx->force_ll1 && (live >= 2 || ctx->force_ll2) && gsv_gpt_ll2_supported(ctx, live, n_steps))
-    return gsv_gpt_decode_ll2_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (!ctx->force_barrier_kernel && gsv_gpt_ll_supported(ctx, live, n_steps))
     return gsv_gpt_decode_ll_launch(ctx, live, n_steps, (cudaStream_t)stream);
   return gsv_gpt_decode_launch(ctx, n_steps, (cudaStream_t)stream);

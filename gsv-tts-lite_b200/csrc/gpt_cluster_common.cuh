@@ -1,5 +1,5 @@
 // gpt_cluster_common.cuh -- device helpers shared by the cluster decode kernels (gpt_decode_cl.cu: one sequence per
-// cluster; gpt_decode_cln.cu: several sequences per cluster): mbarrier / bulk-copy / st.async wrappers, the staged
+// cluster; gpt_decode_cl8.cu: eight sequences per cluster; gpt_decode_hx.cu: one sequence over every cluster): mbarrier / bulk-copy / st.async wrappers, the staged
 // vector layout, register dot products, transposing-butterfly reductions, LayerNorm pieces, timeline markers.
 #pragma once
 #include <cstdlib>

@@ -85,7 +85,7 @@ struct gsv_gpt_ctx {
   int decode_sms;                 // gsv_gpt_set_decode_sms: CTAs of the single-sequence decode kernel (0 = every SM)
   void* cl8_pack;                 // gpt_decode_cl8.cu: block weights re-tiled into chunk / mma-fragment order (first launch)
   void* cl8_head_pack;            // ... and the head rows
-  int use_cln;                    // GSV_DECODE_IMPL=cl2 / cl4: clusters serving 2 / 4 sequences each
+  int use_cl8;                    // GSV_DECODE_IMPL=cl8: the tensor-core cluster kernel for any live count
   void* hx_pack;                  // gpt_decode_hx.cu: per-(layer, CTA) weight blobs (first launch)
   void* hx_head_pack;             // ... and the per-CTA head rows
   int hx_clusters_ok;             // 0 not asked yet, 1 every cluster of the kernel is co-resident, -1 not
@@ -94,7 +94,6 @@ struct gsv_gpt_ctx {
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
   int force_ll1;                  // GSV_DECODE_IMPL=ll1: first-generation small-batch kernel (A/B checks)
-  int force_ll2;                  // GSV_DECODE_IMPL=ll2: second-generation kernel also for a single live sequence
 };
 
 // nn.Linear on the tcgen05 implicit-GEMM kernel (vocoder.cu / conv_umma.cuh): out[r][n] = act(X[r] . W[n] + bias[n]),
@@ -117,12 +116,9 @@ int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);
 size_t gsv_gpt_ll_buffer_bytes(const gsv_gpt_ctx* ctx);
 bool gsv_gpt_ll_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
 int gsv_gpt_decode_ll_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
-bool gsv_gpt_ll2_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
-int gsv_gpt_decode_ll2_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
 int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
 bool gsv_gpt_cl_supported(const gsv_gpt_ctx* ctx, int live_slots);
 int gsv_gpt_decode_cl_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
-int gsv_gpt_decode_cln_launch(gsv_gpt_ctx* ctx, int live_slots, int nb, int n_steps, cudaStream_t st);
 int gsv_gpt_decode_cl8_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cudaStream_t st);
 size_t gsv_gpt_hx_buffer_words(const gsv_gpt_ctx* ctx);
 bool gsv_gpt_hx_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);

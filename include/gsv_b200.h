@@ -128,9 +128,10 @@ int gsv_gpt_prefill_finish(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_y, int
 /* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
  * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
  * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).
- * The kernel is picked from the number of live slots: 1 -> grid-wide flag-in-data kernel, 2..7 -> one thread-block
- * cluster per sequence, 8 and more -> clusters serving eight sequences each on tensor-core tiles.
- * Environment (tuning / A-B only): GSV_DECODE_IMPL = ll1 | ll2 | cl | cl2 | cl4 | cl8 | gemm | barrier; GSV_GPT_GEMM = cuda. */
+ * The kernel is picked from the number of live slots: 1 -> head-cluster kernel (4 CTAs per attention head, 2 grid-wide
+ * exchanges per layer), 2..7 -> one thread-block cluster per sequence, 8 and more -> clusters serving eight sequences each on
+ * tensor-core tiles.
+ * Environment (tuning / A-B only): GSV_DECODE_IMPL = hx | ll1 | cl | cl8 | gemm | barrier; GSV_HX_CS = 4 | 8 | 16; GSV_GPT_GEMM = cuda. */
 int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream);
 
 /* Copy slot state to host memory (asynchronously on `stream`; caller synchronises):
