@@ -84,18 +84,21 @@ __global__ void __launch_bounds__(128) enc_add_ln_kernel(T* __restrict__ x, cons
 
 // ---- multi-head attention with optional window-4 relative-position terms (attentions.py:119-161) ----------------------
 // One warp per (query row, head).  q / k / v are rows of channels-last buffers (row strides ldq / ldk / ldv, head h at
-// +h*DK).  Keys outside [klo, khi) are masked with -1e4 like the reference's masked_fill; key Tk-1 is always kept when
-// keep_last (MRTE's null key, mrte_model.py:31).  rel_k / rel_v: [2*WIN+1][DK] T or null.  probs: [H][Tq][Tk] fp32 or null.
+// +h*DK).  win: [n_win][2] (start, end) per query row (n_win == Tq) or one for all (n_win == 1): keys outside are masked
+// with -1e4 like the reference's masked_fill, key Tk-1 is always kept (MRTE's null key, mrte_model.py:31); null: no mask.  rel_k / rel_v: [2*WIN+1][DK] T or null.  probs: [H][Tq][Tk] fp32 or null.
 template <typename T, int DK>
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
                                                              const T* __restrict__ v, int ldv, T* __restrict__ out, int ldo, int Tq,
                                                              int Tk, int H, const T* __restrict__ rel_k, const T* __restrict__ rel_v,
-                                                             int klo, int khi, int keep_last, float* __restrict__ probs) {
+                                                             const int* __restrict__ win, int n_win, float* __restrict__ probs) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * AT_WARPS + warp;
   if (item >= Tq * H) return;
   const int i = item / H, h = item - i * H;
+  // key window of this query row: [klo, khi) plus the last key (MRTE), or everything
+  int klo = 0, khi = Tk, keep_last = 0;
+  if (win != nullptr) { const int r = n_win > 1 ? i : 0; klo = win[2 * r]; khi = win[2 * r + 1]; keep_last = 1; }
   float* sc = sm + (size_t)warp * (Tk + DK + 16);       // [Tk] scores / probabilities
   float* qs = sc + Tk;                                   // [DK] scaled query
   float* rk = qs + DK;                                   // [9] q . E_k[o]
@@ -311,13 +314,13 @@ struct Fwd {
   }
   template <int DK>
   void attention(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int Tq, int Tk, int H, const T* rel_k,
-                 const T* rel_v, int klo, int khi, int keep_last, float* probs) {
+                 const T* rel_v, const int* win, int n_win, float* probs) {
     if (rc) return;
     const size_t smem = (size_t)AT_WARPS * (Tk + DK + 16) * sizeof(float);
     if (smem > 200 * 1024) { gsv_set_error("enc_p: %d keys exceed the attention kernel's shared memory", Tk); rc = GSV_ERR_ARG; return; }
     cudaFuncSetAttribute(attn_kernel<T, DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attn_kernel<T, DK><<<(Tq * H + AT_WARPS - 1) / AT_WARPS, AT_WARPS * 32, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, Tq, Tk, H, rel_k,
-                                                                                       rel_v, klo, khi, keep_last, probs);
+                                                                                       rel_v, win, n_win, probs);
     ctx->launches += 1;
   }
   // attentions.Encoder (attentions.py:59-80) on x [Tn][C], in place; buffers: qkv [Tn][3C], att [Tn][C], tmp [Tn][C], hid [Tn][F]
@@ -330,7 +333,7 @@ struct Fwd {
       const EW* ev = get(a + "emb_rel_v");
       if (!ek || !ev) return;
       attention<96>(qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, Tn, Tn, H, reinterpret_cast<const T*>(ek->w),
-                    reinterpret_cast<const T*>(ev->w), 0, Tn, 0, nullptr);
+                    reinterpret_cast<const T*>(ev->w), nullptr, 0, nullptr);
       linear(att, Tn, C, a + "conv_o", C, tmp);
       const EW* n1 = get(pre + "norm_layers_1." + std::to_string(l));
       if (!n1) return;
@@ -348,7 +351,7 @@ struct Fwd {
 
 template <typename T>
 int encp_forward_t(gsv_encp_ctx* ctx, const int64_t* codes, int n_codes, const int64_t* text, int n_text, const void* ge_v, int Tg,
-                   float speed, int stream_mode, int valid_start, int overlap_len, int slice_lo, int slice_hi, const float* noise,
+                   float speed, int stream_mode, int valid_start, int overlap_len, const int* slices, int n_slices, const float* noise,
                    float noise_scale, unsigned long long seed, void* z_p_v, float* m_out, float* logs_out, float* attn_out, int* out_T,
                    cudaStream_t st) {
   const gsv_encp_dims& d = ctx->dims;
@@ -420,11 +423,7 @@ int encp_forward_t(gsv_encp_ctx* ctx, const int64_t* codes, int n_codes, const i
   f.linear(tx, Nt, C, "enc_p.mrte.text_pre", Cm, tp);
   f.linear(s, Tn, Cm, "enc_p.mrte.cross_attention.conv_q", Cm, cq);
   f.linear(tp, Nt, Cm, "enc_p.mrte.cross_attention.kv", 2 * Cm, ckv);
-  {
-    const bool sliced = slice_lo >= 0;
-    f.template attention<128>(cq, Cm, ckv, 2 * Cm, ckv + Cm, 2 * Cm, ca, Cm, Tn, Nt, d.mrte_heads, nullptr, nullptr, sliced ? slice_lo : 0,
-                              sliced ? slice_hi : Nt, sliced ? 1 : 0, attn_out);
-  }
+  f.template attention<128>(cq, Cm, ckv, 2 * Cm, ckv + Cm, 2 * Cm, ca, Cm, Tn, Nt, d.mrte_heads, nullptr, nullptr, slices, n_slices, attn_out);
   f.linear(ca, Tn, Cm, "enc_p.mrte.cross_attention.conv_o", Cm, cx);
   if (f.rc) return f.rc;
   mrte_combine_kernel<T><<<Tn, 128, 0, st>>>(cx, s, ge_in, Tg, Tn, Cm, ca);
@@ -510,15 +509,16 @@ extern "C" int gsv_encp_output_frames(gsv_encp_ctx* ctx, int n_codes, float spee
 }
 
 extern "C" int gsv_encp_forward(gsv_encp_ctx* ctx, const int64_t* dev_codes, int n_codes, const int64_t* dev_text, int n_text,
-                                const void* dev_ge, int Tg, float speed, int stream_mode, int valid_start, int overlap_len, int slice_lo,
-                                int slice_hi, const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p,
+                                const void* dev_ge, int Tg, float speed, int stream_mode, int valid_start, int overlap_len,
+                                const int32_t* dev_slices, int n_slices, const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p,
                                 float* dev_logs_p, float* dev_attn, int* out_frames, void* stream) {
   GSV_ARG(ctx && dev_codes && dev_text && dev_z_p && n_codes >= 1 && n_text >= 1);
+  GSV_ARG(dev_slices == nullptr || n_slices == 1 || n_slices == 2 * n_codes);
   if (ctx->dims.dtype == GSV_F16)
-    return encp_forward_t<__half>(ctx, dev_codes, n_codes, dev_text, n_text, dev_ge, Tg, speed, stream_mode, valid_start, overlap_len, slice_lo,
-                                  slice_hi, dev_noise, noise_scale, seed, dev_z_p, dev_m_p, dev_logs_p, dev_attn, out_frames, (cudaStream_t)stream);
+    return encp_forward_t<__half>(ctx, dev_codes, n_codes, dev_text, n_text, dev_ge, Tg, speed, stream_mode, valid_start, overlap_len, dev_slices,
+                                  n_slices, dev_noise, noise_scale, seed, dev_z_p, dev_m_p, dev_logs_p, dev_attn, out_frames, (cudaStream_t)stream);
   return encp_forward_t<__nv_bfloat16>(ctx, dev_codes, n_codes, dev_text, n_text, dev_ge, Tg, speed, stream_mode, valid_start, overlap_len,
-                                       slice_lo, slice_hi, dev_noise, noise_scale, seed, dev_z_p, dev_m_p, dev_logs_p, dev_attn, out_frames,
+                                       dev_slices, n_slices, dev_noise, noise_scale, seed, dev_z_p, dev_m_p, dev_logs_p, dev_attn, out_frames,
                                        (cudaStream_t)stream);
 }
 

@@ -302,7 +302,11 @@ class SynthesizerTrn(FlowDecoder):
         attn = torch.empty(4, 2 * n, nt, device=dev, dtype=torch.float32)
         m_p = torch.empty(self.inter_channels, tp, device=dev, dtype=torch.float32) if return_stats else None
         logs_p = torch.empty_like(m_p) if return_stats else None
-        lo, hi = (-1, -1) if slice_indices is None else (int(slice_indices[0, 0]), int(slice_indices[0, 1]))
+        sl = None
+        if slice_indices is not None:                               # [1, 2] or one (start, end) row per frame
+            sl = slice_indices.to(device=dev, dtype=torch.int32).reshape(-1, 2).contiguous()
+            if sl.shape[0] not in (1, 2 * n):
+                raise ValueError(f"slice_indices has {sl.shape[0]} rows; expected 1 or {2 * n}")
         noise = self._noise.to(device=dev, dtype=torch.float32).contiguous() if self._noise is not None else None
         if noise is not None and tuple(noise.shape[-2:]) != (self.inter_channels, tp):
             raise ValueError(f"injected noise has shape {tuple(noise.shape)}, expected [{self.inter_channels}, {tp}]")
@@ -310,7 +314,8 @@ class SynthesizerTrn(FlowDecoder):
         frames = C.c_int(0)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         N.check(lib.gsv_encp_forward(self._enc_ctx, codes.data_ptr(), n, text.data_ptr(), nt, ge_c.data_ptr(), tg, speed,
-                                     1 if stream_mode else 0, vs, ov, lo, hi, noise.data_ptr() if noise is not None else None,
+                                     1 if stream_mode else 0, vs, ov, sl.data_ptr() if sl is not None else None,
+                                     sl.shape[0] if sl is not None else 0, noise.data_ptr() if noise is not None else None,
                                      float(noise_scale), seed, z_p.data_ptr(), m_p.data_ptr() if return_stats else None,
                                      logs_p.data_ptr() if return_stats else None, attn.data_ptr(), C.byref(frames), st))
         assert frames.value == tp

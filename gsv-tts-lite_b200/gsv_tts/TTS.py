@@ -6,10 +6,14 @@ What is here: the constructor keywords, ``load_gpt_model`` / ``load_sovits_model
 ``infer_batched`` (TTS.py:232-247, 695-764) for callers that already hold phoneme ids, BERT features, prompt
 tokens and the vocoder latents.
 
-What is not: the text front end (G2P, language segmentation, BERT / HuBERT / speaker-embedding featurisers)
-and ``enc_p`` are outside the scope of this package.  ``infer`` /
-``infer_stream`` / ``infer_batched`` therefore need a ``frontend`` object that supplies those pieces and raise a
-clear error without one -- they never fall back to a CPU path.
+``infer_phones`` / ``infer_phones_stream`` are the reference's ``infer`` / ``infer_stream`` from the point where the text
+front end has done its work (phoneme ids, BERT rows, prompt tokens, speaker embedding): GPT decode, ``vq_model.decode``
+(prior encoder + flow + HiFi-GAN), monotonic alignment, silence trimming, SOLA splicing -- all on the device.
+
+What is not here: the text front end itself (G2P, language segmentation, BERT / HuBERT / speaker-embedding featurisers;
+SURVEY.md 2 rows 7-9).  ``infer`` / ``infer_stream`` / ``infer_batched`` keep the reference's signatures and take those
+pieces from a ``frontend`` plug-in (three methods, see ``TTS.infer``); without one they raise -- they never fall back to
+a CPU path.
 """
 from __future__ import annotations
 
@@ -201,19 +205,253 @@ class TTS:
             audio = audio / peak                                    # TTS.py:276-278
         return AudioClip(audio, self.samplerate, orig_text=text)
 
-    # ---- text entry points need the front end -----------------------------------------------------------------------
+    # ---- host glue of infer / infer_stream, on the device (reference TTS.py:1612-1797; csrc/glue.cu) ---------------------------
+    def _native_dtype(self, t: torch.Tensor):
+        from . import _native as N
+        return N, N.dtype_code(t.dtype)
+
+    def _viterbi_monotonic(self, attn: torch.Tensor) -> torch.Tensor:
+        """TTS.py:1744-1797: attn [H, T, N] -> int64 [T] monotonic text index per frame (-1 before the first aligned frame).
+        One launch instead of a Python loop over the frames."""
+        import ctypes as C
+        from . import _native as N
+        attn = attn.to(torch.float32).contiguous()
+        H, T, Nn = attn.shape
+        work = torch.empty(T * Nn * 5, dtype=torch.uint8, device=attn.device)
+        assign = torch.empty(T, dtype=torch.int32, device=attn.device)
+        st = C.c_void_p(torch.cuda.current_stream(attn.device).cuda_stream)
+        N.check(N.lib().gsv_glue_viterbi_monotonic(attn.data_ptr(), H, T, Nn, work.data_ptr(), assign.data_ptr(), st))
+        return assign.to(torch.int64)
+
+    def _silence_offset(self, audio: torch.Tensor, tail: bool, threshold, frame_length, hop_length, search_len, margin) -> int:
+        import ctypes as C
+        N, code = self._native_dtype(audio)
+        audio = audio.contiguous()
+        work = torch.empty(2, dtype=torch.int32, device=audio.device)
+        out = torch.empty(1, dtype=torch.int32, device=audio.device)
+        st = C.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)
+        N.check(N.lib().gsv_glue_silence_offset(audio.data_ptr(), audio.numel(), code, 1 if tail else 0, float(threshold), frame_length,
+                                                hop_length, search_len, margin, work.data_ptr(), out.data_ptr(), st))
+        return int(out.item())
+
+    def _find_head_threshold_offsets(self, audio, threshold=0.02, frame_length=512, hop_length=256, search_len=64000, margin=3200):
+        """TTS.py:1630-1645 (frame RMS in fp32 here; the reference squares and averages in the 16-bit storage type)."""
+        return self._silence_offset(audio, False, threshold, frame_length, hop_length, search_len, margin)
+
+    def _find_tail_threshold_offsets(self, audio, threshold=0.01, frame_length=512, hop_length=256, search_len=64000, margin=3200):
+        """TTS.py:1647-1662."""
+        return self._silence_offset(audio, True, threshold, frame_length, hop_length, search_len, margin)
+
+    def _sola_algorithm(self, f1_overlap, f2, overlap_len, search_len: int = 320):
+        """TTS.py:1612-1628: f1_overlap [1,1,ov], f2 [1,1,n] -> (f2 aligned and cross-faded [1,1,n - offset], offset tensor)."""
+        import ctypes as C
+        N, code = self._native_dtype(f2)
+        f1, f2c = f1_overlap.reshape(-1).contiguous(), f2.reshape(-1).contiguous()
+        n2 = f2c.numel()
+        work = torch.empty(search_len + 1, dtype=torch.float32, device=f2.device)
+        off = torch.empty(1, dtype=torch.int32, device=f2.device)
+        out = torch.empty(n2, dtype=f2.dtype, device=f2.device)
+        st = C.c_void_p(torch.cuda.current_stream(f2.device).cuda_stream)
+        N.check(N.lib().gsv_glue_sola(f1.data_ptr(), f2c.data_ptr(), n2, int(overlap_len), int(search_len), code, work.data_ptr(),
+                                      off.data_ptr(), out.data_ptr(), st))
+        k = int(off.item())
+        return out[: n2 - k].view(1, 1, -1), off
+
+    def _get_subtitles(self, word2ph, assign, speed, last_end_s=0):
+        """TTS.py:1664-1707: frame alignment -> word timings (host arithmetic on T small integers)."""
+        frame_time = (1 / self.sovits_hz) / speed
+        assign = assign.tolist() if hasattr(assign, "tolist") else list(assign)
+        ph_end_s, cur = [], int(assign[0])
+        for f in range(1, len(assign)):
+            if int(assign[f]) != cur:
+                ph_end_s.append(f * frame_time)
+                cur = int(assign[f])
+        ph_end_s.append(len(assign) * frame_time)
+        idx = -1
+        end_s = last_end_s + ph_end_s.pop(0) if assign[0] == -1 else last_end_s
+        subtitles, word = [], None
+        for i in range(len(word2ph["word"])):
+            word, ph = word2ph["word"][i], word2ph["ph"][i]
+            idx += ph
+            if idx >= len(ph_end_s):
+                break
+            start_s, end_s = end_s, ph_end_s[idx] + last_end_s
+            subtitles.append({"text": word, "start_s": start_s, "end_s": end_s})
+        if end_s - last_end_s != ph_end_s[-1]:
+            start_s, end_s = end_s, ph_end_s[-1] + last_end_s
+            subtitles.append({"text": word, "start_s": start_s, "end_s": end_s})
+        return subtitles
+
+    @staticmethod
+    def _increment_subtitle_times(subtitles, increment):
+        for sub in subtitles:
+            sub["start_s"] += increment
+            if sub["end_s"]:
+                sub["end_s"] += increment
+
+    # ---- the reference's infer / infer_stream from the point where the front end has produced its features ---------------------
+    @torch.inference_mode()
+    def infer_phones(self, phones1: Sequence[int], bert1: torch.Tensor, prompt: torch.Tensor, phones2: Sequence[int], bert2: torch.Tensor,
+                     ge: torch.Tensor, word2ph: Optional[dict] = None, text: str = "", return_subtitles: bool = False, top_k: int = 15,
+                     top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5,
+                     speed: float = 1.0, gpt_model: Optional[str] = None, sovits_model: Optional[str] = None) -> AudioClip:
+        """``TTS.infer`` (TTS.py:232-286) after ``_prepare_*_resources`` and ``get_phones_and_bert``: GPT decode ->
+        ``vq_model.decode`` -> monotonic alignment (-> subtitles) -> leading-silence trim -> peak normalisation -> 0.2 s tail.
+        phones1 / bert1 / prompt: the cached prompt's phoneme ids, BERT rows [N1,1024] and semantic tokens [1,Ny]; phones2 /
+        bert2: the target text's; ge: the speaker embedding [1,gin,1]."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev = self.tts_config.device
+        ids = torch.tensor(list(phones1) + list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
+        bert = torch.cat([bert1.to(dev), bert2.to(dev)]).unsqueeze(0)
+        pred = gpt.infer(ids, prompt, bert, top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty)
+        ph2 = torch.tensor(list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
+        audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed)
+        audio = audio[0, 0, :]
+        assign = self._viterbi_monotonic(attn)
+        subtitles = []
+        if return_subtitles and word2ph is not None:
+            subtitles = self._get_subtitles(word2ph, assign, speed)
+            subtitles[-1]["end_s"] += 0.2
+        head = self._find_head_threshold_offsets(audio)
+        audio = audio[head:]
+        if subtitles:
+            self._increment_subtitle_times(subtitles, -head / self.samplerate)
+            subtitles[0]["start_s"] = max(0, subtitles[0]["start_s"])
+        audio = audio.float().cpu().numpy()
+        peak = float(np.abs(audio).max()) if audio.size else 0.0
+        if peak > 1:
+            audio = audio / peak
+        audio = np.concatenate([audio, np.zeros((int(0.2 * self.samplerate),), dtype=audio.dtype)])
+        return AudioClip(audio, self.samplerate, subtitles=subtitles, orig_text=text)
+
+    def infer_phones_stream(self, phones1: Sequence[int], bert1: torch.Tensor, prompt: torch.Tensor, phones2: Sequence[int],
+                            bert2: torch.Tensor, ge: torch.Tensor, stream_chunk: int = 25, overlap_len: int = 5,
+                            boost_first_chunk: bool = True, cut_mute: float = 0.4, top_k: int = 15, top_p: float = 1.0,
+                            temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5, speed: float = 1.0,
+                            gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, force_steps: Optional[int] = None):
+        """One text cut of ``TTS.infer_stream`` (TTS.py:402-498): every ``stream_chunk`` semantic tokens the whole prefix goes
+        through ``vq_model.decode(stream_mode=True)``; chunks are spliced with SOLA over ``overlap_len`` frames, the first one
+        loses its leading silence, the last one gets ``cut_mute`` seconds of silence.  Yields one ``AudioClip`` per chunk.
+        The decode of chunk c+1 is already in flight on the GPT's SMs while chunk c goes through the prior encoder and the
+        vocoder on a second stream."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev = self.tts_config.device
+        side = torch.cuda.Stream(dev)
+        with torch.inference_mode():
+            ids = torch.tensor(list(phones1) + list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
+            bert = torch.cat([bert1.to(dev), bert2.to(dev)]).unsqueeze(0)
+            ph2 = torch.tensor(list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
+            ge = ge.to(dev)
+        overlap_samples = overlap_len * vq.samples_per_frame
+        audio_len_s, last_overlap, valid_start, chunk_idx = 0.0, None, 0, 0
+        it = gpt.infer_stream(ids, prompt, bert, top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
+                              stream_chunk=stream_chunk, boost_first_chunk=boost_first_chunk, force_steps=force_steps)
+        try:
+            while True:
+                with torch.inference_mode():
+                    try:
+                        pred, is_final = next(it)
+                    except StopIteration:
+                        break
+                    with torch.cuda.stream(side):
+                        side.wait_event(gpt.chunk_ready)
+                        pred.record_stream(side)
+                        audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed, stream_mode=True,
+                                                valid_start_idx=valid_start, overlap_len=overlap_len)
+                        if last_overlap is not None:
+                            audio, _ = self._sola_algorithm(last_overlap, audio, overlap_samples)
+                        last_overlap = audio[:, :, -overlap_samples:].clone()
+                        if not is_final:
+                            audio = audio[:, :, :-overlap_samples]
+                            valid_start = attn.shape[1] - overlap_len
+                        audio = audio[0, 0, :]
+                        if chunk_idx == 0:
+                            audio = audio[self._find_head_threshold_offsets(audio):]
+                        if is_final:
+                            audio = torch.cat([audio, torch.zeros(int(cut_mute * self.samplerate), dtype=audio.dtype, device=dev)])
+                        out = audio.float().cpu().numpy()
+                audio_len_s += len(out) / self.samplerate
+                chunk_idx += 1
+                yield AudioClip(out, self.samplerate, audio_len_s=audio_len_s)
+        finally:
+            vq.enc_p.y_overlap = None                      # TTS.py:498
+
+    # ---- text entry points: the front end (G2P, BERT, HuBERT, speaker embedding) is a plug-in ----------------------------------
     def _need_frontend(self, name):
         if self.frontend is None:
             raise FrontendRequired(
-                f"TTS.{name} needs the text / audio front end (G2P, BERT, HuBERT, speaker embedding, enc_p), which is "
-                "outside this package's scope (SURVEY.md 2 rows 7-9): pass frontend=..., or call infer_features().")
+                f"TTS.{name} needs the text / audio front end (G2P, BERT, HuBERT, speaker embedding), which is outside this "
+                "package's scope (SURVEY.md 2 rows 7-9): pass frontend=..., or call infer_phones() / infer_phones_stream().")
         return self.frontend
 
-    def infer(self, *args, **kwargs):
-        return self._need_frontend("infer").infer(self, *args, **kwargs)
+    def infer(self, spk_audio_path, prompt_audio_path: str, prompt_audio_text: str, text: str, return_subtitles: bool = False,
+              top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5,
+              speed: float = 1.0, gpt_model: Optional[str] = None, sovits_model: Optional[str] = None) -> AudioClip:
+        """``TTS.infer`` (TTS.py:150-286).  The front end supplies ``speaker(tts, sovits_model, spk_audio_path) -> ge``,
+        ``prompt(tts, gpt_model, prompt_audio_path, prompt_audio_text) -> (prompt tokens, phones1, bert1)`` and
+        ``phones_and_bert(text) -> (phones2, word2ph, bert2, norm_text)`` (reference _prepare_sovits_resources,
+        _prepare_gpt_resources, get_phones_and_bert); everything after that runs here."""
+        fe = self._need_frontend("infer")
+        ge = fe.speaker(self, sovits_model, spk_audio_path)
+        prompt, phones1, bert1 = fe.prompt(self, gpt_model, prompt_audio_path, prompt_audio_text)
+        phones2, word2ph, bert2, _norm = fe.phones_and_bert(text)
+        return self.infer_phones(phones1, bert1, prompt, phones2, bert2, ge, word2ph=word2ph, text=text, return_subtitles=return_subtitles,
+                                 top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
+                                 noise_scale=noise_scale, speed=speed, gpt_model=gpt_model, sovits_model=sovits_model)
 
-    def infer_stream(self, *args, **kwargs):
-        return self._need_frontend("infer_stream").infer_stream(self, *args, **kwargs)
+    def infer_stream(self, spk_audio_path, prompt_audio_path: str, prompt_audio_text: str, text: str, cut_minlen: int = 10,
+                     cut_mute: float = 0.4, stream_chunk: int = 25, overlap_len: int = 5, boost_first_chunk: bool = True, top_k: int = 15,
+                     top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5,
+                     speed: float = 1.0, gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, **_ignored):
+        """``TTS.infer_stream`` (TTS.py:289-504): the text is cut, every cut streams through ``infer_phones_stream``."""
+        fe = self._need_frontend("infer_stream")
+        ge = fe.speaker(self, sovits_model, spk_audio_path)
+        prompt, phones1, bert1 = fe.prompt(self, gpt_model, prompt_audio_path, prompt_audio_text)
+        total = 0.0
+        for i, cut in enumerate(cut_text(text, cut_minlen)):
+            phones2, _w2p, bert2, _norm = fe.phones_and_bert(cut)
+            for clip in self.infer_phones_stream(phones1, bert1, prompt, phones2, bert2, ge, stream_chunk=stream_chunk,
+                                                 overlap_len=overlap_len, boost_first_chunk=boost_first_chunk if i == 0 else False,
+                                                 cut_mute=cut_mute, top_k=top_k, top_p=top_p, temperature=temperature,
+                                                 repetition_penalty=repetition_penalty, noise_scale=noise_scale, speed=speed,
+                                                 gpt_model=gpt_model, sovits_model=sovits_model):
+                total += len(clip.audio_data) / self.samplerate
+                clip.audio_len_s = total
+                clip.orig_text = text
+                yield clip
 
-    def infer_batched(self, *args, **kwargs):
-        return self._need_frontend("infer_batched").infer_batched(self, *args, **kwargs)
+    @torch.inference_mode()
+    def infer_batched(self, spk_audio_paths, prompt_audio_paths, prompt_audio_texts, texts, top_k: int = 15, top_p: float = 1.0,
+                      temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5, speed: float = 1.0,
+                      gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, **_ignored):
+        """``TTS.infer_batched`` (TTS.py:507-868): every text goes through the continuous-batched GPT (``infer_batched``), then
+        through ``vq_model.decode`` one utterance at a time (the reference concatenates a SoVITS batch into ONE sequence whose
+        encoder attends across utterance boundaries, TTS.py:730-764; decoding them separately is the per-utterance result the
+        single path gives).  Returns a tuple of ``AudioClip`` in input order."""
+        fe = self._need_frontend("infer_batched")
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev = self.tts_config.device
+        one = lambda v, i: v[i] if isinstance(v, (list, tuple)) else v
+        ids, prompts, berts, ph2s, ges = [], [], [], [], []
+        for i, text in enumerate(texts):
+            ge = fe.speaker(self, sovits_model, one(spk_audio_paths, i))
+            prompt, phones1, bert1 = fe.prompt(self, gpt_model, one(prompt_audio_paths, i), one(prompt_audio_texts, i))
+            phones2, _w2p, bert2, _norm = fe.phones_and_bert(text)
+            ids.append(torch.tensor(list(phones1) + list(phones2), dtype=torch.int64, device=dev))
+            prompts.append(prompt.reshape(-1))
+            berts.append(torch.cat([bert1.to(dev), bert2.to(dev)]))
+            ph2s.append(torch.tensor(list(phones2), dtype=torch.int64, device=dev).unsqueeze(0))
+            ges.append(ge)
+        toks, order = gpt.infer_batched(ids, prompts, berts, top_k=top_k, top_p=top_p, temperature=temperature,
+                                        repetition_penalty=repetition_penalty)
+        clips: List[Optional[AudioClip]] = [None] * len(texts)
+        for t, i in zip(toks, order.tolist()):
+            audio, _attn = vq.decode(t.view(1, 1, -1), ph2s[i], ges[i], noise_scale=noise_scale, speed=speed)
+            audio = audio[0, 0, :]
+            head = self._find_head_threshold_offsets(audio)
+            tail = self._find_tail_threshold_offsets(audio)
+            clips[i] = self._clip(audio[head:audio.numel() - tail].float().cpu().numpy(), texts[i])
+        return tuple(clips)

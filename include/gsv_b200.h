@@ -258,17 +258,38 @@ int gsv_encp_destroy(gsv_encp_ctx* ctx);
 int gsv_encp_output_frames(gsv_encp_ctx* ctx, int n_codes, float speed, int stream_mode, int valid_start);
 /* dev_codes [n_codes] int64, dev_text [n_text] int64, dev_ge [gin][Tg] T (torch layout; Tg == 1 or 2 * n_codes; NULL: none).
  * stream_mode / valid_start / overlap_len: the cross-fade with the previous chunk's tail, kept in the context
- * (enc_p.y_overlap, models.py:208-215; gsv_encp_reset_stream forgets it, TTS.py:498).  slice_lo < 0: every text position is
- * attended; else [slice_lo, slice_hi) plus the last one (mrte_model.py:26-32).  dev_noise [inter][T'] fp32 stands for
+ * (enc_p.y_overlap, models.py:208-215; gsv_encp_reset_stream forgets it, TTS.py:498).  Text window of the MRTE cross
+ * attention (mrte_model.py:26-32): dev_slices [n_slices][2] int32 rows (start, end), n_slices == 1 (one window for every
+ * frame) or 2 * n_codes (one per frame: the concatenated utterances of infer_batched, TTS.py:740-747); the last text
+ * position is always attended; NULL: every position.  dev_noise [inter][T'] fp32 stands for
  * randn_like(m_p) (NULL: in-kernel Philox normal keyed by `seed`).  Outputs: dev_z_p [inter][T'] T (what flow_dec takes);
  * optional dev_m_p / dev_logs_p [inter][T'] fp32; optional dev_attn [mrte_heads][2 n_codes][n_text] fp32 (what decode()
  * returns as attn, models.py:427-429); *out_frames = T'. */
 int gsv_encp_forward(gsv_encp_ctx* ctx, const int64_t* dev_codes, int n_codes, const int64_t* dev_text, int n_text, const void* dev_ge,
-                     int Tg, float speed, int stream_mode, int valid_start, int overlap_len, int slice_lo, int slice_hi,
+                     int Tg, float speed, int stream_mode, int valid_start, int overlap_len, const int32_t* dev_slices, int n_slices,
                      const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p, float* dev_logs_p,
                      float* dev_attn, int* out_frames, void* stream);
 int gsv_encp_reset_stream(gsv_encp_ctx* ctx);
 int64_t gsv_encp_launch_count(gsv_encp_ctx* ctx);
+
+/* ======================================================================================
+ * Host glue of TTS.infer / infer_stream as device kernels: results stay on the device.
+ * ====================================================================================== */
+
+/* _viterbi_monotonic (reference gsv_tts/TTS.py:1744-1797): dev_attn [H][T][N] fp32 (what decode() returns) ->
+ * dev_assign [T] int32: text index per frame, monotonic, -1 before the first frame whose averaged row peaks at index 0.
+ * dev_work: T * N * 5 bytes of scratch. */
+int gsv_glue_viterbi_monotonic(const float* dev_attn, int H, int T, int N, void* dev_work, int32_t* dev_assign, void* stream);
+/* _find_head_threshold_offsets (tail = 0, TTS.py:1630-1645) / _find_tail_threshold_offsets (tail = 1, :1647-1662): the
+ * first / last frame (frame_length samples every hop_length) of the first / last search_len samples whose RMS exceeds
+ * `threshold`, turned into the number of samples to cut.  dev_audio [n] T; dev_work: 8 bytes; *dev_offset int32. */
+int gsv_glue_silence_offset(const void* dev_audio, int n, int dtype, int tail, float threshold, int frame_length, int hop_length,
+                            int search_len, int margin, void* dev_work, int32_t* dev_offset, void* stream);
+/* _sola_algorithm (TTS.py:1612-1628): dev_f1_overlap [overlap_len] T (tail of the previous chunk), dev_f2 [n2] T (new
+ * chunk) -> *dev_offset (best alignment in [0, search_len]) and dev_out [n2 - offset] T: the cross-faded overlap followed by
+ * the rest of the aligned chunk.  dev_work: (search_len + 1) floats; dev_out must hold n2 elements. */
+int gsv_glue_sola(const void* dev_f1_overlap, const void* dev_f2, int n2, int overlap_len, int search_len, int dtype, void* dev_work,
+                  int32_t* dev_offset, void* dev_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -188,9 +188,70 @@ def make_encp(name, key):
     print(f"encp {name}: m_p std {float(out['m_p'].std()):.3f} logs mean {float(out['logs_p'].mean()):.3f}")
 
 
+def reference_glue_methods():
+    """The bodies of the reference's own glue methods, compiled from the source text of gsv_tts/TTS.py (the module cannot be
+    imported here: it needs av, pysbd, ...).  Returns (namespace of plain functions taking ``self`` first, fake self)."""
+    import ast
+    import types
+    import torch.nn.functional as F
+    src = open(os.path.join(ref_shim.REF_ROOT, "gsv_tts", "TTS.py")).read()
+    want = {"_viterbi_monotonic", "_sola_algorithm", "_find_head_threshold_offsets", "_find_tail_threshold_offsets", "_get_subtitles"}
+    fns = [n for cls in ast.parse(src).body if isinstance(cls, ast.ClassDef) and cls.name == "TTS"
+           for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {f.name for f in fns} == want
+    ns = {"torch": torch, "F": F, "np": np}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "reference_TTS_glue", "exec"), ns)
+    me = types.SimpleNamespace(tts_config=types.SimpleNamespace(device=torch.device("cpu"), dtype=torch.float32), samplerate=32000, sovits_hz=50)
+    return ns, me
+
+
+def glue_cases(seed=0):
+    """Seeded inputs for the glue functions: attention maps with a monotonic drift (three sizes, one with heads stuck on
+    the null key), a waveform with leading / trailing silence, two overlapping chunks for SOLA."""
+    g = torch.Generator().manual_seed(seed)
+    attn = []
+    for T_, N_ in ((40, 12), (7, 3), (123, 50), (400, 97)):
+        logits = torch.randn(4, T_, N_, generator=g) * 2
+        pos = torch.arange(T_).float()[:, None] / T_ * N_
+        logits = logits - 0.5 * (torch.arange(N_)[None, :] - pos).abs()[None]
+        if T_ == 123:
+            logits[1:, 20:30, N_ - 1] += 30.0          # three heads look at the null key for ten frames
+            logits[0, 24:27, N_ - 1] += 30.0           # ... all four for three of them: the default distribution is used
+        attn.append(torch.softmax(logits, -1))
+    n = 70000
+    t = torch.arange(n)
+    audio = torch.randn(n, generator=g) * 0.05 * ((t > 9000) & (t < 61000)).float() + torch.randn(n, generator=g) * 0.002
+    f1 = torch.randn(3200, generator=g)
+    f2 = torch.randn(9000, generator=g) * 0.5
+    f2[137:3337] += 2 * f1
+    return attn, audio, f1, f2
+
+
+def make_glue():
+    ns, me = reference_glue_methods()
+    attn, audio, f1, f2 = glue_cases()
+    out = {}
+    for i, a in enumerate(attn):
+        out[f"attn{i}"] = a.numpy()
+        out[f"assign{i}"] = ns["_viterbi_monotonic"](me, a).numpy()
+    out["audio"] = audio.numpy()
+    out["head_offset"] = np.int64(ns["_find_head_threshold_offsets"](me, audio))
+    out["tail_offset"] = np.int64(ns["_find_tail_threshold_offsets"](me, audio))
+    silent = torch.zeros(5000)
+    out["head_offset_silent"] = np.int64(ns["_find_head_threshold_offsets"](me, silent))
+    out["tail_offset_silent"] = np.int64(ns["_find_tail_threshold_offsets"](me, silent))
+    r, off = ns["_sola_algorithm"](me, f1.view(1, 1, -1), f2.view(1, 1, -1), 3200)
+    out.update(sola_f1=f1.numpy(), sola_f2=f2.numpy(), sola_out=r[0, 0].numpy(), sola_offset=np.int64(int(off)))
+    np.savez_compressed(os.path.join(OUT, "glue.npz"), **out)
+    print("glue: assign sizes", [int(out[f"assign{i}"].shape[0]) for i in range(len(attn))], "head", int(out["head_offset"]),
+          "tail", int(out["tail_offset"]), "sola offset", int(out["sola_offset"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["gpt", "batched", "voc", "encp"]
+    which = sys.argv[1:] or ["gpt", "batched", "voc", "encp", "glue"]
+    if "glue" in which:
+        make_glue()
     if "gpt" in which:
         make_gpt("tiny", syn.GPT_CONFIG_TINY, nx=40, ny=30, n_forced=12, max_seq=256, eos_boost=6.0, infer_seed=7, with_bf16=True)
         make_gpt("full", syn.GPT_CONFIG, nx=48, ny=60, n_forced=8, max_seq=512, eos_boost=6.0, infer_seed=11, with_bf16=True)
