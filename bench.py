@@ -4,9 +4,11 @@
 Headline workload at every N (weak scaling, one process per GPU, independent utterances per rank):
 BASELINE.json configs[1] -- V2Pro, batch=1 streaming, seq_len <= 512:
     prompt Nx=64 phonemes + Ny=100 prompt tokens -> prefill; 200 generated semantic tokens (EOS masked)
-    in 8 stream chunks of 25 (kv 164 -> 364, gpt_cache (1,512)); after every chunk the SoVITS
-    flow + HiFi-GAN vocoder turns 50 (first) / 55 (later) latent frames into 32 kHz audio.
-One "step" = one such utterance, driven through the PUBLIC entry ``gsv_tts.TTS.infer_features_stream`` (models loaded
+    in 8 stream chunks of 25 (kv 164 -> 364, gpt_cache (1,512)); after every chunk ``vq_model.decode(stream_mode=True)``
+    re-encodes the token prefix (prior encoder: 12 relative-position layers + MRTE), and the reverse flow + HiFi-GAN turn the
+    new 45-55 latent frames into 32 kHz audio, spliced to the previous chunk with SOLA (the reference's infer_stream loop,
+    TTS.py:402-498).
+One "step" = one such utterance, driven through the PUBLIC entry ``gsv_tts.TTS.infer_phones_stream`` (models loaded
 with ``TTS.load_gpt_model`` / ``load_sovits_model`` from checkpoint files in the reference's formats).
     value  = generated AR tokens / device time of the step, inputs resident in HBM;
     e2e    = the same call with HOST (pinned) inputs: host->device copies of the prompt, BERT features and latents and
@@ -42,22 +44,26 @@ import torch  # noqa: E402
 
 NX, NY, N_TOK, CHUNK = 64, 100, 200, 25
 FRAMES_FIRST, FRAMES_NEXT = 50, 55        # sovits_cache=[50,55] (reference README_EN.md:214)
-WORKLOAD = "V2Pro batch=1 streaming: prefill 64+100, 200 tokens in 8 chunks of 25, flow+HiFi-GAN 50/55 frames per chunk"
-METRIC = "AR tokens/sec (V2Pro, batch=1 streaming, end-to-end incl. prefill + vocoder)"
+WORKLOAD = "V2Pro batch=1 streaming: prefill 64+100, 200 tokens in 8 chunks of 25; per chunk prior encoder over the prefix + flow + HiFi-GAN on the new 45-55 frames + SOLA"
+METRIC = "AR tokens/sec (V2Pro, batch=1 streaming, end-to-end incl. prefill + prior encoder + vocoder)"
 REF_SAMPLE_TOKENS = 100                    # the CPU reference arm's bounded sample per step
 W_BYTES = (24 * (12 * 512 * 512 + 13 * 512) + 1025 * 512) * 2      # 152.4 MB of 16-bit weights per step
 KV_BYTES = 49152                                                   # per live position per sequence
 DEC_FLOP = {"v2Pro": 813.1e6 + 14.2e6, "v2ProPlus": 1828.4e6 + 14.2e6}   # flow + dec FLOPs per 50 Hz frame
 
 
+N_TEXT = 32                                 # target-text phonemes (the other NX - N_TEXT belong to the prompt)
+
+
 def synth_inputs(seed):
     g = torch.Generator().manual_seed(seed)
-    x = torch.randint(0, 732, (1, NX), generator=g)
+    phones1 = torch.randint(0, 732, (NX - N_TEXT,), generator=g).tolist()
+    phones2 = torch.randint(0, 732, (N_TEXT,), generator=g).tolist()
     y = torch.randint(0, 1024, (1, NY), generator=g)
-    bert = torch.zeros(1, NX, 1024)                        # JA/EN text: bert features are zeros (TextProcessor.py:100)
-    zs = [torch.randn(1, 192, FRAMES_FIRST if i == 0 else FRAMES_NEXT, generator=g) for i in range(N_TOK // CHUNK)]
+    bert1 = torch.zeros(NX - N_TEXT, 1024)                 # JA/EN text: bert features are zeros (TextProcessor.py:100)
+    bert2 = torch.zeros(N_TEXT, 1024)
     ge = torch.randn(1, 1024, 1, generator=g)
-    return x, y, bert, zs, ge
+    return phones1, phones2, y, bert1, bert2, ge
 
 
 def mixed_requests(n, seed, dev, dtype):
@@ -123,9 +129,11 @@ class ClockSampler(threading.Thread):
 # CPU reference arm (oracle port)
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_reference_step(n_tok=N_TOK, threads=None):
-    """One bounded sample of the workload on the host cores with the oracle port of the reference
-    algorithm (fp32, all cores).  Returns (seconds, tokens, description)."""
+    """One bounded sample of the workload on the host cores with the oracle port of the reference algorithm (fp32, all
+    cores): GPT prefill + n_tok decode steps, then per 25-token chunk the prior encoder over the prefix (streaming cross-fade)
+    and flow + HiFi-GAN over the chunk's new frames.  Returns (seconds, tokens, description)."""
     from gsv_tts import _synthetic as syn
+    from oracle.encp_oracle import EncPOracle
     from oracle.gpt_oracle import GptOracle
     from oracle.vocoder_oracle import VocoderOracle
     torch.set_num_threads(threads or os.cpu_count())
@@ -133,15 +141,23 @@ def cpu_reference_step(n_tok=N_TOK, threads=None):
     orc = GptOracle(syn.gpt_state_dict(syn.GPT_CONFIG, 0), syn.GPT_CONFIG)
     model = syn.SOVITS_MODEL["v2Pro"]
     vo = VocoderOracle(syn.sovits_flow_dec_state_dict(model, 0), model)
-    x, y, bert, zs, ge = synth_inputs(1234)
+    enc = EncPOracle(syn.sovits_encp_state_dict(model, 0), model)
+    phones1, phones2, y, bert1, bert2, ge = synth_inputs(1234)
+    x = torch.tensor(phones1 + phones2)
     torch.manual_seed(0)
     t0 = time.perf_counter()
-    orc.infer(x[0], y[0], bert[0], max_seq=512, force_steps=n_tok)
+    toks = orc.infer(x, y[0], torch.cat([bert1, bert2]), max_seq=512, force_steps=n_tok)[0]          # [1, n]
     n_chunks = max(1, n_tok // CHUNK)
-    for z in zs[:n_chunks]:
-        vo.flow_dec(z, torch.ones(1, 1, z.shape[-1]), ge)
+    vs = 0
+    for c in range(n_chunks):
+        codes = toks[:, : CHUNK * (c + 1)].unsqueeze(0)
+        z_p, mask, _m, _l, ge2 = enc.decode_front(codes, torch.tensor(phones2).unsqueeze(0), ge, torch.randn(1, 192, 2 * codes.shape[-1] - vs),
+                                                  stream_mode=True, valid_start_idx=vs, overlap_len=5)
+        vo.flow_dec(z_p, mask, ge2)
+        vs = 2 * codes.shape[-1] - 5
     dt = time.perf_counter() - t0
-    return dt, n_tok, f"1 utterance: prefill {NX}+{NY}, {n_tok} tokens, {n_chunks} vocoder chunks, fp32, {torch.get_num_threads()} threads"
+    return dt, n_tok, (f"1 utterance: prefill {NX}+{NY}, {n_tok} tokens, {n_chunks} chunks of prior encoder + vocoder, fp32, "
+                       f"{torch.get_num_threads()} threads")
 
 
 def run_reference_arm(args, rank, world):
@@ -186,7 +202,9 @@ def write_checkpoints(tmp, sovits_keys=("v2Pro",)):
         model = dict(syn.SOVITS_MODEL[key])
         hps = {"data": {"filter_length": 2048, "hop_length": 640, "n_speakers": 300}, "train": {"segment_size": 20480}, "model": model}
         sp = os.path.join(tmp, f"s2_{key}_synthetic.pth")
-        torch.save({"config": hps, "weight": syn.sovits_flow_dec_state_dict(model, 0)}, sp)
+        sd = dict(syn.sovits_flow_dec_state_dict(model, 0))
+        sd.update(syn.sovits_encp_state_dict(model, 0))              # prior encoder, quantizer codebook, ge_to512
+        torch.save({"config": hps, "weight": sd}, sp)
         spaths[key] = sp
     return gpath, spaths
 
@@ -260,35 +278,31 @@ def main():
     voc = tts.sovits_models[spaths["v2Pro"]].vq_model
     timer = DecodeTimer(gpt)
 
-    x, y, bert, zs, ge = synth_inputs(1234 + rank)
-    dev_in = dict(x=x.to(dev), y=y.to(dev), bert=bert.to(dev, dtype), zs=[z.to(dev, dtype) for z in zs], ge=ge.to(dev, dtype))
-    host_in = dict(x=x.pin_memory(), y=y.pin_memory(), bert=bert.to(dtype).pin_memory(), zs=[z.to(dtype).pin_memory() for z in zs],
-                   ge=ge.to(dtype).pin_memory())
-    mask_first = torch.ones(1, 1, FRAMES_FIRST, device=dev, dtype=dtype)
-    mask_next = torch.ones(1, 1, FRAMES_NEXT, device=dev, dtype=dtype)
+    phones1, phones2, y, bert1, bert2, ge = synth_inputs(1234 + rank)
+    dev_in = dict(y=y.to(dev), bert1=bert1.to(dev, dtype), bert2=bert2.to(dev, dtype), ge=ge.to(dev, dtype))
+    host_in = dict(y=y.pin_memory(), bert1=bert1.to(dtype).pin_memory(), bert2=bert2.to(dtype).pin_memory(), ge=ge.to(dtype).pin_memory())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
     gpt.debug_seed = 99
     stream = torch.cuda.current_stream(dev)
 
     def utterance(inp, first_clip_time=None):
         """One streaming utterance through the public API: 8 chunks of 25 tokens, one AudioClip each."""
-        state = {"c": 0}
-
-        def features_of_chunk(tokens, final):      # stands for enc_p (SURVEY.md 8 f-1): the chunk's latents
-            c = state["c"]
-            state["c"] += 1
-            z = inp["zs"][min(c, len(inp["zs"]) - 1)]
-            return z.to(dev, non_blocking=True), (mask_first if z.shape[-1] == FRAMES_FIRST else mask_next), inp["ge"].to(dev, non_blocking=True)
-
         n_clips = 0
         samples = 0
-        for clip in tts.infer_features_stream(inp["x"], inp["bert"], inp["y"], features_of_chunk, stream_chunk=CHUNK, force_steps=N_TOK):
+        for clip in tts.infer_phones_stream(phones1, inp["bert1"], inp["y"], phones2, inp["bert2"], inp["ge"], stream_chunk=CHUNK,
+                                            overlap_len=5, force_steps=N_TOK):
             if n_clips == 0 and first_clip_time is not None:
                 first_clip_time.append(time.perf_counter())
             n_clips += 1
             samples += clip.audio_data.shape[0]
         assert n_clips == N_TOK // CHUNK, n_clips
         return N_TOK, samples
+
+    def launch_total():
+        n = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count()
+        if voc._enc_ctx is not None:
+            n += int(lib.gsv_encp_launch_count(voc._enc_ctx))
+        return n
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -298,7 +312,7 @@ def main():
 
     def timed(inp, steps, collect):
         evs = []
-        l0 = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count()
+        l0 = launch_total()
         timer.on = collect
         barrier()
         wall0 = time.perf_counter()
@@ -313,7 +327,7 @@ def main():
         wall = time.perf_counter() - wall0
         timer.on = False
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        launches = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count() - l0
+        launches = launch_total() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -377,9 +391,9 @@ def main():
         cpu_base = {"value": ntok / dt, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": desc}
 
     if rank == 0:
-        h2d = sum(t.numel() * t.element_size() for t in [host_in["x"], host_in["y"], host_in["bert"]]) + \
-            sum((z.numel() + host_in["ge"].numel()) * 2 for z in host_in["zs"])
-        d2h = sum(z.shape[-1] * 640 * 4 for z in zs) + (N_TOK // CHUNK) * (512 * 4 + 8)
+        n_chunks = N_TOK // CHUNK
+        h2d = sum(t.numel() * t.element_size() for t in host_in.values()) + (NX + N_TEXT) * 8
+        d2h = 2 * N_TOK * 640 * 4 + n_chunks * (512 * 4 + 8) + n_chunks * 3 * 4       # audio (fp32), tokens + state per chunk, glue offsets
         ref_gpu = None
         try:
             with open(os.path.join(ROOT, "profiles", "r02_ref_gpu_baseline.json")) as f:
@@ -395,9 +409,9 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD, "l2": "256 MB flush between timed steps; 152 MB of weights (> L2) streamed per token",
-                       "api": "gsv_tts.TTS.infer_features_stream (models from TTS.load_gpt_model / load_sovits_model)",
+                       "api": "gsv_tts.TTS.infer_phones_stream (models from TTS.load_gpt_model / load_sovits_model)",
                        "parallelism": f"{world} independent utterance streams, rank 0 reads the checkpoints, NCCL broadcast GPU to GPU at load only",
-                       "overlap": "vocoder of chunk c on a second stream while chunk c+1 decodes on 64 SMs",
+                       "overlap": "prior encoder + vocoder of chunk c on a second stream while chunk c+1 decodes on 64 SMs",
                        "reference_arm_sample": f"{REF_SAMPLE_TOKENS} tokens / {REF_SAMPLE_TOKENS // CHUNK} vocoder chunks per step (per-token rate)"},
             "rtf": (ms_total / 1e3 / args.steps) / audio_s, "ttft_ms": ttft_ms,
             "roofline": roofline, "cpu_baseline": cpu_base,
@@ -431,17 +445,17 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
         xs = [torch.randint(0, 732, (NX,), generator=g).to(dev) for _ in range(B)]
         ys = [torch.randint(0, 1024, (NY,), generator=g).to(dev) for _ in range(B)]
         bs = [torch.zeros(NX, 1024, device=dev, dtype=dtype) for _ in range(B)]
-        zs = [torch.randn(192, 2 * N_TOK, generator=g).to(dev, dtype) for _ in range(B)]
-        ges = [torch.randn(1024, 1, generator=g).to(dev, dtype) for _ in range(B)]
+        ph2 = [torch.randint(0, 732, (N_TEXT,), generator=g).to(dev) for _ in range(B)]
+        ges = [torch.randn(1, 1024, 1, generator=g).to(dev, dtype) for _ in range(B)]
         gpt.debug_seed = 11
-        tts.infer_features_batched(xs, bs, ys, max_new=[16] * B)             # warm-up (kernel choice, weight re-tiling)
-        tts.vocode_features_batched(zs, ges)                                  # same shapes as the timed call (tensor maps, scratch)
+        warm = tts.infer_features_batched(xs, bs, ys, max_new=[16] * B)      # warm-up (kernel choice, weight re-tiling)
+        tts.decode_batched([torch.zeros(N_TOK, dtype=torch.int64, device=dev)] * B, ph2, ges)   # same shapes as the timed call
         timer.on = True
         gpt.debug_seed = 11
         t_gpt, toks = sync_time(lambda: tts.infer_features_batched(xs, bs, ys, max_new=[N_TOK] * B))
         launches = timer.take()
         timer.on = False
-        t_voc, clips = sync_time(lambda: tts.vocode_features_batched(zs, ges))
+        t_voc, clips = sync_time(lambda: tts.decode_batched(toks, ph2, ges))
         n_tok = sum(int(t.numel()) for t in toks)
         steps = min(sum(n for _, n in launches), N_TOK + 1)      # the last launch stops early once every sequence is done
         ms_dec = sum(ms for ms, _ in launches)
@@ -454,7 +468,7 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
             "decode_us_per_step": us_step, "decode_tok_s": B * 1e6 / us_step,
             "roofline": {"kernel": "gpt_decode_hx_kernel" if B == 1 else "gpt_decode_cl8_kernel", "bound": "hbm", "achieved": ach,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "bytes_per_step": bytes_step},
-            "gpt_stage_tok_s": n_tok / t_gpt, "gpt_stage_ms": t_gpt * 1e3, "vocoder_ms": t_voc * 1e3,
+            "gpt_stage_tok_s": n_tok / t_gpt, "gpt_stage_ms": t_gpt * 1e3, "sovits_stage_ms": t_voc * 1e3,
             "e2e_tok_s": n_tok / (t_gpt + t_voc), "e2e_rtf": (t_gpt + t_voc) / audio_s, "audio_s_per_s": audio_s / (t_gpt + t_voc),
             "tokens": n_tok,
         }
@@ -476,12 +490,12 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
     mine = _shard.shard_by_length([len(a) + m for a, m in zip(xs, mx)], world)[rank]
     gz = torch.Generator().manual_seed(99 + rank)
     lx, ly, lb, lm = [xs[i] for i in mine], [ys[i] for i in mine], [bs[i] for i in mine], [mx[i] for i in mine]
-    ges = [torch.randn(1024, 1, generator=gz).to(dev, dtype) for _ in mine]
+    ges = [torch.randn(1, 1024, 1, generator=gz).to(dev, dtype) for _ in mine]
+    ph2s = [torch.randint(0, 732, (max(8, len(a) // 2),), generator=gz).to(dev) for a in lx]
 
     def run4():
         toks = tts.infer_features_batched(lx, lb, ly, max_new=lm)
-        zs = [torch.randn(192, 2 * int(t.numel()), device=dev, dtype=dtype) for t in toks]   # stands for enc_p (row f-1)
-        clips = tts.vocode_features_batched(zs, ges)
+        clips = tts.decode_batched(toks, ph2s, ges)                                 # prior encoder per utterance, batched flow + HiFi-GAN
         return sum(c.audio_data.shape[0] for c in clips) / 32000.0
 
     gpt.debug_seed = 6
@@ -498,7 +512,7 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
         t4, audio4 = float(tmax.item()), float(asum.item())
         got = _shard.gather_in_order({i: 1 for i in mine}, n4)                   # every request answered exactly once
         assert len(got) == n4
-    out["config4"] = {"workload": f"{n4} utterances (32 per GPU) sharded by length over {world} rank(s); continuous batch + flow/HiFi-GAN per rank",
+    out["config4"] = {"workload": f"{n4} utterances (32 per GPU) sharded by length over {world} rank(s); continuous batch + prior encoder + flow/HiFi-GAN per rank",
                       "audio_s": audio4, "ms": t4 * 1e3, "audio_s_per_s": audio4 / t4, "rtf": t4 / audio4}
 
     # ---- config 5: vocoder only, 10 s of latents x batch 64 (rank 0)

@@ -199,6 +199,20 @@ class TTS:
             i += n
         return clips
 
+    @torch.inference_mode()
+    def decode_batched(self, tokens: Sequence[torch.Tensor], phones2: Sequence[torch.Tensor], ge: Sequence[torch.Tensor],
+                       noise_scale: float = 0.5, speed: float = 1.0, sovits_model: Optional[str] = None, max_frames: int = 8192):
+        """SoVITS stage of ``infer_batched`` for a list of utterances: the prior encoder runs per utterance (its attention
+        must not cross utterance boundaries), the latents then go through flow + HiFi-GAN in padded, length-sorted groups
+        (``vocode_features_batched``).  tokens[i] int64 [N_i], phones2[i] int64 [Nt_i], ge[i] [1,gin,1] -> AudioClips."""
+        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        zs, gs = [], []
+        for t, ph, g in zip(tokens, phones2, ge):
+            z_p, _mask, g2, _attn = vq.prior(t.view(1, 1, -1), ph.view(1, -1), g, noise_scale=noise_scale, speed=speed)
+            zs.append(z_p[0])
+            gs.append(g2[0])
+        return self.vocode_features_batched(zs, gs, sovits_model=sovits_model, max_frames=max_frames)
+
     def _clip(self, audio: np.ndarray, text: str = "") -> AudioClip:
         peak = float(np.abs(audio).max()) if audio.size else 0.0
         if peak > 1.0:
