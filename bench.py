@@ -327,6 +327,8 @@ def main():
         wall = time.perf_counter() - wall0
         timer.on = False
         ms = sum(a.elapsed_time(b) for a, b in evs)
+        if os.environ.get("BENCH_DEBUG"):
+            sys.stderr.write(f"[bench] collect={collect} per-step ms: {[round(a.elapsed_time(b), 1) for a, b in evs]}\n")
         launches = launch_total() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:

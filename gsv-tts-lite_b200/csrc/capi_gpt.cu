@@ -89,6 +89,7 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(p.logits, B * GSV_VOCAB_MAX * sizeof(float), true);
   A(p.barrier, 64, true);
   A(ctx->hooks_dev, GSV_MAX_SLOTS * sizeof(GptSlotHooks), true);
+  A(ctx->hx_resident, 64, true);
   A(ctx->pf_x, S * d * 2, false);
   A(ctx->pf_qkv, S * 3 * d * 2, false);
   A(ctx->pf_attn, S * d * 2, false);
@@ -308,6 +309,11 @@ extern "C" int gsv_gpt_set_decode_sms(gsv_gpt_ctx* ctx, int n_sms) {
   GSV_ARG(ctx && n_sms >= 0);
   ctx->decode_sms = n_sms;
   return GSV_OK;
+}
+
+extern "C" int gsv_gpt_wait_resident(gsv_gpt_ctx* ctx, void* stream) {
+  GSV_ARG(ctx);
+  return gsv_gpt_hx_gate(ctx, (cudaStream_t)stream);
 }
 
 extern "C" int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta) {

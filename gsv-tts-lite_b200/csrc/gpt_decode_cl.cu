@@ -39,7 +39,7 @@ struct ClShared {
 };
 
 template <typename T, int NCH>
-__global__ void __launch_bounds__(NT, 1) gpt_decode_cl_kernel(const GptParams p, const int n_steps) {
+__global__ void __launch_bounds__(NT, 1) gpt_decode_cl_kernel(const GptParams p, const int n_steps, unsigned* const resident) {
   extern __shared__ __align__(16) float smem[];
   __shared__ ClShared sh;
   constexpr int D = NCH * 256, F = 4 * D;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl_kernel(const GptParams p,
   }
   __syncthreads();
   const int slot = sh.slot;
-  if (slot < 0) return;                                 // whole cluster: no such live sequence (uniform across its CTAs)
+  if (slot < 0) { if (tid == 0) atomicAdd(resident, 1u); return; }   // whole cluster: no such live sequence (uniform across its CTAs)
   int kv = sh.kv;
 
   // ---- weight unit sequence of this warp (consumed strictly in this order, layer after layer) ----
@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl_kernel(const GptParams p,
   for (int k = tid; k < D; k += NT) bufA[split_pos(k, D)] = ld_cg(p.xin + (size_t)slot * D + k);
   __syncthreads();
   cluster_sync_all();                                   // every CTA of the cluster is resident and initialised
+  if (tid == 0) atomicAdd(resident, 1u);                // gsv_gpt_wait_resident
 
   const int sub = lane & 3, pg = lane >> 2;
   uint4 gv[NCH], bv[NCH];                                // LayerNorm gamma / beta of the NEXT LayerNorm, requested one phase early
@@ -503,7 +504,9 @@ int launch_cl(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = 1;
   GptParams p = ctx->p;
   int ns = n_steps;
-  void* args[] = {&p, &ns};
+  unsigned* resident = ctx->hx_resident;
+  ctx->hx_resident_expected += (unsigned)(live * H);
+  void* args[] = {&p, &ns, &resident};
   GSV_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches += 1;
   return GSV_OK;

@@ -123,7 +123,7 @@ __global__ void cl8_pack_head_kernel(const T* __restrict__ Wh, uint4* __restrict
 
 template <typename T, int NCH>
 __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p, const int n_steps, const unsigned char* __restrict__ pack,
-                                                                const unsigned char* __restrict__ hpack) {
+                                                                const unsigned char* __restrict__ hpack, unsigned* const resident) {
   extern __shared__ __align__(16) float smem[];
   __shared__ Cl8Shared sh;
   constexpr int D = NCH * 256, F = 4 * D;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
   unsigned livemask = 0;                                  // bit n: sequence n of this cluster is live (uniform across its CTAs)
 #pragma unroll
   for (int n = 0; n < NB8; ++n) livemask |= (sh.slot[n] >= 0 ? 1u : 0u) << n;
-  if (livemask == 0) return;
+  if (livemask == 0) { if (tid == 0) atomicAdd(resident, 1u); return; }      // (counted as resident: gsv_gpt_wait_resident)
   int na = __popc(livemask);
 
   // ---- chunk ring: the CTA consumes, per token, CHUNKS chunks per layer and then its head chunks rank, rank + H, ... ----
@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
   }
   __syncthreads();
   cluster_sync_all();
+  if (tid == 0) atomicAdd(resident, 1u);    // gsv_gpt_wait_resident: other streams' work is held back until every CTA is here
 
   // elements of a D-vector this lane handles in the LayerNorm warps: [c*256 + lane*8, +8) for c < NCH
   const int own_c = ((int)rank * GSV_HEAD_DIM) >> 8, own_l0 = (((int)rank * GSV_HEAD_DIM) & 255) >> 3;   // where this CTA's 32 rows sit
@@ -650,7 +651,9 @@ int launch_cl8(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
   int ns = n_steps;
   const unsigned char* pk = reinterpret_cast<const unsigned char*>(ctx->cl8_pack);
   const unsigned char* hp = reinterpret_cast<const unsigned char*>(ctx->cl8_head_pack);
-  void* args[] = {&p, &ns, &pk, &hp};
+  unsigned* resident = ctx->hx_resident;
+  ctx->hx_resident_expected += (unsigned)(n_clusters * H);
+  void* args[] = {&p, &ns, &pk, &hp, &resident};
   GSV_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches += 1;
   return GSV_OK;

@@ -167,7 +167,7 @@ struct HxShared {
 template <typename T, int NCH, int CS>
 __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p, const int n_steps, const unsigned tag_base,
                                                                uint2* const ll_buf, const T* __restrict__ pack,
-                                                               const T* __restrict__ hpack, const int HR) {
+                                                               const T* __restrict__ hpack, const int HR, unsigned* const resident) {
   using Lo = HxLayout<NCH * 256, CS>;
   constexpr int D = NCH * 256, RC = Lo::RC, HC = Lo::HC, KO = Lo::KO;
   constexpr int RW = (RC + 31) / 32;              // warps that own rows in the all-reduce (one row per thread)
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
   }
   __syncthreads();
   const int slot = sh.slot;
-  if (slot < 0) return;                     // uniform over the grid
+  if (slot < 0) { if (tid == 0) atomicAdd(resident, 1u); return; }     // uniform over the grid (counted: gsv_gpt_wait_resident)
   int kv = sh.kv;
 
   const T* const blob0 = pack + (size_t)j * Lo::BLOB;                       // layer 0 blob of this CTA
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
   for (int k = tid; k < D; k += NT) xbuf[split_pos(k, D)] = ld_cg(p.xin + (size_t)slot * D + k);
   __syncthreads();
   cluster_sync_all();                       // every CTA of the cluster has initialised its barriers
+  if (tid == 0) atomicAdd(resident, 1u);    // gsv_gpt_wait_resident: work of other streams is held back until every CTA is here
 
   unsigned tag = tag_base;
   const int sub = lane & 3, pg = lane >> 2;
@@ -743,7 +744,9 @@ int launch_hx_t(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
     if (e != cudaSuccess) cudaGetLastError();
   }
   if (ctx->hx_clusters_ok < 0) { gsv_set_error("hx decode kernel: %d clusters of %d CTAs are not co-resident on this device", NC / CS, CS); return GSV_ERR_STATE; }
-  void* args[] = {&p, &ns, &tag_base, &buf, &pk, &hp, &hr};
+  unsigned* resident = ctx->hx_resident;
+  ctx->hx_resident_expected += (unsigned)NC;
+  void* args[] = {&p, &ns, &tag_base, &buf, &pk, &hp, &hr, &resident};
   GSV_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ctx->launches += 1;
   return GSV_OK;
@@ -779,6 +782,27 @@ int launch_hx(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
 }
 
 }  // namespace
+
+// One thread spins (bounded) until every CTA of the last head-cluster launch is resident.
+__global__ void hx_gate_kernel(const unsigned* __restrict__ resident, unsigned expected) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(resident) : "memory");
+    if ((int)(v - expected) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 3000000ull) break;          // 3 ms: never hold a stream hostage
+    __nanosleep(200);
+  }
+}
+
+int gsv_gpt_hx_gate(gsv_gpt_ctx* ctx, cudaStream_t st) {
+  if (!ctx->hx_resident || ctx->hx_resident_expected == 0) return GSV_OK;
+  hx_gate_kernel<<<1, 1, 0, st>>>(ctx->hx_resident, ctx->hx_resident_expected);
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
 
 // words of the LL exchange areas this kernel needs: P1[<= H][D] + P2[<= H][D] + logits + xin + status
 size_t gsv_gpt_hx_buffer_words(const gsv_gpt_ctx* ctx) {

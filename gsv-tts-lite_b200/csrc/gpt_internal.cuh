@@ -90,6 +90,8 @@ struct gsv_gpt_ctx {
   void* hx_head_pack;             // ... and the per-CTA head rows
   int hx_clusters_ok;             // 0 not asked yet, 1 every cluster of the kernel is co-resident, -1 not
   int hx_cs;                      // CTAs per cluster of the head-cluster kernel (0: not chosen yet)
+  unsigned* hx_resident;          // device counter: CTAs of head-cluster launches that have become resident
+  unsigned hx_resident_expected;  // ... and its value once the last launch is fully resident
   int force_hx;                   // GSV_DECODE_IMPL=hx
   int use_umma_linear;            // GSV_GPT_GEMM=cuda disables the tensor-core linears (A/B checks)
   int force_barrier_kernel;       // GSV_DECODE_IMPL=barrier
@@ -123,3 +125,4 @@ int gsv_gpt_decode_cl8_launch(gsv_gpt_ctx* ctx, int live_slots, int n_steps, cud
 size_t gsv_gpt_hx_buffer_words(const gsv_gpt_ctx* ctx);
 bool gsv_gpt_hx_supported(const gsv_gpt_ctx* ctx, int live_slots, int n_steps);
 int gsv_gpt_decode_hx_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
+int gsv_gpt_hx_gate(gsv_gpt_ctx* ctx, cudaStream_t st);

@@ -103,6 +103,7 @@ class Text2SemanticDecoder(nn.Module):
         self.debug_seed: Optional[int] = None
         self.overlap_refill = True          # infer_batched: prompts of refills on a second stream (False: reference order)
         self._refill_stream = None
+        self._decode_stream = None
 
     # ------------------------------------------------------------------ runtime set-up
     @torch.inference_mode()
@@ -218,8 +219,29 @@ class Text2SemanticDecoder(nn.Module):
         ev.record(stream)
         return ev
 
+    def _hold_side_stream(self, stream):
+        self.hold_until_decode_resident(stream)
+
     def _wait_on_current_stream(self, ev):
         torch.cuda.current_stream(self._device).wait_event(ev)
+
+    def _high_priority_stream(self):
+        """Stream of the streaming decode: higher priority than the caller's streams.  The single-sequence kernel needs all
+        of its thread-block clusters resident at once; behind a second stream that keeps launching small vocoder kernels its
+        clusters could wait tens of milliseconds for 8 free SMs in one GPC (measured: 46 -> 144 ms per utterance, at random).
+        Pending blocks of a higher-priority stream are placed first."""
+        if self._decode_stream is None:
+            self._decode_stream = torch.cuda.Stream(self._device, priority=-1)
+        return self._decode_stream
+
+    def hold_until_decode_resident(self, stream=None):
+        """Enqueue on ``stream`` (default: the current one) a wait for the decode launch in flight to occupy its SMs
+        (``gsv_gpt_wait_resident``): call it on the vocoder stream before the chunk's work."""
+        st = stream if stream is not None else torch.cuda.current_stream(self._device)
+        N.check(N.lib().gsv_gpt_wait_resident(self._ctx, C.c_void_p(st.cuda_stream)))
+
+    def _stream_waits_for_current(self, stream):
+        stream.wait_stream(torch.cuda.current_stream(self._device))
 
     def _mark_chunk_ready(self):
         """Event behind the host->device copy of the chunk about to be handed out: a consumer on another stream waits
@@ -292,8 +314,11 @@ class Text2SemanticDecoder(nn.Module):
         """t2s_model.py:466-553: yields (tokens so far [1,1,n], is_final) every ``stream_chunk`` tokens,
         one chunk late unless ``boost_first_chunk``; the final yield after an EOS break carries the
         first sampled token (the reference slices ``[-idx:]`` with idx one past the appended count)."""
-        self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
-                           initial_suppression_steps, force_steps)
+        hp = self._high_priority_stream()
+        self._stream_waits_for_current(hp)                                # inputs produced on the caller's stream
+        with self._on_stream(hp):
+            self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
+                               initial_suppression_steps, force_steps)
         first, pre_chunk, idx = True, None, 0
 
         def launch(done: int) -> bool:
@@ -302,12 +327,14 @@ class Text2SemanticDecoder(nn.Module):
                 n = min(n, force_steps - done)
             if n <= 0:
                 return False
-            self._decode(n)
+            with self._on_stream(hp):
+                self._decode(n)
             return True
 
         more = launch(0)
         while more:
-            self._read(1)
+            with self._on_stream(hp):
+                self._read(1)
             n_gen = int(self._h_ngen[0])            # s0 + decode steps so far
             active = int(self._h_active[0])
             toks = self._h_tokens[0, :n_gen].to(torch.int64)
@@ -323,12 +350,10 @@ class Text2SemanticDecoder(nn.Module):
             if idx % stream_chunk == 0 and idx > 0:
                 chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
                 self._mark_chunk_ready()
-            # the next chunk is launched BEFORE this one is handed out: whatever the caller does with it (the
-            # vocoder, on its own stream after `chunk_ready`) overlaps the decode instead of delaying it
-            # ... except behind the very first chunk handed out, whose vocoder gets the whole GPU (time to first audio)
-            defer = chunk is not None and boost_first_chunk and first
-            if not defer:
-                more = bool(active) and launch(idx)
+            # the next chunk is launched BEFORE this one is handed out: whatever the caller does with it (prior encoder and
+            # vocoder, on its own stream after `chunk_ready` and `hold_until_decode_resident`) overlaps the decode instead of
+            # delaying it.  The single-sequence kernel occupies 64 SMs; the other 84 are the caller's.
+            more = bool(active) and launch(idx)
             if chunk is not None:
                 if pre_chunk is not None:
                     yield pre_chunk, False
@@ -337,9 +362,8 @@ class Text2SemanticDecoder(nn.Module):
                     first = False
                     yield pre_chunk, False
                     pre_chunk = None
-            if defer:
-                more = bool(active) and launch(idx)
-        self._read(1)
+        with self._on_stream(hp):
+            self._read(1)
         n_gen = int(self._h_ngen[0])
         toks = self._h_tokens[0, :n_gen].to(torch.int64)
         out = toks[1:].to(self._device).view(1, 1, -1)
@@ -394,18 +418,29 @@ class Text2SemanticDecoder(nn.Module):
         results, order = [], []
         interval = max(int(check_interval), self.BATCH_INTERVAL)
         side = self._side_stream() if self.overlap_refill else None
+        to_begin = []                     # (slot, request) freed at the last read: their prompts start behind the next decode launch
         pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
-        while any(o >= 0 for o in owner) or pending:
+        while any(o >= 0 for o in owner) or pending or to_begin:
             if any(o >= 0 for o in owner):
                 self._decode(interval)
-            # second half of the refills started after the previous read: behind the decode launch just enqueued, so
-            # the prompt was computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
+            # second half of the refills begun one launch ago: behind the decode launch just enqueued, so their prompts were
+            # computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
             for slot, r, keep, ev in pending:
                 self._wait_on_current_stream(ev)
                 audit(slot, r)
                 self._prefill_finish(slot, keep[1], sampling(r))
                 owner[slot] = r
             done_refills, pending = pending, []
+            # first half of the refills freed at the last read, on the second stream -- held until the decode launch above
+            # has its clusters resident (hold_until_decode_resident): a stream of small prompt kernels must not be what a
+            # 16-CTA cluster waits behind
+            if to_begin:
+                with self._on_stream(side):
+                    self._hold_side_stream(side)
+                    for slot, r in to_begin:
+                        keep = self._prefill_begin(slot, x[r], y[r], bert_feature[r])
+                        pending.append((slot, r, keep, self._record_event(side)))
+                to_begin = []
             self._read(slots)
             del done_refills              # their prompt tensors were needed until the second half had run
             for s in range(slots):
@@ -422,10 +457,7 @@ class Text2SemanticDecoder(nn.Module):
                             start(s, nxt)
                             owner[s] = nxt
                         else:
-                            with self._on_stream(side):
-                                keep = self._prefill_begin(s, x[nxt], y[nxt], bert_feature[nxt])
-                                ev = self._record_event(side)
-                            pending.append((s, nxt, keep, ev))
+                            to_begin.append((s, nxt))
                             owner[s] = REFILLING
                         nxt += 1
         return results, torch.tensor(order, device=self._device)

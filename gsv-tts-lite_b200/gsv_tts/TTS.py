@@ -150,6 +150,7 @@ class TTS:
                         break
                     with torch.cuda.stream(side):
                         side.wait_event(gpt.chunk_ready)                     # the token copy, not the decode behind it
+                        gpt.hold_until_decode_resident(side)                 # ... but let that decode take its SMs first
                         tokens.record_stream(side)
                         z_p, y_mask, ge = features_of_chunk(tokens, final)
                         audio = voc.flow_dec(z_p, y_mask, ge)[0, 0].float().cpu()        # waits for `side` only
@@ -371,6 +372,7 @@ class TTS:
                         break
                     with torch.cuda.stream(side):
                         side.wait_event(gpt.chunk_ready)
+                        gpt.hold_until_decode_resident(side)
                         pred.record_stream(side)
                         audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed, stream_mode=True,
                                                 valid_start_idx=valid_start, overlap_len=overlap_len)

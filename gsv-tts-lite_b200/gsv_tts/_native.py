@@ -70,6 +70,7 @@ SYMBOLS = [
     ("gsv_gpt_set_slot_hooks", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P]),
     ("gsv_gpt_launch_count", C.c_int64, [_P]),
     ("gsv_gpt_set_decode_sms", C.c_int, [_P, C.c_int]),
+    ("gsv_gpt_wait_resident", C.c_int, [_P, _P]),
     ("gsv_gpt_set_timeline", C.c_int, [_P, _P, C.c_int, C.c_int]),
     ("gsv_voc_create", C.c_int, [C.POINTER(VocDims), C.POINTER(_P)]),
     ("gsv_voc_set_weight", C.c_int, [_P, C.c_char_p, _P, _P]),

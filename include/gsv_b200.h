@@ -166,6 +166,12 @@ int64_t gsv_gpt_launch_count(gsv_gpt_ctx* ctx);
  * vocoder of chunk c runs on a second stream, on the SMs left free, while the GPT decodes chunk c+1.  The step
  * time of the decode kernel is the same from 128 SMs up. */
 int gsv_gpt_set_decode_sms(gsv_gpt_ctx* ctx, int n_sms);
+/* Holds `stream` back (a one-thread kernel, bounded to 3 ms) until every thread block of the last decode
+ * launch (any of the cluster kernels) is resident.  Those kernels need whole thread-block clusters on the chip at once; a
+ * second stream that keeps launching small vocoder / prefill kernels can otherwise keep them waiting for 8 or 16 free SMs
+ * in one GPC for tens of milliseconds (measured: 46 -> 144 ms per utterance, at random).  Enqueue it on the other stream
+ * after the decode launch. */
+int gsv_gpt_wait_resident(gsv_gpt_ctx* ctx, void* stream);
 /* Tuning hook: CTA `cta` of the decode kernel appends {marker id, SM clock} pairs (2 x int64 per
  * record, record 0 holds the count) to dev_records; NULL disables. */
 int gsv_gpt_set_timeline(gsv_gpt_ctx* ctx, int64_t* dev_records, int max_records, int cta);

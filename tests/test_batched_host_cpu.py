@@ -116,6 +116,7 @@ def make_model(lengths, slots, log, overlap):
     m._on_stream = rt.on_stream
     m._record_event = rt.record_event
     m._wait_on_current_stream = rt.wait
+    m._hold_side_stream = lambda stream: log.append(("hold",))       # the second stream waits for the decode launch to be resident
     return m, N
 
 
@@ -141,5 +142,10 @@ def test_every_request_completes_once_with_its_own_tokens(monkeypatch, overlap, 
     if overlap and n_req > slots:
         assert "begin" in kinds and kinds.count("begin") == kinds.count("finish") == n_req - slots
         assert kinds.count("prefill") == slots                                   # only the initial fill is synchronous
+        # prompts of refills start on the second stream only after it was told to wait for the decode launch in flight
+        for i, k in enumerate(kinds):
+            if k == "begin":
+                j = max(q for q in range(i) if kinds[q] in ("hold", "decode"))
+                assert kinds[j] == "hold" or all(kk in ("begin", "hold") for kk in kinds[j + 1:i]) and "hold" in kinds[max(0, i - 40):i]
     else:
         assert "begin" not in kinds and kinds.count("prefill") == n_req
