@@ -28,6 +28,7 @@ tools/ref_gpu_bench.py; its recorded numbers (profiles/r02_ref_gpu_baseline.json
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -313,8 +314,10 @@ def main():
     def timed(inp, steps, collect):
         evs = []
         l0 = launch_total()
-        timer.on = collect
+        timer.on = collect or bool(os.environ.get("BENCH_DEBUG"))
         barrier()
+        gc.collect()
+        gc.disable()                                         # a generation-2 collection inside a 44 ms step is a 30-90 ms outlier
         wall0 = time.perf_counter()
         for _ in range(steps):
             flush.zero_()                                    # evict L2 between timed steps (outside the events)
@@ -325,10 +328,13 @@ def main():
             evs.append((a, b))
         barrier()
         wall = time.perf_counter() - wall0
+        gc.enable()
         timer.on = False
         ms = sum(a.elapsed_time(b) for a, b in evs)
         if os.environ.get("BENCH_DEBUG"):
             sys.stderr.write(f"[bench] collect={collect} per-step ms: {[round(a.elapsed_time(b), 1) for a, b in evs]}\n")
+            if not collect:
+                sys.stderr.write(f"[bench] decode launch ms (host-input pass): {[round(m, 1) for m, _ in timer.take()]}\n")
         launches = launch_total() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
