@@ -89,41 +89,51 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (via NVML)."""
+class ClockSampler:
+    """SM clock / throttle reasons sampled through NVML DURING the timed region: one sample per utterance, taken by the
+    consumer of the stream right after it received the middle clip -- the decode of the next chunk is running on the GPU at
+    that moment and the host has nothing to launch.  (A sampling THREAD was measured to cost 60-100 ms outliers per 44 ms step:
+    an NVML query that lands while the host is issuing the ~200 launches of a prefill stalls them.)"""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-
-    def run(self):
+        self.samples, self.reasons, self.max_mhz, self.on, self.cost_ms = [], set(), None, False, []
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.names = {
                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
-            while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.05)
         except Exception as e:            # pragma: no cover
+            self.nv = None
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def sample(self):
+        if not self.on or self.nv is None:
+            return
+        t0 = time.perf_counter()
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, nm in self.names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception as e:            # pragma: no cover
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+        self.cost_ms.append(round((time.perf_counter() - t0) * 1e3, 2))
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -286,16 +296,26 @@ def main():
     gpt.debug_seed = 99
     stream = torch.cuda.current_stream(dev)
 
+    DEBUG_CLIPS = None
+    sampler = ClockSampler(local)
+
     def utterance(inp, first_clip_time=None):
         """One streaming utterance through the public API: 8 chunks of 25 tokens, one AudioClip each."""
         n_clips = 0
         samples = 0
+        t_prev = time.perf_counter()
         for clip in tts.infer_phones_stream(phones1, inp["bert1"], inp["y"], phones2, inp["bert2"], inp["ge"], stream_chunk=CHUNK,
                                             overlap_len=5, force_steps=N_TOK):
             if n_clips == 0 and first_clip_time is not None:
                 first_clip_time.append(time.perf_counter())
             n_clips += 1
             samples += clip.audio_data.shape[0]
+            if n_clips == 4:
+                sampler.sample()
+            if DEBUG_CLIPS is not None:
+                t_now = time.perf_counter()
+                DEBUG_CLIPS.append(round((t_now - t_prev) * 1e3, 1))
+                t_prev = t_now
         assert n_clips == N_TOK // CHUNK, n_clips
         return N_TOK, samples
 
@@ -312,7 +332,9 @@ def main():
         torch.cuda.synchronize(dev)
 
     def timed(inp, steps, collect):
+        nonlocal DEBUG_CLIPS
         evs = []
+        DEBUG_CLIPS = [] if os.environ.get("BENCH_DEBUG") else None
         l0 = launch_total()
         timer.on = collect or bool(os.environ.get("BENCH_DEBUG"))
         barrier()
@@ -333,8 +355,10 @@ def main():
         ms = sum(a.elapsed_time(b) for a, b in evs)
         if os.environ.get("BENCH_DEBUG"):
             sys.stderr.write(f"[bench] collect={collect} per-step ms: {[round(a.elapsed_time(b), 1) for a, b in evs]}\n")
+            sys.stderr.write(f"[bench] host ms between clips: {DEBUG_CLIPS}\n")
             if not collect:
                 sys.stderr.write(f"[bench] decode launch ms (host-input pass): {[round(m, 1) for m, _ in timer.take()]}\n")
+        DEBUG_CLIPS = None
         launches = launch_total() - l0
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
@@ -343,13 +367,13 @@ def main():
 
     for _ in range(args.warmup):
         utterance(dev_in)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.on = not os.environ.get("BENCH_NO_SAMPLER")
     ms_total, wall, launches = timed(dev_in, args.steps, True)
     decode_launches = timer.take()
     ms_e2e, wall_e2e, _ = timed(host_in, args.steps, False)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.on = False
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write(f"[bench] NVML sample cost ms: {sampler.cost_ms}\n")
     # TTFT (BASELINE config 2): host call -> first AudioClip in host memory, median of 5
     ttfts = []
     for _ in range(5):

@@ -245,6 +245,240 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   }
 }
 
+// ---- weight-stationary, persistent variant (stride-1 convolutions on large grids) -------------------------------------
+// What the launch lists of a B = 16..64 call showed (profiles/r02_voc_shares_*.txt): the one-tile-per-CTA kernel above spends
+// 12-24 us per 128 x 128 tile of which 1-3 us are MMAs -- fill latency, the epilogue and the drain run one after the other,
+// and every tile re-streams the whole weight tensor of its N tile from L2 (229 KB for a 128-channel, 7-tap layer against
+// 34 KB of activations).  Here a CTA
+//   * keeps ALL taps of its N tile resident in shared memory (loaded once, before the predecessor kernel has finished),
+//   * walks over M tiles (blockIdx.x, += gridDim.x); only the activation boxes travel per tile, through a ring that holds
+//     about two tiles,
+//   * owns NACC accumulators in tensor memory: while the epilogue warps of set s drain accumulator s (tile i), the MMA
+//     thread fills accumulator s+1 (tile i+1),
+//   * has 4 NACC epilogue warps; a thread owns one time step of the tile and walks over its channels in groups of 16, with
+//     the fp32 residual / MRF-accumulator values of the NEXT group already requested (the first group's before the
+//     accumulator is even complete).
+// The N tile is chosen by the host so that weights + ring fit (conv_ws_plan); CTAs with the same blockIdx.x and different
+// N tiles read the same activation boxes at about the same time (L2 hits).
+constexpr int kMaxAcc = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T>
+struct ParamsWS {
+  CUtensorMap tm_a;      // activations (C, Tin, B), box (BK, a_rows, 1)
+  CUtensorMap tm_w;      // weights (Cin, Cout, KW), box (BK, BN, 1)
+  int kchunks;           // ceil(Cin / BK)
+  int in_off;            // first input channel
+  int KW, dil, pad;
+  int mt;                // M tiles per batch element
+  int n_mtiles;          // B * mt
+  int a_rows;            // rows of the activation box = 128 + halo
+  int a_stage_bytes;     // a_rows * BK * 2 rounded up to 1024
+  int sa;                // activation ring depth
+  ConvArgs<T> ep;
+};
+
+struct EpiPre {
+  float4 r[4], a[4];
+};
+template <typename T>
+__device__ __forceinline__ void epi_prefetch16(const ConvArgs<T>& a, size_t o, int n8, EpiPre& p) {
+  if (a.res32) {
+    const float4* q = reinterpret_cast<const float4*>(a.res32 + o);
+    p.r[0] = q[0]; p.r[1] = q[1];
+    if (n8 > 1) { p.r[2] = q[2]; p.r[3] = q[3]; }
+  }
+  if (a.acc32 && !a.acc_init) {
+    const float4* q = reinterpret_cast<const float4*>(a.acc32 + o);
+    p.a[0] = q[0]; p.a[1] = q[1];
+    if (n8 > 1) { p.a[2] = q[2]; p.a[3] = q[3]; }
+  }
+}
+// conv_epilogue_row8 for 8 channels whose residual / accumulator inputs were prefetched (half = 0 / 1: which 8 of the 16)
+template <typename T>
+__device__ __forceinline__ void epi_apply8(const ConvArgs<T>& a, int b, int t, int co, size_t o, const float* acc, const EpiPre& p,
+                                           int half) {
+  float v[8], tmp[8];
+  unpack8<T>(*reinterpret_cast<const uint4*>(a.bias + co), tmp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = acc[j] + tmp[j];
+  if (a.add) {
+    const float* ap = a.add + ((size_t)b * a.add_tg + (a.add_tg > 1 ? t : 0)) * a.add_ld + co;
+    const float4 x = *reinterpret_cast<const float4*>(ap), y = *reinterpret_cast<const float4*>(ap + 4);
+    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+  }
+  if (a.res32) {
+    const float4 x = p.r[2 * half], y = p.r[2 * half + 1];
+    const float rr[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = rr[j] + a.res_sign * v[j];
+  }
+  if (a.acc32) {
+    if (!a.acc_init) {
+      const float4 x = p.a[2 * half], y = p.a[2 * half + 1];
+      v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+    }
+    *reinterpret_cast<float4*>(a.acc32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(a.acc32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= a.acc_scale;
+  }
+  if (a.mask) {
+    const float m = Elem<T>::to_f(a.mask[(size_t)b * a.Tout + t]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= m;
+  }
+  if (a.out32) {
+    *reinterpret_cast<float4*>(a.out32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(a.out32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (a.outT) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
+    *reinterpret_cast<uint4*>(a.outT + o) = pack8<T>(v);
+  }
+}
+
+template <int BN, int NACC> struct WsTmem {
+  static constexpr int need = BN * NACC;
+  static constexpr int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+};
+
+template <typename T, int BN, int BK, int NACC>
+__global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const __grid_constant__ ParamsWS<T> P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int ROW_BYTES = BK * 2, W_BYTES = BN * ROW_BYTES;
+  constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
+  constexpr int TMEM_COLS = WsTmem<BN, NACC>::cols;
+  static_assert(BN * NACC <= 512 && NACC <= kMaxAcc, "accumulators fit tensor memory");
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc_full[kMaxAcc], acc_empty[kMaxAcc], w_full;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t base_u = smem_u32(smem_raw);
+  const uint32_t tiles_w = base_u + ((1024u - (base_u & 1023u)) & 1023u);
+  const int n_w = P.kchunks * P.KW;
+  const uint32_t tiles_a = tiles_w + (uint32_t)(n_w * W_STAGE);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int SA = P.sa;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    mbar_init(&w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: the N tile's weights once, then the activation boxes of every M tile of this CTA ----
+      mbar_expect_tx(&w_full, (unsigned)(n_w * W_BYTES));
+      for (int i = 0; i < n_w; ++i) {
+        const int c = i / P.KW, j = i - c * P.KW;
+        tma_load_3d(tiles_w + (uint32_t)(i * W_STAGE), &P.tm_w, &w_full, c * BK, n0, j);
+      }
+      pdl_wait();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.n_mtiles; tile += gridDim.x) {
+        const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
+        for (int c = 0; c < P.kchunks; ++c, ++it) {
+          const int s = it % SA;
+          if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
+          mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
+          tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, q0 - P.pad, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      mbar_wait(&w_full, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < P.n_mtiles; tile += gridDim.x, ++lt) {
+        const int buf = lt % NACC;
+        if (lt >= NACC) mbar_wait(&acc_empty[buf], ((lt / NACC) - 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_d + (uint32_t)(buf * BN);
+        for (int c = 0; c < P.kchunks; ++c, ++it) {
+          const int s = it % SA;
+          mbar_wait(&a_full[s], (it / SA) & 1);
+          tc_fence_after();
+          const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
+          for (int j = 0; j < P.KW; ++j) {
+            const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
+            const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)((c * P.KW + j) * W_STAGE));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&a_empty[s]);          // frees the activation slot when these MMAs have read it
+        }
+        tc_commit(&acc_full[buf]);         // accumulator of this tile complete
+      }
+      pdl_launch_dependents();
+    }
+  } else {
+    // ---- epilogue: set = which accumulator; warp owns TMEM lanes [32*(warp%4), +32) = rows q0 + 32*(warp%4) + lane ----
+    const int set = (warp - 2) >> 2, quarter = warp & 3;
+    pdl_wait();                            // the epilogue reads residual / accumulator streams of earlier kernels
+    int use = 0;
+    for (int lt = set;; lt += NACC, ++use) {
+      const int tile = blockIdx.x + lt * gridDim.x;
+      if (tile >= P.n_mtiles) break;
+      const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
+      const int t = q0 + quarter * 32 + lane;
+      const bool row_ok = t < P.ep.Tout;
+      const size_t orow = ((size_t)b * P.ep.Tout + t) * P.ep.o_ld + P.ep.o_off + n0;
+      EpiPre pre[2];
+      const int n8_0 = (n0 + 8 < P.ep.Cout) ? 2 : 1;
+      if (row_ok) epi_prefetch16<T>(P.ep, orow, n8_0, pre[0]);
+      mbar_wait(&acc_full[set], use & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * BN);
+#pragma unroll
+      for (int g = 0; g < BN / 16; ++g) {
+        const int c0 = g * 16;
+        if (g + 1 < BN / 16 && row_ok && n0 + c0 + 16 < P.ep.Cout)
+          epi_prefetch16<T>(P.ep, orow + c0 + 16, (n0 + c0 + 24 < P.ep.Cout) ? 2 : 1, pre[(g + 1) & 1]);
+        uint32_t v[16];
+        tc_ld16(tbase + (uint32_t)c0, v);
+        tc_ld_wait();
+        if (row_ok && n0 + c0 < P.ep.Cout) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          epi_apply8<T>(P.ep, b, t, n0 + c0, orow + c0, f, pre[g & 1], 0);
+          if (n0 + c0 + 8 < P.ep.Cout) epi_apply8<T>(P.ep, b, t, n0 + c0 + 8, orow + c0 + 8, f + 8, pre[g & 1], 1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -410,7 +410,7 @@ struct Weight {
 // one cached pair of tensor maps per convolution call site of a flow_dec pass (re-encoded when the signature changes)
 struct MapCacheEntry {
   const void *in, *w;
-  int in_ld, Tin, B, Cin, Cout, KW, bn, a_rows;
+  int in_ld, Tin, B, Cin, Cout, KW, bn, bk, a_rows;
   long long w_tap;
   alignas(64) CUtensorMap tm_a;
   alignas(64) CUtensorMap tm_w;
@@ -429,6 +429,7 @@ struct gsv_voc_ctx {
   std::vector<MapCacheEntry> map_cache;   // indexed by call site order within one flow_dec pass
   size_t op_index;
   int use_umma;                           // GSV_VOC_IMPL=cuda disables the tensor-core path (A/B checks)
+  int use_ws;                             // GSV_VOC_WS=0 disables the weight-stationary persistent kernel (A/B checks)
   cudaStream_t side[2];                   // the three ResBlocks of an MRF stage run as three concurrent chains
   cudaEvent_t ev_fork, ev_join[2];
   int mrf_streams;                        // GSV_VOC_MRF=serial: one chain after the other on the caller's stream
@@ -489,7 +490,7 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
   if (op >= map_cache.size()) map_cache.resize(op + 1);
   MapCacheEntry& e = map_cache[op];
   if (e.in != a.in || e.w != a.w || e.in_ld != a.in_ld || e.Tin != a.Tin || e.B != a.B || e.Cin != a.Cin || e.Cout != a.Cout ||
-      e.KW != a.KW || e.bn != bn || e.w_tap != a.w_tap || e.a_rows != a_rows) {
+      e.KW != a.KW || e.bn != bn || e.bk != bk || e.w_tap != a.w_tap || e.a_rows != a_rows) {
     const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
     int rc = umma::make_map(&e.tm_a, bf16, a.in, (uint64_t)a.in_ld, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.in_ld * 2,
                             (uint64_t)a.Tin * a.in_ld * 2, (uint32_t)bk, (uint32_t)a_rows);
@@ -498,7 +499,7 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
                         (uint64_t)a.w_tap * 2, (uint32_t)bk, (uint32_t)bn);
     if (rc) return rc;
     e.in = a.in; e.w = a.w; e.in_ld = a.in_ld; e.Tin = a.Tin; e.B = a.B; e.Cin = a.Cin; e.Cout = a.Cout; e.KW = a.KW;
-    e.bn = bn; e.w_tap = a.w_tap; e.a_rows = a_rows;
+    e.bn = bn; e.bk = bk; e.w_tap = a.w_tap; e.a_rows = a_rows;
   }
   umma::Params<T> P;
   P.tm_a = e.tm_a; P.tm_w = e.tm_w;
@@ -545,6 +546,128 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
   return GSV_OK;
 }
 
+// ---- weight-stationary persistent variant (conv_umma.cuh, second kernel) ---------------------------------------------
+struct WsPlan {
+  int bn, bk, nacc, sa, n_nt, mt;
+  size_t smem;
+};
+// stride-1 convolutions whose N tile's weights (all taps) fit in shared memory beside an activation ring of about two tiles
+template <typename T>
+bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl) {
+  if (a.stride != 1 || a.in_rev || a.o_rev || a.Cin < 16 || a.Cin % 8 || a.in_ld % 8 || a.Cout % 8 || a.KW > 16 ||
+      (a.KW - 1) * a.dil > 120 || (reinterpret_cast<uintptr_t>(a.in) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15) || (a.w_tap % 8))
+    return false;
+  const int mt = (a.Tout + umma::BM - 1) / umma::BM;
+  const long long n_mtiles = (long long)a.B * mt;
+  if (need_large && n_mtiles < 2LL * num_sms) return false;
+  int bk;
+  if (a.Cin == 16) bk = 16;
+  else if (a.Cin <= 32) bk = 32;
+  else if (a.Cin < 64) bk = 64;
+  else if (a.Cin % 64 == 0 || a.Cin % 64 > 32) bk = 64;
+  else bk = 32;
+  const int kchunks = (a.Cin + bk - 1) / bk;
+  const int a_rows = umma::BM + (a.KW - 1) * a.dil;
+  const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
+  static const int cand[6] = {128, 96, 64, 48, 32, 16};
+  for (int ci = 0; ci < 6; ++ci) {
+    const int bn = cand[ci];
+    if (bk == 32 && (bn == 128 || bn == 64)) continue;          // instantiated pairs only
+    if (bk == 16 && bn != 16) continue;
+    if (!(a.Cout % bn == 0 || (bn > a.Cout && bn - a.Cout <= 8))) continue;
+    const int n_nt = (a.Cout + bn - 1) / bn;
+    if (n_nt > num_sms) continue;
+    const int w_stage = (bn * bk * 2 + 1023) & ~1023;
+    const size_t w_bytes = (size_t)kchunks * a.KW * w_stage;
+    int sa = 2 * kchunks;
+    sa = sa < 3 ? 3 : sa;
+    sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
+    while (sa > kchunks + 1 && sa > 2 && w_bytes + (size_t)sa * a_stage > (size_t)umma::kSmemBudget) --sa;
+    if (w_bytes + (size_t)sa * a_stage > (size_t)umma::kSmemBudget) continue;
+    pl.bn = bn; pl.bk = bk; pl.nacc = bn >= 64 ? 2 : 3; pl.sa = sa; pl.n_nt = n_nt; pl.mt = mt;
+    pl.smem = w_bytes + (size_t)sa * a_stage + 1024;
+    return true;
+  }
+  return false;
+}
+
+template <typename T, int BN, int BK, int NACC>
+int launch_ws_inst(const umma::ParamsWS<T>& P, dim3 grid, size_t smem, cudaStream_t st) {
+  static unsigned long long attr_set = 0ull;        // one bit per device
+  int dev = 0;
+  GSV_CUDA(cudaGetDevice(&dev));
+  if (!((attr_set >> (dev & 63)) & 1ull)) {
+    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_ws_kernel<T, BN, BK, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  umma::kSmemBudget + 2048));
+    attr_set |= 1ull << (dev & 63);
+  }
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("GSV_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(64 + 128 * NACC); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::conv_umma_ws_kernel<T, BN, BK, NACC>, P));
+  return GSV_OK;
+}
+
+template <typename T>
+int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const ConvArgs<T>& a, const WsPlan& pl, size_t op, cudaStream_t st) {
+  const int bn = pl.bn, bk = pl.bk;
+  const int a_rows = umma::BM + (a.KW - 1) * a.dil;
+  if (op >= map_cache.size()) map_cache.resize(op + 1);
+  MapCacheEntry& e = map_cache[op];
+  if (e.in != a.in || e.w != a.w || e.in_ld != a.in_ld || e.Tin != a.Tin || e.B != a.B || e.Cin != a.Cin || e.Cout != a.Cout ||
+      e.KW != a.KW || e.bn != bn || e.bk != bk || e.w_tap != a.w_tap || e.a_rows != a_rows) {
+    const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+    int rc = umma::make_map(&e.tm_a, bf16, a.in, (uint64_t)a.in_ld, (uint64_t)a.Tin, (uint64_t)a.B, (uint64_t)a.in_ld * 2,
+                            (uint64_t)a.Tin * a.in_ld * 2, (uint32_t)bk, (uint32_t)a_rows);
+    if (rc) return rc;
+    rc = umma::make_map(&e.tm_w, bf16, a.w, (uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)a.KW, (uint64_t)a.Cin * 2,
+                        (uint64_t)a.w_tap * 2, (uint32_t)bk, (uint32_t)bn);
+    if (rc) return rc;
+    e.in = a.in; e.w = a.w; e.in_ld = a.in_ld; e.Tin = a.Tin; e.B = a.B; e.Cin = a.Cin; e.Cout = a.Cout; e.KW = a.KW;
+    e.bn = bn; e.bk = bk; e.w_tap = a.w_tap; e.a_rows = a_rows;
+  }
+  umma::ParamsWS<T> P;
+  P.tm_a = e.tm_a; P.tm_w = e.tm_w;
+  P.kchunks = (a.Cin + bk - 1) / bk;
+  P.in_off = a.in_off;
+  P.KW = a.KW; P.dil = a.dil; P.pad = (a.KW - 1) * a.dil / 2;
+  P.mt = pl.mt; P.n_mtiles = a.B * pl.mt;
+  P.a_rows = a_rows;
+  P.a_stage_bytes = (a_rows * bk * 2 + 1023) & ~1023;
+  P.sa = pl.sa;
+  P.ep = a;
+  int gx = num_sms / pl.n_nt;
+  if (gx > P.n_mtiles) gx = P.n_mtiles;
+  const dim3 grid(gx, pl.n_nt, 1);
+  int rc = GSV_ERR_ARG;
+#define GSV_WS(BN_, BK_, NA_) rc = launch_ws_inst<T, BN_, BK_, NA_>(P, grid, pl.smem, st)
+  if (bk == 64) {
+    if (bn == 128) GSV_WS(128, 64, 2);
+    else if (bn == 96) GSV_WS(96, 64, 2);
+    else if (bn == 64) GSV_WS(64, 64, 2);
+    else if (bn == 48) GSV_WS(48, 64, 3);
+    else if (bn == 32) GSV_WS(32, 64, 3);
+    else GSV_WS(16, 64, 3);
+  } else if (bk == 32) {
+    if (bn == 96) GSV_WS(96, 32, 2);
+    else if (bn == 48) GSV_WS(48, 32, 3);
+    else if (bn == 32) GSV_WS(32, 32, 3);
+    else GSV_WS(16, 32, 3);
+  } else {
+    GSV_WS(16, 16, 3);
+  }
+#undef GSV_WS
+  if (rc) return rc;
+  GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
 template <typename T>
 int launch_conv(gsv_voc_ctx* ctx, const ConvArgs<T>& a, cudaStream_t st) {
   if (a.Cin % 8 != 0 || a.in_off % 8 != 0 || a.in_ld % 8 != 0) {
@@ -553,7 +676,14 @@ int launch_conv(gsv_voc_ctx* ctx, const ConvArgs<T>& a, cudaStream_t st) {
   }
   {
     const size_t op = ctx->op_index++;
-    if (ctx->use_umma && umma_eligible<T>(a)) {
+    const bool old_ok = ctx->use_umma && umma_eligible<T>(a);
+    WsPlan pl;
+    // large grids, and shapes the one-tile kernel has no instance for (48 / 24 / 96 channels of V2ProPlus)
+    if (ctx->use_umma && ctx->use_ws && conv_ws_plan<T>(a, ctx->num_sms, old_ok && ctx->use_ws != 2, pl)) {
+      ctx->launches += 1;
+      return launch_conv_ws<T>(ctx->map_cache, ctx->num_sms, a, pl, op, st);
+    }
+    if (old_ok) {
       ctx->launches += 1;
       return launch_conv_umma<T>(ctx->map_cache, ctx->num_sms, a, op, st);
     }
@@ -876,6 +1006,8 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
   {
     const char* e = getenv("GSV_VOC_IMPL");
     ctx->use_umma = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
+    const char* ews = getenv("GSV_VOC_WS");
+    ctx->use_ws = (ews && ews[0] == '0') ? 0 : ((ews && ews[0] == '2') ? 2 : 1);   // 2: also on small grids (tests)
   }
   GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
   {

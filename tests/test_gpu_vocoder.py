@@ -98,3 +98,50 @@ def test_edge_lengths_match_oracle(dev, T):
     err = float((audio - want).abs().max())
     print("T", T, "max|audio - oracle|", err)
     assert err < TOL_AUDIO[dtype]
+
+
+@pytest.mark.parametrize("name,key", [("tiny", "tiny"), ("v2pro", "v2Pro"), ("v2proplus", "v2ProPlus")])
+def test_weight_stationary_kernel_forced_matches_golden(dev, name, key, monkeypatch):
+    """GSV_VOC_WS=2 sends every stride-1 convolution the persistent weight-stationary kernel can take through it, small
+    grids included (by default it serves grids of >= 2 tiles per SM and the channel counts the one-tile kernel has no
+    instance for): same goldens, same bounds."""
+    from tests import gpu_harness as H
+    monkeypatch.setenv("GSV_VOC_WS", "2")
+    dtype = torch.float16
+    e = H.vocoder_error(name, key, dtype, dev)
+    print(name, {k: v for k, v in e.items()})
+    tol_golden = TOL_AUDIO[dtype]
+    if e["ref16_vs_golden"] is not None:
+        tol_golden = max(tol_golden, e["ref16_vs_golden"])
+    assert e["z_vs_golden"] < TOL_Z[dtype]
+    assert e["audio_vs_golden"] < tol_golden
+    assert e["audio_vs_oracle"] < TOL_AUDIO[dtype]
+
+
+@pytest.mark.parametrize("key", ["v2Pro", "v2ProPlus"])
+def test_weight_stationary_kernel_on_large_grids(dev, key, monkeypatch):
+    """B=3, T=150 (ragged last tiles, grids above two tiles per SM from the third upsampling stage on): the persistent kernel
+    issues the same MMAs in the same order as the one-tile kernel, so V2Pro is bit-equal to GSV_VOC_WS=0; V2ProPlus'
+    48 / 24-channel stages run on CUDA cores there, so the two differ by rounding only."""
+    from tests import gpu_harness as H
+    g = torch.Generator().manual_seed(11)
+    B, T = 3, 150
+    model = syn.SOVITS_MODEL[key]
+    z_p = torch.randn(B, 192, T, generator=g).to(dev)
+    mask = torch.ones(B, 1, T, device=dev)
+    mask[1, :, 100:] = 0
+    ge = torch.randn(B, model["gin_channels"], 1, generator=g).to(dev)
+    out = {}
+    for ws in ("0", "1"):
+        monkeypatch.setenv("GSV_VOC_WS", ws)
+        fd, _, _ = H.build_vocoder(key, torch.float16, dev)
+        out[ws] = fd.flow_dec(z_p, mask, ge).float().clone()
+        again = fd.flow_dec(z_p, mask, ge).float()
+        assert torch.equal(out[ws], again)
+    err = float((out["0"] - out["1"]).abs().max())
+    print(key, "max|ws - one-tile|", err)
+    assert torch.isfinite(out["1"]).all()
+    if key == "v2Pro":
+        assert err == 0.0
+    else:
+        assert err < 1e-3

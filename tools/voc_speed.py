@@ -7,7 +7,7 @@ dev = torch.device("cuda:0")
 key = sys.argv[1] if len(sys.argv) > 1 else "v2Pro"
 fd, sd, model = H.build_vocoder(key, torch.bfloat16, dev)
 flop_frame = (813.1e6 if key != "v2ProPlus" else 1828.4e6) + 14.2e6
-for B, T in [(1, 50), (1, 55), (1, 500), (8, 100), (16, 500)]:
+for B, T in [(1, 50), (1, 55), (1, 500), (8, 100), (16, 500), (64, 500)]:
     z = torch.randn(B, 192, T, device=dev, dtype=torch.bfloat16)
     mk = torch.ones(B, 1, T, device=dev, dtype=torch.bfloat16)
     ge = torch.randn(B, model["gin_channels"], 1, device=dev, dtype=torch.bfloat16)
