@@ -30,7 +30,7 @@
 namespace umma {
 
 constexpr int BM = 128;          // time steps per tile
-constexpr int kMaxSA = 12;       // activation ring depth (upper bound)
+constexpr int kMaxSA = 16;       // activation ring depth (upper bound)
 constexpr int kMaxSW = 12;       // weight ring depth (upper bound)
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 //     thread fills accumulator s+1 (tile i+1),
 //   * has 4 NACC epilogue warps; a thread owns one time step of the tile and walks over its channels in groups of 16, with
 //     the fp32 residual / MRF-accumulator values of the NEXT group already requested (the first group's before the
-//     accumulator is even complete).
+//     accumulator is even complete) and the rows of the next unit requested into L2.
 // The N tile is chosen by the host so that weights + ring fit (conv_ws_plan); CTAs with the same blockIdx.x and different
 // N tiles read the same activation boxes at about the same time (L2 hits).
 constexpr int kMaxAcc = 4;
@@ -342,18 +342,23 @@ __device__ __forceinline__ void epi_apply8(const ConvArgs<T>& a, int b, int t, i
   }
 }
 
-template <int BN, int NACC> struct WsTmem {
-  static constexpr int need = BN * NACC;
-  static constexpr int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+template <int COLS> struct WsTmem {
+  static constexpr int cols = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
 };
 
-template <typename T, int BN, int BK, int NACC>
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// MS consecutive M tiles form one unit: one accumulator hand-over (two mbarrier round trips) per unit, so that narrow tiles
+// (16 / 32 channels: a tile is 2-4 K outputs) do not pay the hand-over latency per tile.
+template <typename T, int BN, int BK, int NACC, int MS>
 __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const __grid_constant__ ParamsWS<T> P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROW_BYTES = BK * 2, W_BYTES = BN * ROW_BYTES;
   constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
-  constexpr int TMEM_COLS = WsTmem<BN, NACC>::cols;
-  static_assert(BN * NACC <= 512 && NACC <= kMaxAcc, "accumulators fit tensor memory");
+  constexpr int ACC_COLS = MS * BN;
+  constexpr int G = BN / 16;
+  constexpr int TMEM_COLS = WsTmem<ACC_COLS * NACC>::cols;
+  static_assert(ACC_COLS * NACC <= 512 && NACC <= kMaxAcc, "accumulators fit tensor memory");
   __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc_full[kMaxAcc], acc_empty[kMaxAcc], w_full;
   __shared__ uint32_t tmem_base_s;
   const uint32_t base_u = smem_u32(smem_raw);
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
   const int SA = P.sa;
+  const int n_units = (P.n_mtiles + MS - 1) / MS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -392,13 +398,17 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
       }
       pdl_wait();
       int it = 0;
-      for (int tile = blockIdx.x; tile < P.n_mtiles; tile += gridDim.x) {
-        const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
-        for (int c = 0; c < P.kchunks; ++c, ++it) {
-          const int s = it % SA;
-          if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
-          mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
-          tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, q0 - P.pad, b);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        for (int sub = 0; sub < MS; ++sub) {
+          const int tile = unit * MS + sub;
+          if (tile >= P.n_mtiles) break;
+          const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
+          for (int c = 0; c < P.kchunks; ++c, ++it) {
+            const int s = it % SA;
+            if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
+            mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
+            tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, q0 - P.pad, b);
+          }
         }
       }
     }
@@ -409,61 +419,92 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
                                  ((uint32_t)(BM >> 4) << 24);
       mbar_wait(&w_full, 0);
       int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < P.n_mtiles; tile += gridDim.x, ++lt) {
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++lt) {
         const int buf = lt % NACC;
         if (lt >= NACC) mbar_wait(&acc_empty[buf], ((lt / NACC) - 1) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_d + (uint32_t)(buf * BN);
-        for (int c = 0; c < P.kchunks; ++c, ++it) {
-          const int s = it % SA;
-          mbar_wait(&a_full[s], (it / SA) & 1);
-          tc_fence_after();
-          const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
-          for (int j = 0; j < P.KW; ++j) {
-            const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
-            const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)((c * P.KW + j) * W_STAGE));
+        for (int sub = 0; sub < MS; ++sub) {
+          if (unit * MS + sub >= P.n_mtiles) break;
+          const uint32_t d = tmem_d + (uint32_t)(buf * ACC_COLS + sub * BN);
+          for (int c = 0; c < P.kchunks; ++c, ++it) {
+            const int s = it % SA;
+            mbar_wait(&a_full[s], (it / SA) & 1);
+            tc_fence_after();
+            const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
+            for (int j = 0; j < P.KW; ++j) {
+              const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
+              const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)((c * P.KW + j) * W_STAGE));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)
+                tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&a_empty[s]);          // frees the activation slot when these MMAs have read it
           }
-          tc_commit(&a_empty[s]);          // frees the activation slot when these MMAs have read it
         }
-        tc_commit(&acc_full[buf]);         // accumulator of this tile complete
+        tc_commit(&acc_full[buf]);           // accumulators of this unit complete
       }
       pdl_launch_dependents();
     }
   } else {
     // ---- epilogue: set = which accumulator; warp owns TMEM lanes [32*(warp%4), +32) = rows q0 + 32*(warp%4) + lane ----
     const int set = (warp - 2) >> 2, quarter = warp & 3;
-    pdl_wait();                            // the epilogue reads residual / accumulator streams of earlier kernels
+    const ConvArgs<T>& ep = P.ep;
+    const int n_valid = ep.Cout - n0 < BN ? ep.Cout - n0 : BN;     // channels of this N tile that exist
+    pdl_wait();                              // the epilogue reads residual / accumulator streams of earlier kernels
+    // residual / MRF-accumulator rows of a unit, requested into L2 one unit ahead of their use
+    auto l2_rows = [&](int unit) {
+      if (!ep.res32 && !(ep.acc32 && !ep.acc_init)) return;
+      for (int sub = 0; sub < MS; ++sub) {
+        const int tile = unit * MS + sub;
+        if (tile >= P.n_mtiles) break;
+        const int b = tile / P.mt, t = (tile - b * P.mt) * BM + quarter * 32 + lane;
+        if (t >= ep.Tout) continue;
+        const size_t o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off + n0;
+        for (int c = 0; c < n_valid; c += 32) {
+          if (ep.res32) l2_prefetch(ep.res32 + o + c);
+          if (ep.acc32 && !ep.acc_init) l2_prefetch(ep.acc32 + o + c);
+        }
+      }
+    };
+    if (blockIdx.x + set * (int)gridDim.x < n_units) l2_rows(blockIdx.x + set * gridDim.x);
     int use = 0;
     for (int lt = set;; lt += NACC, ++use) {
-      const int tile = blockIdx.x + lt * gridDim.x;
-      if (tile >= P.n_mtiles) break;
-      const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
-      const int t = q0 + quarter * 32 + lane;
-      const bool row_ok = t < P.ep.Tout;
-      const size_t orow = ((size_t)b * P.ep.Tout + t) * P.ep.o_ld + P.ep.o_off + n0;
+      const int unit = blockIdx.x + lt * gridDim.x;
+      if (unit >= n_units) break;
+      if (unit + NACC * (int)gridDim.x < n_units) l2_rows(unit + NACC * gridDim.x);
+      int tt[MS], bb[MS];
+      size_t orow[MS];
+      bool ok[MS];
+#pragma unroll
+      for (int sub = 0; sub < MS; ++sub) {
+        const int tile = unit * MS + sub;
+        const int b = tile / P.mt;
+        bb[sub] = b;
+        tt[sub] = (tile - b * P.mt) * BM + quarter * 32 + lane;
+        ok[sub] = tile < P.n_mtiles && tt[sub] < ep.Tout;
+        orow[sub] = ((size_t)b * ep.Tout + tt[sub]) * ep.o_ld + ep.o_off + n0;
+      }
       EpiPre pre[2];
-      const int n8_0 = (n0 + 8 < P.ep.Cout) ? 2 : 1;
-      if (row_ok) epi_prefetch16<T>(P.ep, orow, n8_0, pre[0]);
+      if (ok[0]) epi_prefetch16<T>(ep, orow[0], n_valid > 8 ? 2 : 1, pre[0]);
       mbar_wait(&acc_full[set], use & 1);
       tc_fence_after();
-      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * BN);
+      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * ACC_COLS);
 #pragma unroll
-      for (int g = 0; g < BN / 16; ++g) {
-        const int c0 = g * 16;
-        if (g + 1 < BN / 16 && row_ok && n0 + c0 + 16 < P.ep.Cout)
-          epi_prefetch16<T>(P.ep, orow + c0 + 16, (n0 + c0 + 24 < P.ep.Cout) ? 2 : 1, pre[(g + 1) & 1]);
+      for (int u = 0; u < MS * G; ++u) {
+        const int sub = u / G, c0 = (u % G) * 16;
+        if (u + 1 < MS * G) {
+          const int sub1 = (u + 1) / G, c1 = ((u + 1) % G) * 16;
+          if (ok[sub1] && c1 < n_valid) epi_prefetch16<T>(ep, orow[sub1] + c1, c1 + 8 < n_valid ? 2 : 1, pre[(u + 1) & 1]);
+        }
         uint32_t v[16];
-        tc_ld16(tbase + (uint32_t)c0, v);
+        tc_ld16(tbase + (uint32_t)(sub * BN + c0), v);
         tc_ld_wait();
-        if (row_ok && n0 + c0 < P.ep.Cout) {
+        if (ok[sub] && c0 < n_valid) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          epi_apply8<T>(P.ep, b, t, n0 + c0, orow + c0, f, pre[g & 1], 0);
-          if (n0 + c0 + 8 < P.ep.Cout) epi_apply8<T>(P.ep, b, t, n0 + c0 + 8, orow + c0 + 8, f + 8, pre[g & 1], 1);
+          epi_apply8<T>(ep, bb[sub], tt[sub], n0 + c0, orow[sub] + c0, f, pre[u & 1], 0);
+          if (c0 + 8 < n_valid) epi_apply8<T>(ep, bb[sub], tt[sub], n0 + c0 + 8, orow[sub] + c0 + 8, f + 8, pre[u & 1], 1);
         }
       }
       tc_fence_before();

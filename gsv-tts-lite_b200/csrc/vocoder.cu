@@ -548,10 +548,13 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
 
 // ---- weight-stationary persistent variant (conv_umma.cuh, second kernel) ---------------------------------------------
 struct WsPlan {
-  int bn, bk, nacc, sa, n_nt, mt;
+  int bn, bk, nacc, ms, sa, n_nt, mt;
   size_t smem;
 };
-// stride-1 convolutions whose N tile's weights (all taps) fit in shared memory beside an activation ring of about two tiles
+constexpr size_t kWsBudget = 222 * 1024;      // dynamic shared memory of the persistent kernel (227 KB per CTA minus barriers)
+inline int ws_ms(int bn) { return bn <= 32 ? 4 : (bn <= 96 ? 2 : 1); }      // M tiles per accumulator hand-over
+inline int ws_nacc(int bn) { return bn >= 64 ? 2 : 3; }
+// stride-1 convolutions whose N tile's weights (all taps) fit in shared memory beside an activation ring of about two units
 template <typename T>
 bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl) {
   if (a.stride != 1 || a.in_rev || a.o_rev || a.Cin < 16 || a.Cin % 8 || a.in_ld % 8 || a.Cout % 8 || a.KW > 16 ||
@@ -560,45 +563,50 @@ bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl
   const int mt = (a.Tout + umma::BM - 1) / umma::BM;
   const long long n_mtiles = (long long)a.B * mt;
   if (need_large && n_mtiles < 2LL * num_sms) return false;
-  int bk;
-  if (a.Cin == 16) bk = 16;
-  else if (a.Cin <= 32) bk = 32;
-  else if (a.Cin < 64) bk = 64;
-  else if (a.Cin % 64 == 0 || a.Cin % 64 > 32) bk = 64;
-  else bk = 32;
-  const int kchunks = (a.Cin + bk - 1) / bk;
+  int bk0;
+  if (a.Cin == 16) bk0 = 16;
+  else if (a.Cin <= 32) bk0 = 32;
+  else if (a.Cin < 64) bk0 = 64;
+  else if (a.Cin % 64 == 0 || a.Cin % 64 > 32) bk0 = 64;
+  else bk0 = 32;
   const int a_rows = umma::BM + (a.KW - 1) * a.dil;
-  const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
   static const int cand[6] = {128, 96, 64, 48, 32, 16};
   for (int ci = 0; ci < 6; ++ci) {
     const int bn = cand[ci];
-    if (bk == 32 && (bn == 128 || bn == 64)) continue;          // instantiated pairs only
-    if (bk == 16 && bn != 16) continue;
     if (!(a.Cout % bn == 0 || (bn > a.Cout && bn - a.Cout <= 8))) continue;
+    if (bn < 64 && bn < a.Cout) break;      // narrow N tiles re-read the activations too often: the one-tile kernel does better
     const int n_nt = (a.Cout + bn - 1) / bn;
-    if (n_nt > num_sms) continue;
-    const int w_stage = (bn * bk * 2 + 1023) & ~1023;
-    const size_t w_bytes = (size_t)kchunks * a.KW * w_stage;
-    int sa = 2 * kchunks;
-    sa = sa < 3 ? 3 : sa;
-    sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
-    while (sa > kchunks + 1 && sa > 2 && w_bytes + (size_t)sa * a_stage > (size_t)umma::kSmemBudget) --sa;
-    if (w_bytes + (size_t)sa * a_stage > (size_t)umma::kSmemBudget) continue;
-    pl.bn = bn; pl.bk = bk; pl.nacc = bn >= 64 ? 2 : 3; pl.sa = sa; pl.n_nt = n_nt; pl.mt = mt;
-    pl.smem = w_bytes + (size_t)sa * a_stage + 1024;
-    return true;
+    const int ms = ws_ms(bn);
+    // 64 channels per chunk first; 32 per chunk halves the ring's bytes per stage when the weights leave little room
+    for (int bk = bk0; bk >= 16; bk >>= 1) {
+      if (bk < bk0 && (bk0 != 64 || bk != 32 || a.Cin % 32)) break;
+      if (bk == 16 && bn != 16) break;
+      const int kchunks = (a.Cin + bk - 1) / bk;
+      const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
+      const int w_stage = (bn * bk * 2 + 1023) & ~1023;
+      const size_t w_bytes = (size_t)kchunks * a.KW * w_stage;
+      int sa = 2 * ms * kchunks;
+      sa = sa < 3 ? 3 : sa;
+      sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
+      const int sa_min = kchunks + 1 > 2 ? kchunks + 1 : 2;
+      while (sa > sa_min && w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) --sa;
+      if (w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) continue;
+      pl.bn = bn; pl.bk = bk; pl.nacc = ws_nacc(bn); pl.ms = ms; pl.sa = sa; pl.n_nt = n_nt; pl.mt = mt;
+      pl.smem = w_bytes + (size_t)sa * a_stage + 1024;
+      return true;
+    }
   }
   return false;
 }
 
-template <typename T, int BN, int BK, int NACC>
+template <typename T, int BN, int BK, int NACC, int MS>
 int launch_ws_inst(const umma::ParamsWS<T>& P, dim3 grid, size_t smem, cudaStream_t st) {
   static unsigned long long attr_set = 0ull;        // one bit per device
   int dev = 0;
   GSV_CUDA(cudaGetDevice(&dev));
   if (!((attr_set >> (dev & 63)) & 1ull)) {
-    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_ws_kernel<T, BN, BK, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  umma::kSmemBudget + 2048));
+    GSV_CUDA(cudaFuncSetAttribute(umma::conv_umma_ws_kernel<T, BN, BK, NACC, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kWsBudget));
     attr_set |= 1ull << (dev & 63);
   }
   static int use_pdl = -1;
@@ -610,7 +618,7 @@ int launch_ws_inst(const umma::ParamsWS<T>& P, dim3 grid, size_t smem, cudaStrea
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::conv_umma_ws_kernel<T, BN, BK, NACC>, P));
+  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::conv_umma_ws_kernel<T, BN, BK, NACC, MS>, P));
   return GSV_OK;
 }
 
@@ -642,25 +650,28 @@ int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const Con
   P.a_stage_bytes = (a_rows * bk * 2 + 1023) & ~1023;
   P.sa = pl.sa;
   P.ep = a;
+  const int n_units = (P.n_mtiles + pl.ms - 1) / pl.ms;
   int gx = num_sms / pl.n_nt;
-  if (gx > P.n_mtiles) gx = P.n_mtiles;
+  if (gx > n_units) gx = n_units;
   const dim3 grid(gx, pl.n_nt, 1);
   int rc = GSV_ERR_ARG;
-#define GSV_WS(BN_, BK_, NA_) rc = launch_ws_inst<T, BN_, BK_, NA_>(P, grid, pl.smem, st)
+#define GSV_WS(BN_, BK_) rc = launch_ws_inst<T, BN_, BK_, (BN_ >= 64 ? 2 : 3), (BN_ <= 32 ? 4 : (BN_ <= 96 ? 2 : 1))>(P, grid, pl.smem, st)
   if (bk == 64) {
-    if (bn == 128) GSV_WS(128, 64, 2);
-    else if (bn == 96) GSV_WS(96, 64, 2);
-    else if (bn == 64) GSV_WS(64, 64, 2);
-    else if (bn == 48) GSV_WS(48, 64, 3);
-    else if (bn == 32) GSV_WS(32, 64, 3);
-    else GSV_WS(16, 64, 3);
+    if (bn == 128) GSV_WS(128, 64);
+    else if (bn == 96) GSV_WS(96, 64);
+    else if (bn == 64) GSV_WS(64, 64);
+    else if (bn == 48) GSV_WS(48, 64);
+    else if (bn == 32) GSV_WS(32, 64);
+    else GSV_WS(16, 64);
   } else if (bk == 32) {
-    if (bn == 96) GSV_WS(96, 32, 2);
-    else if (bn == 48) GSV_WS(48, 32, 3);
-    else if (bn == 32) GSV_WS(32, 32, 3);
-    else GSV_WS(16, 32, 3);
+    if (bn == 128) GSV_WS(128, 32);
+    else if (bn == 96) GSV_WS(96, 32);
+    else if (bn == 64) GSV_WS(64, 32);
+    else if (bn == 48) GSV_WS(48, 32);
+    else if (bn == 32) GSV_WS(32, 32);
+    else GSV_WS(16, 32);
   } else {
-    GSV_WS(16, 16, 3);
+    GSV_WS(16, 16);
   }
 #undef GSV_WS
   if (rc) return rc;

@@ -15,9 +15,10 @@ tot = 0.0
 for d in rec.values():
     us = d.get("gpu__time_duration.sum", 0.0) / 1e3
     key = (d["name"][:70], int(d.get("launch__grid_size", 0)))
-    a = agg.setdefault(key, [0.0, 0])
+    a = agg.setdefault(key, [0.0, 0, 0.0])
     a[0] += us; a[1] += 1
+    a[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     tot += us
 print(f"total {tot/1e3:.3f} ms over {len(rec)} launches")
-for (name, grid), (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-    print(f"{100*us/tot:6.2f}% {us/1e3:9.3f} ms  n={c:4d}  avg {us/c:8.1f} us  grid {grid:7d}  {name}")
+for (name, grid), (us, c, by) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    print(f"{100*us/tot:6.2f}% {us/1e3:9.3f} ms  n={c:4d}  avg {us/c:8.1f} us  dram {by/max(us,1e-9)/1e3:7.0f} GB/s  grid {grid:7d}  {name}")
