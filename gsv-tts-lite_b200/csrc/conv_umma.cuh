@@ -281,64 +281,102 @@ struct ParamsWS {
   ConvArgs<T> ep;
 };
 
+// 256-bit global accesses (sm_100): a thread's 8 fp32 / 16 sixteen-bit channels of a row are one full 32-byte sector
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void stg256u(void* p, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg256u(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
+// residual / MRF-accumulator inputs of 16 channels of one row, requested ahead of their use
 struct EpiPre {
-  float4 r[4], a[4];
+  F8 r[2], a[2];
 };
 template <typename T>
 __device__ __forceinline__ void epi_prefetch16(const ConvArgs<T>& a, size_t o, int n8, EpiPre& p) {
   if (a.res32) {
-    const float4* q = reinterpret_cast<const float4*>(a.res32 + o);
-    p.r[0] = q[0]; p.r[1] = q[1];
-    if (n8 > 1) { p.r[2] = q[2]; p.r[3] = q[3]; }
+    p.r[0] = ldg256(a.res32 + o);
+    if (n8 > 1) p.r[1] = ldg256(a.res32 + o + 8);
   }
   if (a.acc32 && !a.acc_init) {
-    const float4* q = reinterpret_cast<const float4*>(a.acc32 + o);
-    p.a[0] = q[0]; p.a[1] = q[1];
-    if (n8 > 1) { p.a[2] = q[2]; p.a[3] = q[3]; }
+    p.a[0] = ldg256(a.acc32 + o);
+    if (n8 > 1) p.a[1] = ldg256(a.acc32 + o + 8);
   }
 }
-// conv_epilogue_row8 for 8 channels whose residual / accumulator inputs were prefetched (half = 0 / 1: which 8 of the 16)
+// conv_epilogue_row8 for 8 * n8 channels (n8 = 1, 2) whose residual / accumulator inputs were prefetched
 template <typename T>
-__device__ __forceinline__ void epi_apply8(const ConvArgs<T>& a, int b, int t, int co, size_t o, const float* acc, const EpiPre& p,
-                                           int half) {
-  float v[8], tmp[8];
-  unpack8<T>(*reinterpret_cast<const uint4*>(a.bias + co), tmp);
+__device__ __forceinline__ void epi_apply16(const ConvArgs<T>& a, int b, int t, int co, size_t o, const uint32_t* acc, const EpiPre& p, int n8) {
+  float v[16];
+  {
+    uint32_t bw[8];
+    if (n8 > 1) ldg256u(a.bias + co, bw);
+    else { const uint4 u = *reinterpret_cast<const uint4*>(a.bias + co); bw[0] = u.x; bw[1] = u.y; bw[2] = u.z; bw[3] = u.w; bw[4] = bw[5] = bw[6] = bw[7] = 0u; }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = acc[j] + tmp[j];
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = Elem<T>::to_f2(bw[j]);
+      v[2 * j] = __uint_as_float(acc[2 * j]) + f.x;
+      v[2 * j + 1] = __uint_as_float(acc[2 * j + 1]) + f.y;
+    }
+  }
   if (a.add) {
     const float* ap = a.add + ((size_t)b * a.add_tg + (a.add_tg > 1 ? t : 0)) * a.add_ld + co;
-    const float4 x = *reinterpret_cast<const float4*>(ap), y = *reinterpret_cast<const float4*>(ap + 4);
-    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < n8) {
+        const F8 x = ldg256(ap + 8 * h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[8 * h + j] += x.v[j];
+      }
+    }
   }
   if (a.res32) {
-    const float4 x = p.r[2 * half], y = p.r[2 * half + 1];
-    const float rr[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = rr[j] + a.res_sign * v[j];
+    for (int j = 0; j < 16; ++j) v[j] = p.r[j >> 3].v[j & 7] + a.res_sign * v[j];
   }
   if (a.acc32) {
     if (!a.acc_init) {
-      const float4 x = p.a[2 * half], y = p.a[2 * half + 1];
-      v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
-    }
-    *reinterpret_cast<float4*>(a.acc32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(a.acc32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= a.acc_scale;
+      for (int j = 0; j < 16; ++j) v[j] += p.a[j >> 3].v[j & 7];
+    }
+    stg256(a.acc32 + o, v);
+    if (n8 > 1) stg256(a.acc32 + o + 8, v + 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= a.acc_scale;
   }
   if (a.mask) {
     const float m = Elem<T>::to_f(a.mask[(size_t)b * a.Tout + t]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= m;
+    for (int j = 0; j < 16; ++j) v[j] *= m;
   }
   if (a.out32) {
-    *reinterpret_cast<float4*>(a.out32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(a.out32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    stg256(a.out32 + o, v);
+    if (n8 > 1) stg256(a.out32 + o + 8, v + 8);
   }
   if (a.outT) {
+    uint32_t u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
-    *reinterpret_cast<uint4*>(a.outT + o) = pack8<T>(v);
+    for (int j = 0; j < 8; ++j) u[j] = Elem<T>::from_f2(act_apply(v[2 * j], a.act), act_apply(v[2 * j + 1], a.act));
+    if (n8 > 1 && (a.o_ld & 15) == 0) stg256u(a.outT + o, u);           // 16-bit rows of 24 channels are only 16-byte aligned
+    else {
+      *reinterpret_cast<uint4*>(a.outT + o) = make_uint4(u[0], u[1], u[2], u[3]);
+      if (n8 > 1) *reinterpret_cast<uint4*>(a.outT + o + 8) = make_uint4(u[4], u[5], u[6], u[7]);
+    }
   }
 }
 
@@ -357,6 +395,8 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
   constexpr int ACC_COLS = MS * BN;
   constexpr int G = BN / 16;
+  constexpr int SU = (G % 2) ? 2 : 1;
+  static_assert(MS % SU == 0, "sub-tiles pair up when a tile has an odd number of 16-channel groups");
   constexpr int TMEM_COLS = WsTmem<ACC_COLS * NACC>::cols;
   static_assert(ACC_COLS * NACC <= 512 && NACC <= kMaxAcc, "accumulators fit tensor memory");
   __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc_full[kMaxAcc], acc_empty[kMaxAcc], w_full;
@@ -472,39 +512,43 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
       const int unit = blockIdx.x + lt * gridDim.x;
       if (unit >= n_units) break;
       if (unit + NACC * (int)gridDim.x < n_units) l2_rows(unit + NACC * gridDim.x);
-      int tt[MS], bb[MS];
-      size_t orow[MS];
-      bool ok[MS];
-#pragma unroll
-      for (int sub = 0; sub < MS; ++sub) {
+      // row of this thread in sub-tile `sub` of the unit: batch element, time step, validity, output offset
+      auto row_of = [&](int sub, int& b, int& t, size_t& o) -> bool {
         const int tile = unit * MS + sub;
-        const int b = tile / P.mt;
-        bb[sub] = b;
-        tt[sub] = (tile - b * P.mt) * BM + quarter * 32 + lane;
-        ok[sub] = tile < P.n_mtiles && tt[sub] < ep.Tout;
-        orow[sub] = ((size_t)b * ep.Tout + tt[sub]) * ep.o_ld + ep.o_off + n0;
-      }
+        b = tile / P.mt;
+        t = (tile - b * P.mt) * BM + quarter * 32 + lane;
+        o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off + n0;
+        return tile < P.n_mtiles && t < ep.Tout;
+      };
       EpiPre pre[2];
-      if (ok[0]) epi_prefetch16<T>(ep, orow[0], n_valid > 8 ? 2 : 1, pre[0]);
+      {
+        int b, t;
+        size_t o;
+        if (row_of(0, b, t, o)) epi_prefetch16<T>(ep, o, n_valid > 8 ? 2 : 1, pre[0]);
+      }
       mbar_wait(&acc_full[set], use & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * ACC_COLS);
+      // SU sub-tiles per iteration = an even number of 16-channel groups, so the two prefetch buffers alternate at compile time
+      // while the code stays small (the fully unrolled unit did not fit the instruction cache: "no instruction" stalls)
+#pragma unroll 1
+      for (int s0 = 0; s0 < MS; s0 += SU) {
 #pragma unroll
-      for (int u = 0; u < MS * G; ++u) {
-        const int sub = u / G, c0 = (u % G) * 16;
-        if (u + 1 < MS * G) {
-          const int sub1 = (u + 1) / G, c1 = ((u + 1) % G) * 16;
-          if (ok[sub1] && c1 < n_valid) epi_prefetch16<T>(ep, orow[sub1] + c1, c1 + 8 < n_valid ? 2 : 1, pre[(u + 1) & 1]);
-        }
-        uint32_t v[16];
-        tc_ld16(tbase + (uint32_t)(sub * BN + c0), v);
-        tc_ld_wait();
-        if (ok[sub] && c0 < n_valid) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          epi_apply8<T>(ep, bb[sub], tt[sub], n0 + c0, orow[sub] + c0, f, pre[u & 1], 0);
-          if (c0 + 8 < n_valid) epi_apply8<T>(ep, bb[sub], tt[sub], n0 + c0 + 8, orow[sub] + c0 + 8, f + 8, pre[u & 1], 1);
+        for (int u = 0; u < SU * G; ++u) {
+          const int sub = s0 + u / G, c0 = (u % G) * 16;
+          {
+            const int sub1 = (u + 1 < SU * G) ? s0 + (u + 1) / G : s0 + SU, c1 = (u + 1 < SU * G) ? ((u + 1) % G) * 16 : 0;
+            int b1, t1;
+            size_t o1;
+            if (sub1 < MS && c1 < n_valid && row_of(sub1, b1, t1, o1))
+              epi_prefetch16<T>(ep, o1 + c1, c1 + 8 < n_valid ? 2 : 1, pre[(u + 1) & 1]);
+          }
+          uint32_t v[16];
+          tc_ld16(tbase + (uint32_t)(sub * BN + c0), v);
+          tc_ld_wait();
+          int b, t;
+          size_t o;
+          if (sub < MS && c0 < n_valid && row_of(sub, b, t, o)) epi_apply16<T>(ep, b, t, n0 + c0, o + c0, v, pre[u & 1], c0 + 8 < n_valid ? 2 : 1);
         }
       }
       tc_fence_before();
