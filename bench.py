@@ -298,6 +298,23 @@ def main():
 
     DEBUG_CLIPS = None
     sampler = ClockSampler(local)
+    if os.environ.get("BENCH_DEBUG"):
+        # host time spent inside the calls of a streaming utterance (where do first-clip outliers come from?)
+        HOST_TRACE = []
+
+        def traced(obj, name):
+            fn = getattr(obj, name)
+
+            def wrapper(*a, **k):
+                t0 = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    HOST_TRACE.append((name, round((time.perf_counter() - t0) * 1e3, 2), round(t0 * 1e3, 1)))
+            setattr(obj, name, wrapper)
+        for nm in ("_single_setup", "_decode", "_read"):
+            traced(gpt, nm)
+        traced(voc, "decode")
 
     def utterance(inp, first_clip_time=None):
         """One streaming utterance through the public API: 8 chunks of 25 tokens, one AudioClip each."""
@@ -335,6 +352,8 @@ def main():
         nonlocal DEBUG_CLIPS
         evs = []
         DEBUG_CLIPS = [] if os.environ.get("BENCH_DEBUG") else None
+        if DEBUG_CLIPS is not None:
+            del HOST_TRACE[:]
         l0 = launch_total()
         timer.on = collect or bool(os.environ.get("BENCH_DEBUG"))
         barrier()
@@ -356,6 +375,13 @@ def main():
         if os.environ.get("BENCH_DEBUG"):
             sys.stderr.write(f"[bench] collect={collect} per-step ms: {[round(a.elapsed_time(b), 1) for a, b in evs]}\n")
             sys.stderr.write(f"[bench] host ms between clips: {DEBUG_CLIPS}\n")
+            slow = [i for i, (a, b) in enumerate(evs) if a.elapsed_time(b) > 50]
+            per = len(HOST_TRACE) // max(1, steps)
+            for i in slow[:3]:
+                sys.stderr.write(f"[bench] slow step {i}: {HOST_TRACE[i * per:(i + 1) * per][:12]}\n")
+            if slow:
+                sys.stderr.write(f"[bench] normal step: {HOST_TRACE[0:per][:12] if 0 not in slow else HOST_TRACE[per:2 * per][:12]}\n")
+            del HOST_TRACE[:]
             if not collect:
                 sys.stderr.write(f"[bench] decode launch ms (host-input pass): {[round(m, 1) for m, _ in timer.take()]}\n")
         DEBUG_CLIPS = None
@@ -365,8 +391,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), wall, launches
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup):                             # both input kinds: host inputs allocate their own device copies
         utterance(dev_in)
+        utterance(host_in)
     sampler.on = not os.environ.get("BENCH_NO_SAMPLER")
     ms_total, wall, launches = timed(dev_in, args.steps, True)
     decode_launches = timer.take()

@@ -90,11 +90,14 @@ extern "C" int gsv_gpt_create(const gsv_gpt_dims* dims, const gsv_gpt_weights* w
   A(p.barrier, 64, true);
   A(ctx->hooks_dev, GSV_MAX_SLOTS * sizeof(GptSlotHooks), true);
   A(ctx->hx_resident, 64, true);
-  A(ctx->pf_x, S * d * 2, false);
-  A(ctx->pf_qkv, S * 3 * d * 2, false);
-  A(ctx->pf_attn, S * d * 2, false);
-  A(ctx->pf_h, S * F * 2, false);
-  A(ctx->pf_tmp, S * d * 2, false);
+  // prefill scratch: rows of several prompts stacked (gsv_gpt_prefill_begin_many), at least one full-length prompt
+  ctx->pf_rows = (int)(S > 4096 ? S : 4096);
+  const size_t R = (size_t)ctx->pf_rows;
+  A(ctx->pf_x, R * d * 2, false);
+  A(ctx->pf_qkv, R * 3 * d * 2, false);
+  A(ctx->pf_attn, R * d * 2, false);
+  A(ctx->pf_h, R * F * 2, false);
+  A(ctx->pf_tmp, R * d * 2, false);
   A(ctx->pf_last, B * d * 2, true);
   A(ctx->ll_buf, gsv_gpt_ll_buffer_bytes(ctx), true);
   A(ctx->dx, B * d * 2, true);
@@ -167,6 +170,31 @@ extern "C" int gsv_gpt_prefill_begin(gsv_gpt_ctx* ctx, int slot, const int64_t* 
   // caller's contract: the slot's previous sequence has finished (its `active` flag read back as 0) or was released
   return gsv_gpt_prefill_body(ctx, slot, dev_x, nx, dev_y, ny, dev_bert, (cudaStream_t)stream);
 }
+
+extern "C" int gsv_gpt_prefill_begin_many(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_t* const* dev_x, const int* nx,
+                                          const int64_t* const* dev_y, const int* ny, const void* const* dev_bert, void* stream) {
+  GSV_ARG(ctx && slots && dev_x && nx && dev_y && ny && dev_bert);
+  GSV_ARG(n_prompts >= 1 && n_prompts <= GSV_MAX_SLOTS);
+  long long rows = 0;
+  unsigned long long seen = 0ull;
+  for (int i = 0; i < n_prompts; ++i) {
+    GSV_ARG(dev_x[i] && dev_y[i] && dev_bert[i]);
+    GSV_ARG(slots[i] >= 0 && slots[i] < ctx->p.slots);
+    GSV_ARG(nx[i] >= 1 && ny[i] >= 1);
+    if ((seen >> slots[i]) & 1ull) { gsv_set_error("gsv_gpt_prefill_begin_many: slot %d named twice", slots[i]); return GSV_ERR_ARG; }
+    seen |= 1ull << slots[i];
+    const int rc = check_prompt(ctx, nx[i], ny[i]);
+    if (rc) return rc;
+    rows += nx[i] + ny[i];
+  }
+  if (rows > ctx->pf_rows) {
+    gsv_set_error("gsv_gpt_prefill_begin_many: %lld prompt rows exceed the pass capacity %d (gsv_gpt_prefill_capacity)", rows, ctx->pf_rows);
+    return GSV_ERR_ARG;
+  }
+  return gsv_gpt_prefill_body_many(ctx, n_prompts, slots, dev_x, nx, dev_y, ny, dev_bert, (cudaStream_t)stream);
+}
+
+extern "C" int gsv_gpt_prefill_capacity(gsv_gpt_ctx* ctx) { return ctx ? ctx->pf_rows : 0; }
 
 extern "C" int gsv_gpt_prefill_finish(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_y, int ny, const gsv_gpt_sampling* samp,
                                       void* stream) {

@@ -65,7 +65,8 @@ struct gsv_gpt_ctx {
   size_t decode_smem;
   long long launches;
   // prefill scratch (T unless noted), sized for max_seq rows
-  void *pf_x, *pf_qkv, *pf_attn, *pf_h, *pf_tmp;
+  void *pf_x, *pf_qkv, *pf_attn, *pf_h, *pf_tmp;   // [pf_rows][...] T: stacked rows of the prompts of one prefill pass
+  int pf_rows;
   void* pf_last;                  // [slots][d] T: last prompt row of a prefill body, read by its tail
   int pf_nx[GSV_MAX_SLOTS], pf_n[GSV_MAX_SLOTS];   // text / total prompt length of the body waiting for its tail (0 = none)
   float* pf_f32;
@@ -112,6 +113,8 @@ int gsv_umma_conv(gsv_umma_cache* c, size_t op, int dtype, const void* X, int ro
 
 // kernels / launchers implemented in gpt_decode.cu and gpt_prefill.cu
 int gsv_gpt_decode_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st);
+int gsv_gpt_prefill_body_many(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_t* const* xs, const int* nxs,
+                              const int64_t* const* ys, const int* nys, const void* const* berts, cudaStream_t st);
 int gsv_gpt_prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st);
 int gsv_gpt_prefill_tail(gsv_gpt_ctx* ctx, int slot, const int64_t* y, int ny, const gsv_gpt_sampling* samp, cudaStream_t st);
 int gsv_gpt_decode_configure(gsv_gpt_ctx* ctx);

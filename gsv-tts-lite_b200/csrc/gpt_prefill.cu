@@ -1,15 +1,29 @@
-// gpt_prefill.cu -- prompt prefill of one request into one KV-cache slot, and its first token.
+// gpt_prefill.cu -- prompt prefill of one or several requests into their KV-cache slots, and their first tokens.
 //
 // Replaces process_single_data + T2STransformer.process_prompt + the first sample()
 // (reference gsv_tts/GPT_SoVITS/GPT/t2s_model.py:351-383, 31-65, 114-127, 414-420; the same
-// sequence is the slot-refill path of infer_batched, :696-722).
+// sequence is the slot-refill path of infer_batched, :696-722, which the reference runs one request at a time).
 //
-// Round-1 implementation: straightforward tiled kernels (fp32 accumulate, T activations rounded
-// where the reference rounds them).  The GEMMs are the tcgen05 candidate for the next round; the
-// structure (what is fused into which epilogue) is already the final one.
+// Several prompts share one pass: their rows are stacked into one [sum n_i][d] matrix, so the four linears of a layer
+// are ONE tcgen05 launch each over all prompts (rows of the same 128-row tiles) and the per-row kernels (K/V scatter,
+// masked attention, add + LayerNorm) find their prompt through a small segment table passed by value.  The launch count
+// of a pass does not depend on the number of prompts (8 per layer).
 #include "gpt_sample.cuh"
 
 namespace {
+
+// prompts of one pass: rows [row0[i], row0[i+1]) of the stacked matrices belong to prompt i
+struct PfSegs {
+  int n;
+  int row0[GSV_MAX_SLOTS + 1];
+  int nx[GSV_MAX_SLOTS];
+  int slot[GSV_MAX_SLOTS];
+};
+__device__ __forceinline__ int pf_seg_of(const PfSegs& s, int row) {
+  int i = 0;
+  while (i + 1 < s.n && row >= s.row0[i + 1]) ++i;
+  return i;
+}
 
 // ---- embeddings (A.2) ------------------------------------------------------------------------
 // text rows:  round(round(emb_text[x] + bert_proj) + alpha_t*pe[i]);  audio rows: round(emb_audio[y] + alpha_a*pe[m])
@@ -97,26 +111,33 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const T* __restrict__ A, i
 
 // ---- K,V of the prompt into the cache slot: kc[l][slot][h][t][32] ----------------------------------------
 template <typename T>
-__global__ void kv_scatter_kernel(const GptParams p, int layer, int slot, const T* __restrict__ qkv, int n) {
-  const int t = blockIdx.x, d = p.d;
+__global__ void kv_scatter_kernel(const GptParams p, int layer, const PfSegs segs, const T* __restrict__ qkv) {
+  const int row = blockIdx.x, d = p.d;
+  const int sg = pf_seg_of(segs, row);
+  const int slot = segs.slot[sg], t = row - segs.row0[sg];
   T* kc = reinterpret_cast<T*>(p.kc);
   T* vc = reinterpret_cast<T*>(p.vc);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const size_t a = (((size_t)(layer * p.slots + slot) * p.H + (c >> 5)) * p.S + t) * GSV_HEAD_DIM + (c & 31);
-    kc[a] = qkv[(size_t)t * 3 * d + d + c];
-    vc[a] = qkv[(size_t)t * 3 * d + 2 * d + c];
+    kc[a] = qkv[(size_t)row * 3 * d + d + c];
+    vc[a] = qkv[(size_t)row * 3 * d + 2 * d + c];
   }
 }
 
 // ---- masked prompt attention (A.2 mask): text row -> all text; audio row i -> keys 0..i -----------------
 // one warp per (query row, head); 4 lanes x 8 dims per key, 8 keys per pass
 template <typename T>
-__global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n, int nx, int d,
-                                                           int H) {
+__global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__ qkv_all, T* __restrict__ out_all, const PfSegs segs,
+                                                           int n_tot, int d, int H) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * 4 + warp;
-  if (item >= n * H) return;
-  const int i = item / H, h = item - i * H;
+  if (item >= n_tot * H) return;
+  const int gi = item / H, h = item - gi * H;
+  const int sg = pf_seg_of(segs, gi);
+  const int base = segs.row0[sg], nx = segs.nx[sg];
+  const int i = gi - base;                                      // row within its prompt; keys are rows of the same prompt only
+  const T* qkv = qkv_all + (size_t)base * 3 * d;
+  T* out = out_all + (size_t)base * d;
   const int lim = i < nx ? nx : i + 1;
   const int sub = lane & 3, pg = lane >> 2;
   const float qscale = rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f;
@@ -267,37 +288,51 @@ int gemm(const T* A, int lda, const T* W, const T* bias, T* C, int ldc, int M, i
   return GSV_OK;
 }
 
-// Body of a prefill: everything that does not touch the slot's decode state (embeddings, the L layers, the K/V rows of
-// the slot).  It may run on another stream than the decode launches: decode kernels never look at an inactive slot.
-// The last prompt row is parked in pf_last[slot] for prefill_tail().
+// Body of a prefill pass: everything that does not touch the slots' decode state (embeddings, the L layers, the K/V rows of
+// the slots).  It may run on another stream than the decode launches: decode kernels never look at an inactive slot.
+// The last row of every prompt is parked in pf_last[slot] for prefill_tail().
 template <typename T>
-int prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st) {
+int prefill_body(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_t* const* xs, const int* nxs, const int64_t* const* ys,
+                 const int* nys, const void* const* berts, cudaStream_t st) {
   const GptParams& p = ctx->p;
-  const int d = p.d, F = p.F, L = p.L, n = nx + ny;
+  const int d = p.d, F = p.F, L = p.L;
   T* X = reinterpret_cast<T*>(ctx->pf_x);        // [n][d]
   T* QKV = reinterpret_cast<T*>(ctx->pf_qkv);    // [n][3d]
   T* ATT = reinterpret_cast<T*>(ctx->pf_attn);   // [n][d]
   T* Hh = reinterpret_cast<T*>(ctx->pf_h);       // [n][F]
   T* TMP = reinterpret_cast<T*>(ctx->pf_tmp);    // [n][d]
+  PfSegs segs;
+  memset(&segs, 0, sizeof(segs));
+  segs.n = n_prompts;
+  int n = 0;
+  for (int i = 0; i < n_prompts; ++i) {
+    segs.row0[i] = n; segs.nx[i] = nxs[i]; segs.slot[i] = slots[i];
+    n += nxs[i] + nys[i];
+  }
+  segs.row0[n_prompts] = n;
+  const int cap = ctx->pf_rows;
   int rc;
-  // bert_proj (nn.Linear(1024, d), t2s_model.py:172, 354)
-  if ((rc = gemm<T>(reinterpret_cast<const T*>(bert), p.d_bert, reinterpret_cast<const T*>(p.w_bert),
-                    reinterpret_cast<const T*>(p.b_bert), TMP, d, nx, d, p.d_bert, false, st, ctx->launches)))   // bert rows are caller-owned: CUDA cores
-    return rc;
-  embed_kernel<T><<<n, 128, 0, st>>>(p, x, nx, y, ny, TMP, X);
-  ctx->launches += 1;
-  GSV_CHECK_LAUNCH();
+  for (int i = 0; i < n_prompts; ++i) {
+    const int r0 = segs.row0[i];
+    // bert_proj (nn.Linear(1024, d), t2s_model.py:172, 354); bert rows are caller-owned: CUDA cores
+    if ((rc = gemm<T>(reinterpret_cast<const T*>(berts[i]), p.d_bert, reinterpret_cast<const T*>(p.w_bert),
+                      reinterpret_cast<const T*>(p.b_bert), TMP + (size_t)r0 * d, d, nxs[i], d, p.d_bert, false, st, ctx->launches)))
+      return rc;
+    embed_kernel<T><<<nxs[i] + nys[i], 128, 0, st>>>(p, xs[i], nxs[i], ys[i], nys[i], TMP + (size_t)r0 * d, X + (size_t)r0 * d);
+    ctx->launches += 1;
+    GSV_CHECK_LAUNCH();
+  }
   for (int l = 0; l < L; ++l) {
     const T* wqkv = reinterpret_cast<const T*>(p.w_qkv) + (size_t)l * 3 * d * d;
     const T* bqkv = reinterpret_cast<const T*>(p.b_qkv) + (size_t)l * 3 * d;
-    if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches, ctx, (size_t)l * 4 + 0, p.S))) return rc;
-    kv_scatter_kernel<T><<<n, 128, 0, st>>>(p, l, slot, QKV, n);
-    prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(QKV, ATT, n, nx, d, p.H);
+    if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches, ctx, (size_t)l * 4 + 0, cap))) return rc;
+    kv_scatter_kernel<T><<<n, 128, 0, st>>>(p, l, segs, QKV);
+    prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(QKV, ATT, segs, n, d, p.H);
     ctx->launches += 2;
     GSV_CHECK_LAUNCH();
     if ((rc = gemm<T>(ATT, d, reinterpret_cast<const T*>(p.w_o) + (size_t)l * d * d,
                       reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, n, d, d, false, st, ctx->launches, ctx,
-                      (size_t)l * 4 + 1, p.S)))
+                      (size_t)l * 4 + 1, cap)))
       return rc;
     add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln1_g) + (size_t)l * d,
                                                  reinterpret_cast<const T*>(p.ln1_b) + (size_t)l * d, n, d);
@@ -305,21 +340,23 @@ int prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int
     GSV_CHECK_LAUNCH();
     if ((rc = gemm<T>(X, d, reinterpret_cast<const T*>(p.w_1) + (size_t)l * F * d,
                       reinterpret_cast<const T*>(p.b_1) + (size_t)l * F, Hh, F, n, F, d, true, st, ctx->launches, ctx,
-                      (size_t)l * 4 + 2, p.S)))
+                      (size_t)l * 4 + 2, cap)))
       return rc;
     if ((rc = gemm<T>(Hh, F, reinterpret_cast<const T*>(p.w_2) + (size_t)l * d * F,
                       reinterpret_cast<const T*>(p.b_2) + (size_t)l * d, TMP, d, n, d, F, false, st, ctx->launches, ctx,
-                      (size_t)l * 4 + 3, p.S)))
+                      (size_t)l * 4 + 3, cap)))
       return rc;
     add_ln_kernel<T><<<(n + 3) / 4, 128, 0, st>>>(X, TMP, reinterpret_cast<const T*>(p.ln2_g) + (size_t)l * d,
                                                  reinterpret_cast<const T*>(p.ln2_b) + (size_t)l * d, n, d);
     ctx->launches += 1;
     GSV_CHECK_LAUNCH();
   }
-  GSV_CUDA(cudaMemcpyAsync(reinterpret_cast<T*>(ctx->pf_last) + (size_t)slot * d, X + (size_t)(n - 1) * d, (size_t)d * sizeof(T),
-                           cudaMemcpyDeviceToDevice, st));
-  ctx->pf_nx[slot] = nx;
-  ctx->pf_n[slot] = n;
+  for (int i = 0; i < n_prompts; ++i) {
+    GSV_CUDA(cudaMemcpyAsync(reinterpret_cast<T*>(ctx->pf_last) + (size_t)slots[i] * d, X + (size_t)(segs.row0[i + 1] - 1) * d,
+                             (size_t)d * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    ctx->pf_nx[slots[i]] = nxs[i];
+    ctx->pf_n[slots[i]] = nxs[i] + nys[i];
+  }
   return GSV_OK;
 }
 
@@ -564,9 +601,14 @@ int gsv_gpt_decode_gemm_launch(gsv_gpt_ctx* ctx, int n_steps, cudaStream_t st) {
   return decode_gemm_impl<__nv_bfloat16>(ctx, n_steps, st);
 }
 
+int gsv_gpt_prefill_body_many(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_t* const* xs, const int* nxs,
+                              const int64_t* const* ys, const int* nys, const void* const* berts, cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return prefill_body<__half>(ctx, n_prompts, slots, xs, nxs, ys, nys, berts, st);
+  return prefill_body<__nv_bfloat16>(ctx, n_prompts, slots, xs, nxs, ys, nys, berts, st);
+}
+
 int gsv_gpt_prefill_body(gsv_gpt_ctx* ctx, int slot, const int64_t* x, int nx, const int64_t* y, int ny, const void* bert, cudaStream_t st) {
-  if (ctx->dims.dtype == GSV_F16) return prefill_body<__half>(ctx, slot, x, nx, y, ny, bert, st);
-  return prefill_body<__nv_bfloat16>(ctx, slot, x, nx, y, ny, bert, st);
+  return gsv_gpt_prefill_body_many(ctx, 1, &slot, &x, &nx, &y, &ny, &bert, st);
 }
 
 int gsv_gpt_prefill_tail(gsv_gpt_ctx* ctx, int slot, const int64_t* y, int ny, const gsv_gpt_sampling* samp, cudaStream_t st) {

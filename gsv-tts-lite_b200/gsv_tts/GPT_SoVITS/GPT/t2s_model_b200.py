@@ -197,6 +197,36 @@ class Text2SemanticDecoder(nn.Module):
                                               bert.data_ptr(), self._stream()))
         return x, y, bert
 
+    def _prefill_begin_many(self, items):
+        """First half of the prefills of several idle slots on the CURRENT stream, in as few passes as their stacked rows
+        allow (``gsv_gpt_prefill_begin_many``: one tensor-core launch per linear over all prompts of a pass).
+        ``items`` = [(slot, x, y, bert)]; returns the device tensors each second half needs alive, in order."""
+        lib = N.lib()
+        cap = int(lib.gsv_gpt_prefill_capacity(self._ctx))
+        keep = []
+        for slot, x, y, bert in items:
+            x = x.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+            y = y.to(device=self._device, dtype=torch.int64).contiguous().view(-1)
+            bert = bert.to(device=self._device, dtype=self._dtype).contiguous().view(x.numel(), -1)
+            keep.append((x, y, bert))
+        i = 0
+        while i < len(items):
+            j, rows = i, 0
+            while j < len(items) and j - i < self._max_slots and rows + keep[j][0].numel() + keep[j][1].numel() <= cap:
+                rows += keep[j][0].numel() + keep[j][1].numel()
+                j += 1
+            j = max(j, i + 1)                      # a single over-long prompt is the library's argument error to report
+            n = j - i
+            slots_a = (C.c_int * n)(*[items[k][0] for k in range(i, j)])
+            xs = (C.c_void_p * n)(*[keep[k][0].data_ptr() for k in range(i, j)])
+            nxs = (C.c_int * n)(*[keep[k][0].numel() for k in range(i, j)])
+            ys = (C.c_void_p * n)(*[keep[k][1].data_ptr() for k in range(i, j)])
+            nys = (C.c_int * n)(*[keep[k][1].numel() for k in range(i, j)])
+            bs = (C.c_void_p * n)(*[keep[k][2].data_ptr() for k in range(i, j)])
+            N.check(lib.gsv_gpt_prefill_begin_many(self._ctx, n, slots_a, xs, nxs, ys, nys, bs, self._stream()))
+            i = j
+        return keep
+
     def _prefill_finish(self, slot, y, samp: N.GptSampling):
         N.check(N.lib().gsv_gpt_prefill_finish(self._ctx, slot, y.data_ptr(), y.numel(), C.byref(samp), self._stream()))
 
@@ -411,10 +441,21 @@ class Text2SemanticDecoder(nn.Module):
         FREE, REFILLING = -1, -2
         owner = [FREE] * slots
         nxt = 0
-        for s in range(min(slots, B)):
-            start(s, nxt)
-            owner[s] = nxt
-            nxt += 1
+        n0 = min(slots, B)
+        if self.overlap_refill:
+            # the first wave in stacked passes (the reference prefills it as ONE padded batch, t2s_model.py:576-634)
+            keeps = self._prefill_begin_many([(s, x[s], y[s], bert_feature[s]) for s in range(n0)])
+            for s in range(n0):
+                audit(s, s)
+                self._prefill_finish(s, keeps[s][1], sampling(s))
+                owner[s] = s
+            del keeps
+            nxt = n0
+        else:
+            for s in range(n0):
+                start(s, nxt)
+                owner[s] = nxt
+                nxt += 1
         results, order = [], []
         interval = max(int(check_interval), self.BATCH_INTERVAL)
         side = self._side_stream() if self.overlap_refill else None
@@ -437,9 +478,10 @@ class Text2SemanticDecoder(nn.Module):
             if to_begin:
                 with self._on_stream(side):
                     self._hold_side_stream(side)
-                    for slot, r in to_begin:
-                        keep = self._prefill_begin(slot, x[r], y[r], bert_feature[r])
-                        pending.append((slot, r, keep, self._record_event(side)))
+                    keeps = self._prefill_begin_many([(slot, x[r], y[r], bert_feature[r]) for slot, r in to_begin])
+                    ev = self._record_event(side)
+                    for (slot, r), keep in zip(to_begin, keeps):
+                        pending.append((slot, r, keep, ev))
                 to_begin = []
             self._read(slots)
             del done_refills              # their prompt tensors were needed until the second half had run

@@ -101,6 +101,16 @@ class TTS:
     def get_sovits_list(self):
         return list(self.sovits_models)
 
+    def _side_stream(self, dev) -> "torch.cuda.Stream":
+        """The stream the SoVITS stage of a streaming call runs on, created ONCE per TTS object: torch's caching allocator keeps
+        its free blocks per stream, so a fresh stream per call makes every tensor of the call's first chunk a cudaMalloc --
+        which waits for the running decode kernel each time (measured: 20-60 ms on the first clip of an utterance, at random)."""
+        cache = self.__dict__.setdefault("_side_streams", {})
+        key = str(dev)
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(dev)
+        return cache[key]
+
     def _pick(self, table, path, what):
         if path is None:
             if not table:
@@ -137,7 +147,7 @@ class TTS:
         gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
         voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         dev = gpt._device
-        side = torch.cuda.Stream(dev)
+        side = self._side_stream(dev)
         gpt.set_decode_sms(decode_sms)
         try:
             it = gpt.infer_stream(phoneme_ids, prompt_tokens, bert, top_k=top_k, top_p=top_p, temperature=temperature,
@@ -353,7 +363,7 @@ class TTS:
         gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
         vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         dev = self.tts_config.device
-        side = torch.cuda.Stream(dev)
+        side = self._side_stream(dev)
         with torch.inference_mode():
             ids = torch.tensor(list(phones1) + list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
             bert = torch.cat([bert1.to(dev), bert2.to(dev)]).unsqueeze(0)

@@ -60,6 +60,9 @@ SYMBOLS = [
     ("gsv_gpt_prefill", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, C.POINTER(GptSampling), _P]),
     ("gsv_gpt_prefill_begin", C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     ("gsv_gpt_prefill_finish", C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(GptSampling), _P]),
+    ("gsv_gpt_prefill_begin_many", C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(_P),
+                                            C.POINTER(C.c_int), C.POINTER(_P), _P]),
+    ("gsv_gpt_prefill_capacity", C.c_int, [_P]),
     ("gsv_gpt_decode", C.c_int, [_P, C.c_int, _P]),
     ("gsv_gpt_read", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     ("gsv_gpt_state_ptrs", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),

@@ -125,6 +125,15 @@ int gsv_gpt_prefill_begin(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_x, int 
 int gsv_gpt_prefill_finish(gsv_gpt_ctx* ctx, int slot, const int64_t* dev_y, int ny, const gsv_gpt_sampling* samp,
                            void* stream);
 
+/* `begin` for several idle slots in ONE pass: the prompts' rows are stacked, so each linear of a layer is
+ * one tensor-core launch over all of them and the launch count does not grow with n_prompts (the reference's refill path
+ * prefills one request at a time with ~20 eager ops per layer, t2s_model.py:696-722).  Host arrays of length n_prompts:
+ * slots (distinct), device pointers dev_x[i] / dev_y[i] / dev_bert[i], lengths nx[i] / ny[i]; the sum of nx[i] + ny[i] must
+ * not exceed gsv_gpt_prefill_capacity(ctx).  Each slot is then made live by its own gsv_gpt_prefill_finish. */
+int gsv_gpt_prefill_begin_many(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_t* const* dev_x, const int* nx,
+                               const int64_t* const* dev_y, const int* ny, const void* const* dev_bert, void* stream);
+int gsv_gpt_prefill_capacity(gsv_gpt_ctx* ctx);
+
 /* Run up to n_steps decode steps over every active slot: T2STransformer.decode_next_token x n
  * (t2s_model.py:129-143) + ar_predict_layer + sample + next-token embedding (:430-456, :637-653, :727-728),
  * with per-slot stop at EOS / full cache evaluated on the device (no host sync per token, cf. :426, :451-453).

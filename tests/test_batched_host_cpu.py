@@ -33,8 +33,15 @@ class FakeRuntime:
         self._activate(slot, int(x[0]), samp)
         self.log.append(("prefill", slot, int(x[0])))
 
+    def prefill_begin_many(self, items):
+        """One stacked pass over several idle slots (gsv_gpt_prefill_begin_many)."""
+        assert len({it[0] for it in items}) == len(items), "a slot named twice in one pass"
+        self.log.append(("begin_many", len(items)))
+        return [self.prefill_begin(*it) for it in items]
+
     def prefill_begin(self, slot, x, y, bert):
-        assert self.stream == "side", "the first half belongs on the second stream"
+        first_wave = not any(e[0] == "decode" for e in self.log)
+        assert self.stream == "side" or first_wave, "the first half of a REFILL belongs on the second stream"
         st = self.slot[slot]
         assert st is None or not st["active"], "begin on a slot that is still decoding"
         self.begun[slot] = int(x[0])
@@ -43,7 +50,8 @@ class FakeRuntime:
 
     def prefill_finish(self, slot, y, samp):
         assert self.stream == "main" and slot in self.begun
-        assert self.log and self.log[-1][0] in ("decode", "wait", "finish"), "finish goes behind a decode launch"
+        first_wave = not any(e[0] == "decode" for e in self.log)
+        assert first_wave or (self.log and self.log[-1][0] in ("decode", "wait", "finish")), "finish goes behind a decode launch"
         self._activate(slot, self.begun.pop(slot), samp)
         self.log.append(("finish", slot))
 
@@ -109,6 +117,7 @@ def make_model(lengths, slots, log, overlap):
     m._release_all = rt.release_all
     m._prefill = rt.prefill
     m._prefill_begin = rt.prefill_begin
+    m._prefill_begin_many = rt.prefill_begin_many
     m._prefill_finish = rt.prefill_finish
     m._decode = rt.decode
     m._read = rt.read
@@ -139,13 +148,18 @@ def test_every_request_completes_once_with_its_own_tokens(monkeypatch, overlap, 
         n = min(lengths[r], max_new[r])
         assert t.tolist() == [r * 1000 + i for i in range(1, n + 1)], (r, t.tolist())   # s0 dropped, EOS cut, max_new respected
     kinds = [e[0] for e in log]
-    if overlap and n_req > slots:
-        assert "begin" in kinds and kinds.count("begin") == kinds.count("finish") == n_req - slots
-        assert kinds.count("prefill") == slots                                   # only the initial fill is synchronous
+    if overlap:
+        # every request goes through begin (stacked passes) + finish; nothing is prefilled synchronously
+        assert kinds.count("begin") == kinds.count("finish") == n_req and "prefill" not in kinds
+        first_decode = kinds.index("decode")
+        wave = min(slots, n_req)
+        assert kinds[:first_decode].count("begin_many") == 1 and kinds[:first_decode].count("begin") == wave    # first wave: ONE pass
         # prompts of refills start on the second stream only after it was told to wait for the decode launch in flight
         for i, k in enumerate(kinds):
-            if k == "begin":
+            if k == "begin_many" and i > first_decode:
                 j = max(q for q in range(i) if kinds[q] in ("hold", "decode"))
-                assert kinds[j] == "hold" or all(kk in ("begin", "hold") for kk in kinds[j + 1:i]) and "hold" in kinds[max(0, i - 40):i]
+                assert kinds[j] == "hold"
+                n_pass = log[i][1]
+                assert kinds[i + 1:i + 1 + n_pass] == ["begin"] * n_pass         # the slots freed at one read share one pass
     else:
         assert "begin" not in kinds and kinds.count("prefill") == n_req
