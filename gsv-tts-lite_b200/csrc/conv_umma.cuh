@@ -277,7 +277,9 @@ struct ParamsWS {
   int n_mtiles;          // B * mt
   int a_rows;            // rows of the activation box = 128 + halo
   int a_stage_bytes;     // a_rows * BK * 2 rounded up to 1024
-  int sa;                // activation ring depth
+  int sa;                // activation ring depth (>= sub-tiles per unit)
+  int w_resident;        // 1: all (chunk, tap) weight tiles of the N tile stay in shared memory; 0: streamed through a ring
+  int sw;                // weight ring depth when streamed
   ConvArgs<T> ep;
 };
 
@@ -399,12 +401,12 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   static_assert(MS % SU == 0, "sub-tiles pair up when a tile has an odd number of 16-channel groups");
   constexpr int TMEM_COLS = WsTmem<ACC_COLS * NACC>::cols;
   static_assert(ACC_COLS * NACC <= 512 && NACC <= kMaxAcc, "accumulators fit tensor memory");
-  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc_full[kMaxAcc], acc_empty[kMaxAcc], w_full;
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc_full[kMaxAcc], acc_empty[kMaxAcc], w_full[kMaxSW], w_empty[kMaxSW];
   __shared__ uint32_t tmem_base_s;
   const uint32_t base_u = smem_u32(smem_raw);
   const uint32_t tiles_w = base_u + ((1024u - (base_u & 1023u)) & 1023u);
   const int n_w = P.kchunks * P.KW;
-  const uint32_t tiles_a = tiles_w + (uint32_t)(n_w * W_STAGE);
+  const uint32_t tiles_a = tiles_w + (uint32_t)((P.w_resident ? n_w : P.sw) * W_STAGE);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < NACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-    mbar_init(&w_full, 1);
+    for (int s = 0; s < kMaxSW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w) : "memory");
@@ -428,26 +430,41 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
+  // Loop order of a unit: channel chunk outermost, then tap, then sub-tile -- a weight tile (chunk, tap) meets the MS
+  // activation boxes of its chunk back to back, so when the weights are STREAMED through a ring (they do not fit: 256-channel
+  // layers, 11-tap 128-channel layers) every weight byte fetched from L2 serves MS tiles.
+  const bool resident = P.w_resident != 0;
+  const int SW = P.sw;                       // streamed: ring depth (resident: every (chunk, tap) has its own place)
   if (warp == 0) {
     if (lane == 0) {
-      // ---- TMA producer: the N tile's weights once, then the activation boxes of every M tile of this CTA ----
-      mbar_expect_tx(&w_full, (unsigned)(n_w * W_BYTES));
-      for (int i = 0; i < n_w; ++i) {
-        const int c = i / P.KW, j = i - c * P.KW;
-        tma_load_3d(tiles_w + (uint32_t)(i * W_STAGE), &P.tm_w, &w_full, c * BK, n0, j);
+      // ---- TMA producer ----
+      if (resident) {                        // weights do not depend on the previous kernel: before the wait
+        mbar_expect_tx(&w_full[0], (unsigned)(n_w * W_BYTES));
+        for (int i = 0; i < n_w; ++i) {
+          const int c = i / P.KW, j = i - c * P.KW;
+          tma_load_3d(tiles_w + (uint32_t)(i * W_STAGE), &P.tm_w, &w_full[0], c * BK, n0, j);
+        }
       }
       pdl_wait();
-      int it = 0;
+      int it = 0, iw = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        for (int sub = 0; sub < MS; ++sub) {
-          const int tile = unit * MS + sub;
-          if (tile >= P.n_mtiles) break;
-          const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
-          for (int c = 0; c < P.kchunks; ++c, ++it) {
+        const int nsub = P.n_mtiles - unit * MS < MS ? P.n_mtiles - unit * MS : MS;
+        for (int c = 0; c < P.kchunks; ++c) {
+          for (int sub = 0; sub < nsub; ++sub, ++it) {
+            const int tile = unit * MS + sub;
+            const int b = tile / P.mt, q0 = (tile - b * P.mt) * BM;
             const int s = it % SA;
             if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
             mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
             tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.in_off + c * BK, q0 - P.pad, b);
+          }
+          if (!resident) {
+            for (int j = 0; j < P.KW; ++j, ++iw) {
+              const int w = iw % SW;
+              if (iw >= SW) mbar_wait(&w_empty[w], ((iw / SW) - 1) & 1);
+              mbar_expect_tx(&w_full[w], W_BYTES);
+              tma_load_3d(tiles_w + (uint32_t)(w * W_STAGE), &P.tm_w, &w_full[w], c * BK, n0, j);
+            }
           }
         }
       }
@@ -457,29 +474,54 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
       // ---- MMA issuer ----
       constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
-      mbar_wait(&w_full, 0);
-      int it = 0, lt = 0;
+      if (resident) mbar_wait(&w_full[0], 0);
+      int it = 0, iw = 0, lt = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++lt) {
         const int buf = lt % NACC;
+        const int nsub = P.n_mtiles - unit * MS < MS ? P.n_mtiles - unit * MS : MS;
         if (lt >= NACC) mbar_wait(&acc_empty[buf], ((lt / NACC) - 1) & 1);
         tc_fence_after();
-        for (int sub = 0; sub < MS; ++sub) {
-          if (unit * MS + sub >= P.n_mtiles) break;
-          const uint32_t d = tmem_d + (uint32_t)(buf * ACC_COLS + sub * BN);
-          for (int c = 0; c < P.kchunks; ++c, ++it) {
-            const int s = it % SA;
-            mbar_wait(&a_full[s], (it / SA) & 1);
-            tc_fence_after();
-            const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
-            for (int j = 0; j < P.KW; ++j) {
-              const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
-              const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)((c * P.KW + j) * W_STAGE));
+        const uint32_t d0 = tmem_d + (uint32_t)(buf * ACC_COLS);
+        for (int c = 0; c < P.kchunks; ++c) {
+          uint32_t a_base[MS];
+          int a_slot[MS];
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+          for (int sub = 0; sub < MS; ++sub) {
+            if (sub < nsub) {
+              a_slot[sub] = (it + sub) % SA;
+              a_base[sub] = tiles_a + (uint32_t)(a_slot[sub] * P.a_stage_bytes);
+              mbar_wait(&a_full[a_slot[sub]], ((it + sub) / SA) & 1);
             }
-            tc_commit(&a_empty[s]);          // frees the activation slot when these MMAs have read it
           }
+          tc_fence_after();
+          uint32_t tap_off = 0;
+          for (int j = 0; j < P.KW; ++j, tap_off += (uint32_t)(P.dil * ROW_BYTES)) {
+            int w = c * P.KW + j;
+            if (!resident) {
+              w = iw % SW;
+              mbar_wait(&w_full[w], (iw / SW) & 1);
+              tc_fence_after();
+            }
+            const uint64_t bd = smem_desc<BK>(tiles_w + (uint32_t)(w * W_STAGE));
+            const uint32_t acc = (c > 0 || j > 0) ? 1u : 0u;
+#pragma unroll
+            for (int sub = 0; sub < MS; ++sub) {
+              if (sub < nsub) {
+                const uint64_t ad = smem_desc<BK>(a_base[sub] + tap_off);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                  tc_mma(d0 + (uint32_t)(sub * BN), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, k > 0 ? 1u : acc);
+              }
+            }
+            if (!resident) {
+              tc_commit(&w_empty[w]);        // frees the weight slot when these MMAs have read it
+              ++iw;
+            }
+          }
+#pragma unroll
+          for (int sub = 0; sub < MS; ++sub)
+            if (sub < nsub) tc_commit(&a_empty[a_slot[sub]]);    // frees the activation slots of this chunk
+          it += nsub;
         }
         tc_commit(&acc_full[buf]);           // accumulators of this unit complete
       }

@@ -548,13 +548,14 @@ int launch_conv_umma(std::vector<MapCacheEntry>& map_cache, int num_sms, const C
 
 // ---- weight-stationary persistent variant (conv_umma.cuh, second kernel) ---------------------------------------------
 struct WsPlan {
-  int bn, bk, nacc, ms, sa, n_nt, mt;
+  int bn, bk, nacc, ms, sa, n_nt, mt, resident, sw;
   size_t smem;
 };
 constexpr size_t kWsBudget = 222 * 1024;      // dynamic shared memory of the persistent kernel (227 KB per CTA minus barriers)
-inline int ws_ms(int bn) { return bn <= 32 ? 4 : (bn <= 96 ? 2 : 1); }      // M tiles per accumulator hand-over
+inline int ws_ms(int bn) { return bn <= 32 ? 4 : 2; }      // M tiles per accumulator hand-over
 inline int ws_nacc(int bn) { return bn >= 64 ? 2 : 3; }
-// stride-1 convolutions whose N tile's weights (all taps) fit in shared memory beside an activation ring of about two units
+// Persistent kernel for a stride-1 convolution: N tile, channels per chunk, ring depths, and whether the N tile's weights
+// (all taps) stay in shared memory or are streamed through a ring (conv_umma.cuh).
 template <typename T>
 bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl) {
   if (a.stride != 1 || a.in_rev || a.o_rev || a.Cin < 16 || a.Cin % 8 || a.in_ld % 8 || a.Cout % 8 || a.KW > 16 ||
@@ -571,29 +572,48 @@ bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl
   else bk0 = 32;
   const int a_rows = umma::BM + (a.KW - 1) * a.dil;
   static const int cand[6] = {128, 96, 64, 48, 32, 16};
-  for (int ci = 0; ci < 6; ++ci) {
-    const int bn = cand[ci];
-    if (!(a.Cout % bn == 0 || (bn > a.Cout && bn - a.Cout <= 8))) continue;
-    if (bn < 64 && bn < a.Cout) break;      // narrow N tiles re-read the activations too often: the one-tile kernel does better
-    const int n_nt = (a.Cout + bn - 1) / bn;
-    const int ms = ws_ms(bn);
-    // 64 channels per chunk first; 32 per chunk halves the ring's bytes per stage when the weights leave little room
-    for (int bk = bk0; bk >= 16; bk >>= 1) {
-      if (bk < bk0 && (bk0 != 64 || bk != 32 || a.Cin % 32)) break;
-      if (bk == 16 && bn != 16) break;
-      const int kchunks = (a.Cin + bk - 1) / bk;
-      const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
-      const int w_stage = (bn * bk * 2 + 1023) & ~1023;
-      const size_t w_bytes = (size_t)kchunks * a.KW * w_stage;
-      int sa = 2 * ms * kchunks;
-      sa = sa < 3 ? 3 : sa;
-      sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
-      const int sa_min = kchunks + 1 > 2 ? kchunks + 1 : 2;
-      while (sa > sa_min && w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) --sa;
-      if (w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) continue;
-      pl.bn = bn; pl.bk = bk; pl.nacc = ws_nacc(bn); pl.ms = ms; pl.sa = sa; pl.n_nt = n_nt; pl.mt = mt;
-      pl.smem = w_bytes + (size_t)sa * a_stage + 1024;
-      return true;
+  // pass 0: weights resident with a ring of two units; pass 1: weights streamed (wide N tiles only: every N tile re-reads the
+  // activations); pass 2: weights resident with whatever ring still fits
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int ci = 0; ci < 6; ++ci) {
+      const int bn = cand[ci];
+      if (!(a.Cout % bn == 0 || (bn > a.Cout && bn - a.Cout <= 8))) continue;
+      if (bn < 64 && bn < a.Cout) break;      // narrow N tiles re-read the activations too often: the one-tile kernel does better
+      const int n_nt = (a.Cout + bn - 1) / bn;
+      if (n_nt > num_sms) continue;
+      const int ms = ws_ms(bn);
+      const int bk = bk0;
+      if ((bk == 16 && bn != 16) || (bk == 32 && (bn == 128 || bn == 64))) continue;      // instantiated pairs only
+      {
+        const int kchunks = (a.Cin + bk - 1) / bk;
+        const int n_w = kchunks * a.KW;
+        const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
+        const int w_stage = (bn * bk * 2 + 1023) & ~1023;
+        int sa = 2 * ms * kchunks;
+        sa = sa < 3 ? 3 : sa;
+        sa = sa > umma::kMaxSA ? umma::kMaxSA : sa;
+        const int sa_good = 2 * ms < sa ? 2 * ms : sa, sa_min = ms + 1;
+        if (pass != 1) {
+          const size_t w_bytes = (size_t)n_w * w_stage;
+          const int floor_sa = pass == 0 ? sa_good : sa_min;
+          while (sa > floor_sa && w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) --sa;
+          if (w_bytes + (size_t)sa * a_stage + 1024 > kWsBudget) continue;
+          pl.resident = 1; pl.sw = n_w;
+          pl.smem = w_bytes + (size_t)sa * a_stage + 1024;
+        } else {
+          if (n_w < 2) continue;
+          sa = sa_good > 3 ? sa_good : 3;
+          long long room = (long long)kWsBudget - 1024 - (long long)sa * a_stage;
+          int sw = (int)(room / w_stage);
+          if (sw > umma::kMaxSW) sw = umma::kMaxSW;
+          if (sw > n_w) sw = n_w;
+          if (sw < 3) continue;
+          pl.resident = 0; pl.sw = sw;
+          pl.smem = (size_t)sw * w_stage + (size_t)sa * a_stage + 1024;
+        }
+        pl.bn = bn; pl.bk = bk; pl.nacc = ws_nacc(bn); pl.ms = ms; pl.sa = sa; pl.n_nt = n_nt; pl.mt = mt;
+        return true;
+      }
     }
   }
   return false;
@@ -649,13 +669,14 @@ int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const Con
   P.a_rows = a_rows;
   P.a_stage_bytes = (a_rows * bk * 2 + 1023) & ~1023;
   P.sa = pl.sa;
+  P.w_resident = pl.resident; P.sw = pl.sw;
   P.ep = a;
   const int n_units = (P.n_mtiles + pl.ms - 1) / pl.ms;
   int gx = num_sms / pl.n_nt;
   if (gx > n_units) gx = n_units;
   const dim3 grid(gx, pl.n_nt, 1);
   int rc = GSV_ERR_ARG;
-#define GSV_WS(BN_, BK_) rc = launch_ws_inst<T, BN_, BK_, (BN_ >= 64 ? 2 : 3), (BN_ <= 32 ? 4 : (BN_ <= 96 ? 2 : 1))>(P, grid, pl.smem, st)
+#define GSV_WS(BN_, BK_) rc = launch_ws_inst<T, BN_, BK_, (BN_ >= 64 ? 2 : 3), (BN_ <= 32 ? 4 : 2)>(P, grid, pl.smem, st)
   if (bk == 64) {
     if (bn == 128) GSV_WS(128, 64);
     else if (bn == 96) GSV_WS(96, 64);
@@ -664,9 +685,7 @@ int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const Con
     else if (bn == 32) GSV_WS(32, 64);
     else GSV_WS(16, 64);
   } else if (bk == 32) {
-    if (bn == 128) GSV_WS(128, 32);
-    else if (bn == 96) GSV_WS(96, 32);
-    else if (bn == 64) GSV_WS(64, 32);
+    if (bn == 96) GSV_WS(96, 32);
     else if (bn == 48) GSV_WS(48, 32);
     else if (bn == 32) GSV_WS(32, 32);
     else GSV_WS(16, 32);

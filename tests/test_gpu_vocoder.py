@@ -120,12 +120,12 @@ def test_weight_stationary_kernel_forced_matches_golden(dev, name, key, monkeypa
 
 @pytest.mark.parametrize("key", ["v2Pro", "v2ProPlus"])
 def test_weight_stationary_kernel_on_large_grids(dev, key, monkeypatch):
-    """B=3, T=150 (ragged last tiles, grids above two tiles per SM from the third upsampling stage on): the persistent kernel
-    issues the same MMAs in the same order as the one-tile kernel, so V2Pro is bit-equal to GSV_VOC_WS=0; V2ProPlus'
-    48 / 24-channel stages run on CUDA cores there, so the two differ by rounding only."""
+    """B=4, T=150 (ragged last tiles, grids above two tiles per SM from the second upsampling stage on, so resident and
+    streamed weights both occur) against GSV_VOC_WS=0 (one-tile kernel; V2ProPlus' 48 / 24-channel stages on CUDA cores): the
+    two differ by fp32 summation order only."""
     from tests import gpu_harness as H
     g = torch.Generator().manual_seed(11)
-    B, T = 3, 150
+    B, T = 4, 150
     model = syn.SOVITS_MODEL[key]
     z_p = torch.randn(B, 192, T, generator=g).to(dev)
     mask = torch.ones(B, 1, T, device=dev)
@@ -141,7 +141,4 @@ def test_weight_stationary_kernel_on_large_grids(dev, key, monkeypatch):
     err = float((out["0"] - out["1"]).abs().max())
     print(key, "max|ws - one-tile|", err)
     assert torch.isfinite(out["1"]).all()
-    if key == "v2Pro":
-        assert err == 0.0
-    else:
-        assert err < 1e-3
+    assert err < 1e-3

@@ -14,11 +14,11 @@ agg = collections.OrderedDict()
 tot = 0.0
 for d in rec.values():
     us = d.get("gpu__time_duration.sum", 0.0) / 1e3
-    key = (d["name"][:70], int(d.get("launch__grid_size", 0)))
+    key = (d["name"][d["name"].find("conv_umma"):][:60] if "conv_umma" in d["name"] else d["name"][:60], int(d.get("launch__grid_size", 0)), int(d.get("launch__shared_mem_per_block_dynamic", 0)) // 1024)
     a = agg.setdefault(key, [0.0, 0, 0.0])
     a[0] += us; a[1] += 1
     a[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     tot += us
 print(f"total {tot/1e3:.3f} ms over {len(rec)} launches")
-for (name, grid), (us, c, by) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
-    print(f"{100*us/tot:6.2f}% {us/1e3:9.3f} ms  n={c:4d}  avg {us/c:8.1f} us  dram {by/max(us,1e-9)/1e3:7.0f} GB/s  grid {grid:7d}  {name}")
+for (name, grid, smem), (us, c, by) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    print(f"{100*us/tot:6.2f}% {us/1e3:9.3f} ms  n={c:4d}  avg {us/c:8.1f} us  dram {by/max(us,1e-9)/1e3:7.0f} GB/s  grid {grid:7d} smem {smem:3d}K  {name}")
