@@ -600,7 +600,7 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
                 ms = e0.elapsed_time(e1)
                 tf = 64 * 500 * DEC_FLOP[key] / (ms / 1e3) / 1e12
                 c5[key] = {"ms": ms, "tflops": tf, "frac_of_tensor_peak": tf / pk["bf16_tflops"], "audio_s_per_s": 64 * 10.0 / (ms / 1e3),
-                           "roofline": {"kernel": "conv_umma_kernel (flow + HiFi-GAN call)", "bound": "tensor", "achieved": tf,
+                           "roofline": {"kernel": "conv_umma_ws_kernel + conv_umma_kernel (flow + HiFi-GAN call)", "bound": "tensor", "achieved": tf,
                                         "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"]}}
                 del z, mk, gg
             except Exception as e:
