@@ -157,6 +157,42 @@ def read_sovits_checkpoint(path: str) -> Tuple[dict, Dict[str, torch.Tensor], st
     return hps, sd, version
 
 
+def to_safetensors(checkpoint_path: str, output_dir: Optional[str] = None) -> str:
+    """Reference ``TTS.to_safetensors`` (TTS.py:1482-1523): a ``.ckpt`` (GPT) or ``.pth`` (SoVITS) checkpoint becomes a directory
+    with ``model.safetensors`` + ``config.json`` / ``hps.json`` -- the third format both loaders read.  The reference saves the
+    state dict of the MODULE it built, so: GPT keys are already in the Lite layout, and the SoVITS ``dec.*`` weight-norm pairs
+    are folded (``dec.remove_weight_norm()``, Loader.py:95) while ``flow.*`` keeps ``weight_g`` / ``weight_v``.  No device, no
+    model construction: this is file conversion only.  Returns the directory."""
+    from safetensors.torch import save_file
+    if output_dir is None:
+        output_dir, _ = os.path.splitext(checkpoint_path)
+    os.makedirs(output_dir, exist_ok=True)
+    suffix = os.path.splitext(checkpoint_path)[1]
+    if suffix == ".ckpt":
+        config, sd = read_gpt_checkpoint(checkpoint_path)
+        meta_name, meta = "config.json", config
+    elif suffix == ".pth":
+        from .GPT_SoVITS.SoVITS.models_b200 import fold_weight_norm
+        hps, raw, _ = read_sovits_checkpoint(checkpoint_path)
+        sd = {}
+        for k, v in raw.items():
+            if k.startswith("dec.") and k.endswith(".weight_g"):
+                continue
+            if k.startswith("dec.") and k.endswith(".weight_v"):
+                base = k[: -len("weight_v")]
+                sd[base + "weight"] = fold_weight_norm(raw[base + "weight_g"].float(), v.float()).to(v.dtype)
+            else:
+                sd[k] = v
+        meta_name, meta = "hps.json", hps
+    else:
+        raise ValueError(f"to_safetensors: expected a .ckpt (GPT) or .pth (SoVITS) file, got {checkpoint_path!r}")
+    save_file({k: v.detach().cpu().contiguous() for k, v in sd.items() if isinstance(v, torch.Tensor)},
+              os.path.join(output_dir, "model.safetensors"))
+    with open(os.path.join(output_dir, meta_name), "w") as f:
+        json.dump(meta, f, indent=4, ensure_ascii=False, default=str)
+    return output_dir
+
+
 class Gpt:
     def __init__(self, t2s_model, config):
         self.t2s_model = t2s_model

@@ -95,6 +95,11 @@ class TTS:
         for p in paths:
             self.sovits_models.pop(p, None)
 
+    def to_safetensors(self, checkpoint_path: str, output_dir: Optional[str] = None):
+        """TTS.py:1482-1523: convert a ``.ckpt`` / ``.pth`` checkpoint into the safetensors directory format the loaders read."""
+        out = Loader.to_safetensors(checkpoint_path, output_dir)
+        log.info("Successfully converted and saved to: %s", out)
+
     def get_gpt_list(self):
         return list(self.gpt_models)
 

@@ -121,3 +121,43 @@ def test_sovits_pth_with_config_pickled_from_module_utils(tmp_path):
     assert version == "v2" and hps["model"]["upsample_rates"] == model["upsample_rates"]
     assert hps["data"]["hop_length"] == 640 and isinstance(hps["model"], dict)
     assert torch.equal(sd["dec.conv_post.weight"], torch.ones(1, 4, 7))
+
+
+def test_to_safetensors_round_trip(tmp_path):
+    """TTS.to_safetensors (reference TTS.py:1482-1523): .ckpt / .pth -> directory the loaders read back; GPT tensors equal,
+    SoVITS dec.* weight-norm folded (the reference saves the module after dec.remove_weight_norm()), flow.* untouched."""
+    from gsv_tts.GPT_SoVITS.SoVITS.models_b200 import fold_weight_norm
+    cfg = syn.GPT_CONFIG_TINY
+    sd = syn.gpt_state_dict(cfg, 0)
+    ckpt = tmp_path / "s1.ckpt"
+    torch.save({"config": cfg, "weight": _upstream_gpt_names(sd, cfg["model"]["n_layer"])}, ckpt)
+    out = Loader.to_safetensors(str(ckpt))
+    assert out == str(tmp_path / "s1")
+    config2, got2 = Loader.read_gpt_checkpoint(out)
+    assert config2 == cfg and sorted(got2) == sorted(sd) and all(torch.equal(got2[k], sd[k]) for k in sd)
+
+    model = dict(syn.SOVITS_MODEL["tiny"], version="v2Pro")
+    s2 = dict(syn.sovits_flow_dec_state_dict(model, 0))
+    s2.update(syn.sovits_encp_state_dict(model, 0))
+    hps = {"data": {"filter_length": 2048, "hop_length": 640, "n_speakers": 300}, "train": {"segment_size": 20480}, "model": model}
+    pth = tmp_path / "s2.pth"
+    torch.save({"config": hps, "weight": s2}, pth)
+    out2 = Loader.to_safetensors(str(pth), str(tmp_path / "conv"))
+    hps2, got, version = Loader.read_sovits_checkpoint(out2)
+    assert version == "v2Pro" and hps2["model"]["upsample_rates"] == list(model["upsample_rates"])
+    assert not any(k.startswith("dec.") and k.endswith(("weight_g", "weight_v")) for k in got)
+    for k, v in s2.items():
+        if k.startswith("dec.") and k.endswith("weight_v"):
+            base = k[: -len("weight_v")]
+            assert torch.allclose(got[base + "weight"], fold_weight_norm(s2[base + "weight_g"], v), atol=1e-6)
+        elif not (k.startswith("dec.") and k.endswith("weight_g")):
+            assert torch.equal(got[k], v), k
+    # and the native class loads the converted directory like the original file
+    from gsv_tts.GPT_SoVITS.SoVITS.models_b200 import SynthesizerTrn
+    a, b = SynthesizerTrn(1025, 32, n_speakers=300, **hps2["model"]), SynthesizerTrn(1025, 32, n_speakers=300, **model)
+    a.load_state_dict(got)
+    b.load_state_dict(s2)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert sorted(sa) == sorted(sb) and all(torch.allclose(sa[k].float(), sb[k].float(), atol=1e-6) for k in sa)
+    with pytest.raises(ValueError):
+        Loader.to_safetensors(str(tmp_path / "x.bin"))
