@@ -403,11 +403,14 @@ class Text2SemanticDecoder(nn.Module):
     @torch.inference_mode()
     def infer_batched(self, x: List[torch.Tensor], y: List[torch.Tensor], bert_feature: List[torch.Tensor],
                       top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0, repetition_penalty: float = 1.35,
-                      check_interval: int = 5, max_new: Optional[List[int]] = None):
+                      check_interval: int = 5, max_new: Optional[List[int]] = None, on_finish=None, on_launch=None):
         """t2s_model.py:555-734: continuous batching.  Slot count = smallest configured batch >= B,
         else the largest (:569-574); no repetition penalty, no token suppression (:613, :651);
         finished rows are harvested and their slot refilled from the queue (:672-722).
-        Returns (list of int64 [n_i] in completion order, int64 [B] original indices)."""
+        Returns (list of int64 [n_i] in completion order, int64 [B] original indices).
+        Two hooks let a caller overlap its next stage with the decode (``TTS.infer_phones_batched``): ``on_finish(r, tokens)``
+        at the harvest of request r, ``on_launch(decoding)`` right after every decode launch -- the place to enqueue work
+        on another stream behind ``hold_until_decode_resident``."""
         B = len(x)
         slots = None
         for b in sorted(self._buckets):
@@ -462,7 +465,8 @@ class Text2SemanticDecoder(nn.Module):
         to_begin = []                     # (slot, request) freed at the last read: their prompts start behind the next decode launch
         pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
         while any(o >= 0 for o in owner) or pending or to_begin:
-            if any(o >= 0 for o in owner):
+            launched = any(o >= 0 for o in owner)
+            if launched:
                 self._decode(interval)
             # second half of the refills begun one launch ago: behind the decode launch just enqueued, so their prompts were
             # computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
@@ -483,6 +487,8 @@ class Text2SemanticDecoder(nn.Module):
                     for (slot, r), keep in zip(to_begin, keeps):
                         pending.append((slot, r, keep, ev))
                 to_begin = []
+            if on_launch is not None:
+                on_launch(launched)
             self._read(slots)
             del done_refills              # their prompt tensors were needed until the second half had run
             for s in range(slots):
@@ -493,6 +499,8 @@ class Text2SemanticDecoder(nn.Module):
                         toks = toks[:-1]
                     results.append(toks.to(self._device))
                     order.append(owner[s])
+                    if on_finish is not None:
+                        on_finish(owner[s], results[-1])
                     owner[s] = FREE
                     if nxt < B:
                         if side is None:

@@ -185,16 +185,13 @@ class TTS:
             res[i] = o
         return res
 
-    @torch.inference_mode()
-    def vocode_features_batched(self, z_p: Sequence[torch.Tensor], ge: Sequence[torch.Tensor], sovits_model: Optional[str] = None,
-                                max_frames: int = 8192) -> List[AudioClip]:
-        """Vocoder stage of ``infer_batched`` (TTS.py:705-764): utterances of different lengths ``z_p[i]`` [192, T_i] are
-        sorted by length and run through flow + HiFi-GAN in padded groups of at most ``max_frames`` frames (padded frames
-        are masked), so that a group is one native call; clips come back in request order."""
-        voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+    def _vocode_groups(self, voc, z_p: Sequence[torch.Tensor], ge: Sequence[torch.Tensor], max_frames: int) -> List[torch.Tensor]:
+        """Utterances of different lengths ``z_p[i]`` [192, T_i] through flow + HiFi-GAN in length-sorted, padded groups of at
+        most ``max_frames`` frames (padded frames are masked; a group is one native call).  Returns fp32 waveforms on the
+        device, in input order -- no host synchronisation."""
         dev, dt = voc._device, voc._dtype
         order = sorted(range(len(z_p)), key=lambda i: -int(z_p[i].shape[-1]))
-        clips: List[Optional[AudioClip]] = [None] * len(z_p)
+        out: List[Optional[torch.Tensor]] = [None] * len(z_p)
         spf = voc.samples_per_frame
         i = 0
         while i < len(order):
@@ -209,25 +206,96 @@ class TTS:
                 zb[r, :, :t] = z_p[k].to(device=dev, dtype=dt, non_blocking=True)
                 mb[r, :, :t] = 1
                 gb[r] = ge[k].to(device=dev, dtype=dt, non_blocking=True).view(voc.gin_channels, 1)
-            audio = voc.flow_dec(zb, mb, gb).float().cpu().numpy()
+            audio = voc.flow_dec(zb, mb, gb).float()
             for r, k in enumerate(grp):
-                clips[k] = self._clip(audio[r, 0, : int(z_p[k].shape[-1]) * spf])
+                out[k] = audio[r, 0, : int(z_p[k].shape[-1]) * spf]
             i += n
-        return clips
+        return out
+
+    @torch.inference_mode()
+    def vocode_features_batched(self, z_p: Sequence[torch.Tensor], ge: Sequence[torch.Tensor], sovits_model: Optional[str] = None,
+                                max_frames: int = 8192) -> List[AudioClip]:
+        """Vocoder stage of ``infer_batched`` (TTS.py:705-764) for latents of different lengths; clips in request order."""
+        voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        return [self._clip(a.cpu().numpy()) for a in self._vocode_groups(voc, z_p, ge, max_frames)]
+
+    def _sovits_stage_device(self, vq, tokens, phones2, ge, noise_scale, speed, max_frames) -> List[torch.Tensor]:
+        """SoVITS stage on the CURRENT stream, no host synchronisation: the prior encoder per utterance (its attention must not
+        cross utterance boundaries), then flow + HiFi-GAN in padded, length-sorted groups; fp32 waveforms on the device."""
+        zs, gs, live = [], [], []
+        for i, (t, ph, g) in enumerate(zip(tokens, phones2, ge)):
+            if t.numel() == 0:                                   # EOS as the first token: nothing to say
+                continue
+            z_p, _mask, g2, _attn = vq.prior(t.view(1, 1, -1), ph.view(1, -1), g, noise_scale=noise_scale, speed=speed)
+            zs.append(z_p[0])
+            gs.append(g2[0])
+            live.append(i)
+        out = [torch.zeros(0, device=vq._device) for _ in tokens]
+        for i, a in zip(live, self._vocode_groups(vq, zs, gs, max_frames) if live else []):
+            out[i] = a
+        return out
 
     @torch.inference_mode()
     def decode_batched(self, tokens: Sequence[torch.Tensor], phones2: Sequence[torch.Tensor], ge: Sequence[torch.Tensor],
                        noise_scale: float = 0.5, speed: float = 1.0, sovits_model: Optional[str] = None, max_frames: int = 8192):
-        """SoVITS stage of ``infer_batched`` for a list of utterances: the prior encoder runs per utterance (its attention
-        must not cross utterance boundaries), the latents then go through flow + HiFi-GAN in padded, length-sorted groups
-        (``vocode_features_batched``).  tokens[i] int64 [N_i], phones2[i] int64 [Nt_i], ge[i] [1,gin,1] -> AudioClips."""
+        """SoVITS stage of ``infer_batched`` for a list of utterances.  tokens[i] int64 [N_i], phones2[i] int64 [Nt_i],
+        ge[i] [1,gin,1] -> AudioClips."""
         vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
-        zs, gs = [], []
-        for t, ph, g in zip(tokens, phones2, ge):
-            z_p, _mask, g2, _attn = vq.prior(t.view(1, 1, -1), ph.view(1, -1), g, noise_scale=noise_scale, speed=speed)
-            zs.append(z_p[0])
-            gs.append(g2[0])
-        return self.vocode_features_batched(zs, gs, sovits_model=sovits_model, max_frames=max_frames)
+        return [self._clip(a.cpu().numpy()) for a in self._sovits_stage_device(vq, tokens, phones2, ge, noise_scale, speed, max_frames)]
+
+    @torch.inference_mode()
+    def infer_phones_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence, phones2: Sequence, ge: Sequence,
+                             top_k=15, top_p=1.0, temperature=1.0, noise_scale: float = 0.5, speed: float = 1.0, max_new=None,
+                             gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, max_frames: int = 8192,
+                             overlap: bool = True, trim_silence: bool = False, texts: Optional[Sequence[str]] = None):
+        """Everything of ``TTS.infer_batched`` after the text front end (TTS.py:695-764): continuous-batched GPT, then the SoVITS
+        stage per utterance.  The reference runs the two stages back to back; here the SoVITS stage of the requests harvested
+        at one read is enqueued on the second stream right behind the next decode launch (held until that launch is resident,
+        ``hold_until_decode_resident``), so it runs on the SMs the batched decode kernel leaves free while the other slots keep
+        decoding.  Returns ``(token lists, AudioClips)`` in request order.  ``overlap=False`` is the back-to-back order."""
+        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
+        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
+        dev = self.tts_config.device
+        n = len(phoneme_ids)
+        tokens: List[Optional[torch.Tensor]] = [None] * n
+        audio: List[Optional[torch.Tensor]] = [None] * n
+        ready: List[int] = []
+        side = self._side_stream(dev) if overlap else None
+
+        def on_finish(r, toks):
+            tokens[r] = toks
+            ready.append(r)
+
+        def run_ready(decoding: bool):
+            if not ready or side is None:
+                return
+            batch = list(ready)
+            del ready[:]
+            side.wait_stream(torch.cuda.current_stream(dev))               # the harvested tokens were copied on the caller's stream
+            with torch.cuda.stream(side):
+                if decoding:
+                    gpt.hold_until_decode_resident(side)
+                for r in batch:
+                    tokens[r].record_stream(side)
+                outs = self._sovits_stage_device(vq, [tokens[r] for r in batch], [phones2[r] for r in batch], [ge[r] for r in batch],
+                                                 noise_scale, speed, max_frames)
+            for r, a in zip(batch, outs):
+                audio[r] = a
+
+        gpt.infer_batched(list(phoneme_ids), list(prompt_tokens), list(bert), top_k=top_k, top_p=top_p, temperature=temperature,
+                          max_new=max_new, on_finish=on_finish, on_launch=run_ready if overlap else None)
+        if overlap:
+            run_ready(False)                                               # what finished at the last read
+            torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            outs = self._sovits_stage_device(vq, tokens, phones2, ge, noise_scale, speed, max_frames)
+            audio = list(outs)
+        clips = []
+        for i, a in enumerate(audio):
+            if trim_silence:                                               # TTS.py:803-812: leading / trailing silence of every utterance
+                a = a[self._find_head_threshold_offsets(a):a.numel() - self._find_tail_threshold_offsets(a)]
+            clips.append(self._clip(a.cpu().numpy(), texts[i] if texts is not None else ""))
+        return tokens, clips
 
     def _clip(self, audio: np.ndarray, text: str = "") -> AudioClip:
         peak = float(np.abs(audio).max()) if audio.size else 0.0
@@ -457,13 +525,11 @@ class TTS:
     def infer_batched(self, spk_audio_paths, prompt_audio_paths, prompt_audio_texts, texts, top_k: int = 15, top_p: float = 1.0,
                       temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5, speed: float = 1.0,
                       gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, **_ignored):
-        """``TTS.infer_batched`` (TTS.py:507-868): every text goes through the continuous-batched GPT (``infer_batched``), then
-        through ``vq_model.decode`` one utterance at a time (the reference concatenates a SoVITS batch into ONE sequence whose
-        encoder attends across utterance boundaries, TTS.py:730-764; decoding them separately is the per-utterance result the
-        single path gives).  Returns a tuple of ``AudioClip`` in input order."""
+        """``TTS.infer_batched`` (TTS.py:507-868): every text goes through the continuous-batched GPT, and through the SoVITS
+        stage one utterance at a time (the reference concatenates a SoVITS batch into ONE sequence whose encoder attends across
+        utterance boundaries, TTS.py:730-764; decoding them separately is the per-utterance result the single path gives), the
+        two stages overlapped (``infer_phones_batched``).  Returns a tuple of ``AudioClip`` in input order."""
         fe = self._need_frontend("infer_batched")
-        gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
-        vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         dev = self.tts_config.device
         one = lambda v, i: v[i] if isinstance(v, (list, tuple)) else v
         ids, prompts, berts, ph2s, ges = [], [], [], [], []
@@ -476,13 +542,7 @@ class TTS:
             berts.append(torch.cat([bert1.to(dev), bert2.to(dev)]))
             ph2s.append(torch.tensor(list(phones2), dtype=torch.int64, device=dev).unsqueeze(0))
             ges.append(ge)
-        toks, order = gpt.infer_batched(ids, prompts, berts, top_k=top_k, top_p=top_p, temperature=temperature,
-                                        repetition_penalty=repetition_penalty)
-        clips: List[Optional[AudioClip]] = [None] * len(texts)
-        for t, i in zip(toks, order.tolist()):
-            audio, _attn = vq.decode(t.view(1, 1, -1), ph2s[i], ges[i], noise_scale=noise_scale, speed=speed)
-            audio = audio[0, 0, :]
-            head = self._find_head_threshold_offsets(audio)
-            tail = self._find_tail_threshold_offsets(audio)
-            clips[i] = self._clip(audio[head:audio.numel() - tail].float().cpu().numpy(), texts[i])
+        _toks, clips = self.infer_phones_batched(ids, berts, prompts, ph2s, ges, top_k=top_k, top_p=top_p, temperature=temperature,
+                                                 noise_scale=noise_scale, speed=speed, gpt_model=gpt_model, sovits_model=sovits_model,
+                                                 trim_silence=True, texts=list(texts))
         return tuple(clips)

@@ -93,3 +93,50 @@ def test_streaming_overlap_matches_back_to_back(tmp_path):
         ref = voc.flow_dec(torch.randn(1, 192, T, generator=zg), torch.ones(1, 1, T), ge)[0, 0].float().cpu().numpy()
         assert clip.audio_data.shape == ref.shape
         assert float(abs(clip.audio_data - ref).max()) == 0.0
+
+
+def test_batched_pipeline_overlap_matches_back_to_back(tmp_path):
+    """infer_phones_batched: the SoVITS stage of the requests harvested at one read runs on the second stream behind the next
+    decode launch.  Same tokens and, with one utterance per vocoder group, bit-equal audio as the back-to-back order; default
+    grouping (padded groups) gives clips of the right lengths."""
+    from gsv_tts import TTS
+    from tests.test_loader_cpu import _upstream_gpt_names
+    cfg = syn.GPT_CONFIG_TINY
+    gsd = syn.gpt_state_dict(cfg, 0, 6.0)
+    gpt_path = tmp_path / "s1.ckpt"
+    torch.save({"config": cfg, "weight": _upstream_gpt_names(gsd, cfg["model"]["n_layer"])}, gpt_path)
+    model = dict(syn.SOVITS_MODEL["tiny"], version="v2Pro")
+    sd = dict(syn.sovits_flow_dec_state_dict(model, 0))
+    sd.update(syn.sovits_encp_state_dict(model, 0))
+    pth = tmp_path / "s2.pth"
+    torch.save({"config": {"model": model}, "weight": sd}, pth)
+    tts = TTS(gpt_cache=[(1, 256), (4, 256)], sovits_cache=[50, 55], device="cuda:0", dtype="float16")
+    tts.load_gpt_model(str(gpt_path))
+    tts.load_sovits_model(str(pth))
+    gpt = tts.gpt_models[str(gpt_path)].t2s_model
+    vq = tts.sovits_models[str(pth)].vq_model
+    g = torch.Generator().manual_seed(8)
+    n_req = 9
+    xs = [torch.randint(0, 732, (int(torch.randint(12, 30, (1,), generator=g)),), generator=g) for _ in range(n_req)]
+    ys = [torch.randint(0, 1024, (int(torch.randint(20, 40, (1,), generator=g)),), generator=g) for _ in range(n_req)]
+    bs = [torch.zeros(x.numel(), 1024) for x in xs]
+    ph2 = [x[x.numel() // 2:].cuda().view(1, -1) for x in xs]
+    ges = [torch.randn(1, model["gin_channels"], 1, generator=g).cuda().half() for _ in range(n_req)]
+    mx = [int(torch.randint(6, 40, (1,), generator=g)) for _ in range(n_req)]
+    runs = {}
+    for overlap in (False, True):
+        gpt.debug_seed, vq.debug_seed = 31, 5
+        runs[overlap] = tts.infer_phones_batched(xs, bs, ys, ph2, ges, max_new=mx, overlap=overlap, max_frames=1)
+    (t0, c0), (t1, c1) = runs[False], runs[True]
+    assert all(torch.equal(a, b) for a, b in zip(t0, t1)) and sum(t.numel() > 0 for t in t0) >= 5
+    for i, (a, b) in enumerate(zip(c0, c1)):
+        assert a.audio_data.shape == b.audio_data.shape == (2 * t0[i].numel() * 640,), i
+        assert a.audio_data.size == 0 or float(abs(a.audio_data - b.audio_data).max()) == 0.0, i     # EOS first: an empty clip
+    gpt.debug_seed, vq.debug_seed = 31, 5
+    t2, c2 = tts.infer_phones_batched(xs, bs, ys, ph2, ges, max_new=mx)
+    assert all(torch.equal(a, b) for a, b in zip(t0, t2))
+    for i, c in enumerate(c2):
+        assert c.audio_data.shape == (2 * t0[i].numel() * 640,)
+        n = c.audio_data.shape[0] - 20 * 640                       # the tail sees the group's padded frames instead of the signal's end
+        if n > 0:
+            assert float(abs(c.audio_data[:n] - c0[i].audio_data[:n]).max()) < 2e-3, i
