@@ -435,6 +435,16 @@ struct gsv_voc_ctx {
   int mrf_streams;                        // GSV_VOC_MRF=serial: one chain after the other on the caller's stream
   std::vector<void*> owned;               // library-owned copies of weights (channel-reversed pre / post of odd flows)
   int num_sms;
+  // CUDA graphs of the streaming shapes (B = 1, T <= 64: the 50 / 55-frame chunks of infer_stream, ~180 launches each):
+  // captured on the second call of a shape over library-owned input / output buffers, replayed afterwards
+  struct ChunkGraph {
+    int T, Tg, calls, failed;
+    cudaGraphExec_t exec;
+    void *z, *mask, *ge, *out;
+    long long launches;
+  };
+  std::vector<ChunkGraph> graphs;
+  int use_graph;                          // GSV_VOC_GRAPH=0: always launch kernel by kernel
 };
 
 namespace {
@@ -759,6 +769,23 @@ struct Arena {
   }
 };
 
+size_t voc_samples_per_frame(const gsv_voc_ctx* ctx) {
+  size_t spf = 1;
+  for (int i = 0; i < ctx->dims.n_ups; ++i) spf *= ctx->dims.upsample_rates[i];
+  return spf;
+}
+
+void voc_drop_graphs(gsv_voc_ctx* ctx) {
+  for (auto& g : ctx->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.z) cudaFree(g.z);
+    if (g.mask) cudaFree(g.mask);
+    if (g.ge) cudaFree(g.ge);
+    if (g.out) cudaFree(g.out);
+  }
+  ctx->graphs.clear();
+}
+
 template <typename T>
 int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const void* ge_, int B, int Tn, int Tg, void* out_,
                   cudaStream_t st) {
@@ -813,6 +840,7 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
   const size_t need = dry.off + 256;
   if (need > ctx->scratch_bytes) {
     GSV_CUDA(cudaStreamSynchronize(st));
+    voc_drop_graphs(ctx);                 // captured graphs point into the old scratch
     if (ctx->scratch) GSV_CUDA(cudaFree(ctx->scratch));
     ctx->scratch = nullptr; ctx->scratch_bytes = 0;
     GSV_CUDA(cudaMalloc(&ctx->scratch, need));
@@ -1036,6 +1064,8 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
   {
     const char* e = getenv("GSV_VOC_IMPL");
     ctx->use_umma = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
+    const char* eg = getenv("GSV_VOC_GRAPH");
+    ctx->use_graph = (eg && eg[0] == '0') ? 0 : 1;
     const char* ews = getenv("GSV_VOC_WS");
     ctx->use_ws = (ews && ews[0] == '0') ? 0 : ((ews && ews[0] == '2') ? 2 : 1);   // 2: also on small grids (tests)
   }
@@ -1057,6 +1087,7 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
 
 extern "C" int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias) {
   GSV_ARG(ctx && name && dev_weight);
+  voc_drop_graphs(ctx);                   // captured graphs hold the old pointers
   // flows applied after an odd number of Flips (reverse order: flow f sees NF - f flips): fold the channel reversal
   // into `pre` (along Cin) and `post` (along Cout, bias too), so that no convolution reads or writes reversed channels
   int f2 = -1;
@@ -1099,6 +1130,7 @@ extern "C" int gsv_voc_set_weight(gsv_voc_ctx* ctx, const char* name, const void
 
 extern "C" int gsv_voc_destroy(gsv_voc_ctx* ctx) {
   if (!ctx) return GSV_OK;
+  voc_drop_graphs(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->zero_bias) cudaFree(ctx->zero_bias);
   for (void* q : ctx->owned) cudaFree(q);
@@ -1119,13 +1151,90 @@ extern "C" int gsv_voc_set_debug_z(gsv_voc_ctx* ctx, void* dev_z) {
 
 extern "C" int64_t gsv_voc_launch_count(gsv_voc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int gsv_voc_graph_count(gsv_voc_ctx* ctx) {
+  int n = 0;
+  if (ctx)
+    for (auto& g : ctx->graphs) n += g.exec ? 1 : 0;
+  return n;
+}
+
+static int flow_dec_dispatch(gsv_voc_ctx* ctx, const void* z, const void* mask, const void* ge, int B, int T, int Tg, void* out,
+                             cudaStream_t st) {
+  if (ctx->dims.dtype == GSV_F16) return flow_dec_impl<__half>(ctx, z, mask, ge, B, T, Tg, out, st);
+  return flow_dec_impl<__nv_bfloat16>(ctx, z, mask, ge, B, T, Tg, out, st);
+}
+
 extern "C" int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const void* dev_mask, const void* dev_ge, int B, int T,
                                 int Tg, void* dev_out, void* stream) {
   GSV_ARG(ctx && dev_z_p && dev_mask && dev_ge && dev_out);
   GSV_ARG(B >= 1 && T >= 1 && (Tg == 1 || Tg == T));
-  if (ctx->dims.dtype == GSV_F16)
-    return flow_dec_impl<__half>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
-  return flow_dec_impl<__nv_bfloat16>(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(ctx->use_graph && B == 1 && T <= 64 && !ctx->debug_z)) return flow_dec_dispatch(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, st);
+  // streaming chunk: first call of a shape runs kernel by kernel (sizes the scratch, encodes the tensor maps), the second is
+  // captured over library-owned buffers, later ones copy in, replay, copy out
+  gsv_voc_ctx::ChunkGraph* g = nullptr;
+  for (auto& c : ctx->graphs)
+    if (c.T == T && c.Tg == Tg) g = &c;
+  if (!g) {
+    ctx->graphs.push_back(gsv_voc_ctx::ChunkGraph{T, Tg, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0});
+    g = &ctx->graphs.back();
+  }
+  g->calls += 1;
+  if (g->failed || g->calls == 1) return flow_dec_dispatch(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, st);
+  const size_t es = 2, zb = (size_t)ctx->dims.inter_channels * T * es, mb = (size_t)T * es,
+               gb = (size_t)ctx->dims.gin_channels * Tg * es, ob = (size_t)T * voc_samples_per_frame(ctx) * es;
+  if (!g->exec) {
+    const int key_T = g->T, key_Tg = g->Tg;
+    void *bz = nullptr, *bm = nullptr, *bg = nullptr, *bo = nullptr;
+    if (cudaMalloc(&bz, zb) != cudaSuccess || cudaMalloc(&bm, mb) != cudaSuccess || cudaMalloc(&bg, gb) != cudaSuccess ||
+        cudaMalloc(&bo, ob) != cudaSuccess) {
+      cudaGetLastError();
+      if (bz) cudaFree(bz);
+      if (bm) cudaFree(bm);
+      if (bg) cudaFree(bg);
+      g->failed = 1;
+      return flow_dec_dispatch(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, st);
+    }
+    g->z = bz; g->mask = bm; g->ge = bg; g->out = bo;
+    const long long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    // (the legacy default stream cannot be captured: callers on it keep the kernel-by-kernel path)
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    bool ok = ce == cudaSuccess;
+    int rc = GSV_OK;
+    if (ok) {
+      rc = flow_dec_dispatch(ctx, bz, bm, bg, 1, T, Tg, bo, st);
+      ce = cudaStreamEndCapture(st, &graph);
+      ok = ce == cudaSuccess && rc == GSV_OK && graph != nullptr;
+    }
+    if (!ok && getenv("GSV_VOC_GRAPH_DEBUG"))
+      fprintf(stderr, "[gsv] chunk graph T=%d not captured: %s (rc %d: %s)\n", T, cudaGetErrorString(ce), rc, rc ? gsv_last_error() : "");
+    // flow_dec_impl may have dropped and re-created the table entry's neighbours only on a scratch growth, which cannot happen
+    // here (the first call sized the scratch); look the entry up again all the same
+    g = nullptr;
+    for (auto& c : ctx->graphs)
+      if (c.T == key_T && c.Tg == key_Tg) g = &c;
+    if (!g) { if (graph) cudaGraphDestroy(graph); return flow_dec_dispatch(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, st); }
+    cudaGraphExec_t exec = nullptr;
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      g->failed = 1;
+      ctx->launches = l0;
+      return flow_dec_dispatch(ctx, dev_z_p, dev_mask, dev_ge, B, T, Tg, dev_out, st);
+    }
+    g->exec = exec;
+    g->launches = ctx->launches - l0;
+    ctx->launches = l0;
+  }
+  GSV_CUDA(cudaMemcpyAsync(g->z, dev_z_p, zb, cudaMemcpyDeviceToDevice, st));
+  GSV_CUDA(cudaMemcpyAsync(g->mask, dev_mask, mb, cudaMemcpyDeviceToDevice, st));
+  GSV_CUDA(cudaMemcpyAsync(g->ge, dev_ge, gb, cudaMemcpyDeviceToDevice, st));
+  GSV_CUDA(cudaGraphLaunch(g->exec, st));
+  GSV_CUDA(cudaMemcpyAsync(dev_out, g->out, ob, cudaMemcpyDeviceToDevice, st));
+  ctx->launches += g->launches;
+  return GSV_OK;
 }
 
 // ---- nn.Linear on the same tensor-core kernel (a convolution with one tap), for the GPT prefill and the

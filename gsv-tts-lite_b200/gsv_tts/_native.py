@@ -81,6 +81,7 @@ SYMBOLS = [
     ("gsv_voc_flow_dec", C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     ("gsv_voc_set_debug_z", C.c_int, [_P, _P]),
     ("gsv_voc_launch_count", C.c_int64, [_P]),
+    ("gsv_voc_graph_count", C.c_int, [_P]),
     ("gsv_encp_create", C.c_int, [C.POINTER(EncpDims), C.POINTER(_P)]),
     ("gsv_encp_set_weight", C.c_int, [_P, C.c_char_p, _P, _P]),
     ("gsv_encp_destroy", C.c_int, [_P]),

@@ -234,6 +234,9 @@ int gsv_voc_flow_dec(gsv_voc_ctx* ctx, const void* dev_z_p, const void* dev_mask
 /* Test hook: also return the flow output z [B][192][T] T (NULL to skip). */
 int gsv_voc_set_debug_z(gsv_voc_ctx* ctx, void* dev_z);
 int64_t gsv_voc_launch_count(gsv_voc_ctx* ctx);
+/* Streaming shapes (B = 1, T <= 64) are captured into CUDA graphs on their second call and replayed afterwards (the reference
+ * captures its SoVITS buckets at load, models.py:322-369); number of graphs currently instantiated (GSV_VOC_GRAPH=0 disables). */
+int gsv_voc_graph_count(gsv_voc_ctx* ctx);
 
 /* ======================================================================================
  * SoVITS prior encoder: semantic tokens -> z_p (the stage between the two hot paths)

@@ -142,3 +142,33 @@ def test_weight_stationary_kernel_on_large_grids(dev, key, monkeypatch):
     print(key, "max|ws - one-tile|", err)
     assert torch.isfinite(out["1"]).all()
     assert err < 1e-3
+
+
+def test_streaming_chunk_graph_replay_equals_kernel_launches(dev, monkeypatch):
+    """B = 1, T <= 64 (the 50 / 55-frame chunks of infer_stream): the second call of a shape is captured into a CUDA graph over
+    library-owned buffers, later calls replay it.  Every call must equal GSV_VOC_GRAPH=0 bit for bit, also after a larger call
+    has re-allocated the scratch in between (the graphs are dropped and re-captured)."""
+    from tests import gpu_harness as H
+    g = torch.Generator().manual_seed(21)
+    monkeypatch.setenv("GSV_VOC_GRAPH", "0")
+    plain, _, model = H.build_vocoder("v2Pro", torch.float16, dev)
+    monkeypatch.setenv("GSV_VOC_GRAPH", "1")
+    fd, _, _ = H.build_vocoder("v2Pro", torch.float16, dev)
+    l0 = fd.launch_count()
+    seq = [50, 50, 50, 55, 55, 50, 55, 200, 50, 50, 50]
+    side = torch.cuda.Stream(dev)                 # as TTS.infer_phones_stream runs it (the legacy default stream cannot be captured)
+    for i, T in enumerate(seq):
+        z = torch.randn(1, 192, T, generator=g).to(dev)
+        mask = torch.ones(1, 1, T, device=dev)
+        if i % 3 == 2:
+            mask[:, :, T - 7:] = 0
+        ge = torch.randn(1, model["gin_channels"], 1, generator=g).to(dev)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(side):
+            a = fd.flow_dec(z, mask, ge)
+        side.synchronize()
+        b = plain.flow_dec(z, mask, ge)
+        assert torch.equal(a, b), (i, T)
+    assert fd.launch_count() - l0 == plain.launch_count()           # a replay counts the kernels it runs
+    from gsv_tts import _native as N
+    assert N.lib().gsv_voc_graph_count(fd._ctx) == 1 and N.lib().gsv_voc_graph_count(plain._ctx) == 0   # T=50 re-captured after the T=200 call; 55 not yet

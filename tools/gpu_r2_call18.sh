@@ -6,4 +6,4 @@ tail -25 gpurun_out/r2c18_voc_tests.log
 for key in v2Pro v2ProPlus; do
 timeout 300 python tools/voc_speed.py $key 2>&1 | tail -8 | tee gpurun_out/r2c18_voc_speed_$key.log
 done
-GSV_VOC_WS=0 timeout 300 python tools/voc_speed.py v2Pro 2>&1 | tail -8 | tee gpurun_out/r2c18_voc_speed_v2Pro_ws0.log
+GSV_VOC_GRAPH=0 timeout 300 python tools/voc_speed.py v2Pro 2>&1 | tail -8 | head -3 | tee gpurun_out/r2c18_voc_speed_v2Pro_nograph.log

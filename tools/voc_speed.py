@@ -7,6 +7,8 @@ dev = torch.device("cuda:0")
 key = sys.argv[1] if len(sys.argv) > 1 else "v2Pro"
 fd, sd, model = H.build_vocoder(key, torch.bfloat16, dev)
 flop_frame = (813.1e6 if key != "v2ProPlus" else 1828.4e6) + 14.2e6
+side = torch.cuda.Stream(dev)      # a capturable stream: B=1, T<=64 shapes replay a CUDA graph from their second call on
+torch.cuda.set_stream(side)
 for B, T in [(1, 50), (1, 55), (1, 500), (8, 100), (16, 500), (64, 500)]:
     z = torch.randn(B, 192, T, device=dev, dtype=torch.bfloat16)
     mk = torch.ones(B, 1, T, device=dev, dtype=torch.bfloat16)
