@@ -20,6 +20,7 @@
 // and land in the layout the B operand is read from ([sequence][k], rows padded by 8 elements); the residual stream
 // (y1, y2, next input) stays fp32.  LayerNorm of sequence n is done once per CTA by warp n; attention of sequence n
 // by warps 2n and 2n+1.
+#include <cstdlib>
 #include <type_traits>
 
 #include "gpt_cluster_common.cuh"
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
   const int g = lane >> 2, t = lane & 3;                  // mma fragment coordinates
   const int H = p.H, L = p.L, V = p.V, S = p.S;
   const unsigned rank = cluster_rank();                  // = head index
-  const int cid = blockIdx.x / H;                         // cluster index: serves live sequences [cid*8, cid*8 + 8)
+  const int cid = blockIdx.x / H, ncl = gridDim.x / H;    // cluster index: serves the live sequences of rank cid, cid + ncl, ...
 
   // shared memory: inA[8][D] fp32 | xa[8][LDX] T | attb[8][LDX] T | hb[8][LDH] T | xin_s[D] | sampler scratch (+ logits) |
   //                red[2][16][RW] | ystage[8][32] fp32 | hstage[8][128] T | chunk ring
@@ -159,14 +160,15 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
   const T* const G2 = reinterpret_cast<const T*>(p.ln2_g);
   const T* const Be2 = reinterpret_cast<const T*>(p.ln2_b);
 
-  // ---- which sequences: the active slots number cid*8 .. cid*8 + 7 ----
+  // ---- which sequences: the active slots are dealt round-robin over the clusters (balanced attention / sampling work) ----
   if (tid < 32) {
     const int flag = tid < p.slots ? ld_cg(p.active + tid) : 0;
     const unsigned m = __ballot_sync(0xffffffffu, flag != 0);
-    const int pos = flag ? __popc(m & ((1u << tid) - 1u)) - cid * NB8 : -1;
+    const int rk = __popc(m & ((1u << tid) - 1u));        // rank of this slot among the live ones
+    const int pos = (flag && rk % ncl == cid) ? rk / ncl : -1;
     if (tid < NB8) { sh.slot[tid] = -1; sh.kv[tid] = 0; sh.alive[tid] = 0.f; }
     __syncwarp();
-    if (flag && pos >= 0 && pos < NB8) { sh.slot[pos] = tid; sh.kv[pos] = ld_cg(p.kv_len + tid); sh.alive[pos] = 1.f; }
+    if (pos >= 0 && pos < NB8) { sh.slot[pos] = tid; sh.kv[pos] = ld_cg(p.kv_len + tid); sh.alive[pos] = 1.f; }
   }
   // zero the staged operands once: columns of sequences that are not live must hold finite values
   for (int i = tid; i < (NB8 * LDX * 2 + NB8 * LDH) / 2; i += NT) reinterpret_cast<unsigned*>(xa)[i] = 0u;
@@ -639,7 +641,18 @@ int launch_cl8(gsv_gpt_ctx* ctx, int live, int n_steps, cudaStream_t st) {
                        (size_t)NB8 * 4 * GSV_HEAD_DIM * 2 + (size_t)NSLOT * chunk_bytes;
   GSV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   GSV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  const int n_clusters = (live + NB8 - 1) / NB8;
+  // Clusters: each streams ALL weights through its GPC's port whatever it serves, so fewer sequences per cluster only shorten
+  // its attention and sampling phases (5.0 us and 11 us of a 17 us layer / a token at eight sequences).  Measured us per step
+  // (clusters: 1 / 2 / 4 / 6 / 7): 8 sequences 425 / 358 / 341 / 333 / 336; 16: - / 423 / 361 / 354 / 349; 32: - / - / 432 /
+  // 400 / 392.  Two sequences per cluster, at most six clusters (seven are co-resident; the second stream's prompts and
+  // vocoder need SMs too).
+  int n_clusters = (live + 1) / 2;
+  n_clusters = n_clusters > 6 ? 6 : n_clusters;
+  {
+    const char* e = getenv("GSV_CL8_CLUSTERS");
+    if (e && atoi(e) > 0) n_clusters = atoi(e);
+  }
+  if (n_clusters * NB8 < live) n_clusters = (live + NB8 - 1) / NB8;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_clusters * H); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = bytes; cfg.stream = st;
