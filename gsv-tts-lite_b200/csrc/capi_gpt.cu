@@ -214,26 +214,27 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   for (int i = 0; i < ctx->p.slots; ++i) live += ctx->slot_live[i];
   if (live == 0) { gsv_set_error("gsv_gpt_decode: no slot has been prefilled"); return GSV_ERR_STATE; }
   // Measured on B200 (tools/decode_speed.py / bench.py, bf16, kv 164..364), us per step (tokens per second):
-  //   live   hx (head clusters)   ll (grid-wide LL)   cl (1 seq/cluster)   cl8 (8/cluster, mma)   gemm (multi-kernel, tcgen05 linears)
-  //    1     168 ( 5.9k)          293                 355                                         1760
-  //    2      -                   381                 359 ( 5.6k)
-  //    4      -                   595                 355 (11.3k)
-  //    6      -                    -                  357 (16.8k)   <- at most 7 sixteen-CTA clusters are co-resident; more run in waves
-  //    8      -                    -                  712 (11.2k)          430 (18.6k)            1567 ( 5.1k)
-  //   16      -                    -                   -                   423 (37.9k)
-  //   32      -                    -                ~2140 (14.9k)          444 (72.1k)            1583 (20.2k)
-  // -> 1: head-cluster kernel (grid-wide LL kernel where its clusters are not co-resident); 2..7: one cluster per sequence;
-  //    8 and more: eight per cluster on the tensor cores; the multi-kernel step where clusters of H CTAs cannot be
-  //    launched; the grid-barrier kernel for shapes none of them takes (GSV_DECODE_IMPL overrides).
+  //   live   hx (head clusters)   ll (grid-wide LL)   cl (1 seq/cluster)   cl8 (<= 8/cluster, mma)   gemm (multi-kernel, tcgen05 linears)
+  //    1     168 ( 5.9k)          293                 355                                            1760
+  //    2      -                   381                 350 ( 5.7k)          334 ( 6.0k)
+  //    4      -                   595                 352 (11.4k)          332 (12.1k)
+  //    6      -                    -                  354 (17.0k)          338 (17.7k)   <- at most 7 sixteen-CTA clusters are co-resident; more run in waves
+  //    8      -                    -                  712 (11.2k)          341 (23.5k)               1567 ( 5.1k)
+  //   16      -                    -                   -                   354 (45.2k)
+  //   32      -                    -                ~2140 (14.9k)          400 (79.9k)               1583 (20.2k)
+  //   (cl8 with the live sequences dealt over min(6, ceil(live / 2)) clusters)
+  // -> 1: head-cluster kernel (grid-wide LL kernel where its clusters are not co-resident); 2 and more: the tensor-core
+  //    cluster kernel (one cluster per sequence for models with fewer than 8 heads); the multi-kernel step where clusters of
+  //    H CTAs cannot be launched; the grid-barrier kernel for shapes none of them takes (GSV_DECODE_IMPL overrides).
   const bool explicit_impl = ctx->force_barrier_kernel || ctx->force_ll1 || ctx->force_gemm;
   // one live sequence: head-cluster kernel (2 grid-wide exchanges per layer instead of 5)
   if ((ctx->force_hx || (live == 1 && !explicit_impl && !ctx->use_cl && !ctx->use_cl8)) && gsv_gpt_hx_supported(ctx, live, n_steps)) {
     const int rc = gsv_gpt_decode_hx_launch(ctx, n_steps, (cudaStream_t)stream);
     if (rc != GSV_ERR_STATE || ctx->force_hx) return rc;      // GSV_ERR_STATE: clusters not co-resident here -> grid-wide kernel below
   }
-  if ((ctx->use_cl8 || (!explicit_impl && !ctx->use_cl && live >= 8)) && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8)
+  if ((ctx->use_cl8 || (!explicit_impl && !ctx->use_cl && live >= 2)) && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8)
     return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
-  if ((ctx->use_cl || (!explicit_impl && live >= 2 && live <= 7)) && gsv_gpt_cl_supported(ctx, live))
+  if ((ctx->use_cl || (!explicit_impl && live >= 2 && live <= 7)) && gsv_gpt_cl_supported(ctx, live))      // models with fewer than 8 heads
     return gsv_gpt_decode_cl_launch(ctx, live, n_steps, (cudaStream_t)stream);
   if (ctx->force_gemm || (live > 4 && !ctx->force_barrier_kernel && ctx->use_umma_linear))
     return gsv_gpt_decode_gemm_launch(ctx, n_steps, (cudaStream_t)stream);

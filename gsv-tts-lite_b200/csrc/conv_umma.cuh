@@ -371,9 +371,14 @@ __device__ __forceinline__ void epi_apply16(const ConvArgs<T>& a, int b, int t, 
     if (n8 > 1) stg256(a.out32 + o + 8, v + 8);
   }
   if (a.outT) {
+    // every activation here is max(v, slope * v) with 0 <= slope <= 1 (identity 1, leaky-ReLU 0.1 / 0.01, ReLU 0): two
+    // instructions per value instead of a chain of compares on the activation code
+    const float slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LRELU_01 ? 0.1f : (a.act == ACT_LRELU_001 ? 0.01f : 0.f));
+    const float zero = a.act == ACT_RELU ? 0.f : -0.f;      // x + (-0) is x for every x; ReLU's 0 * negative = -0 becomes +0 as fmaxf(v, 0) gives
     uint32_t u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) u[j] = Elem<T>::from_f2(act_apply(v[2 * j], a.act), act_apply(v[2 * j + 1], a.act));
+    for (int j = 0; j < 8; ++j)
+      u[j] = Elem<T>::from_f2(fmaxf(v[2 * j], slope * v[2 * j]) + zero, fmaxf(v[2 * j + 1], slope * v[2 * j + 1]) + zero);
     if (n8 > 1 && (a.o_ld & 15) == 0) stg256u(a.outT + o, u);           // 16-bit rows of 24 channels are only 16-byte aligned
     else {
       *reinterpret_cast<uint4*>(a.outT + o) = make_uint4(u[0], u[1], u[2], u[3]);
@@ -555,12 +560,14 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
       if (unit >= n_units) break;
       if (unit + NACC * (int)gridDim.x < n_units) l2_rows(unit + NACC * gridDim.x);
       // row of this thread in sub-tile `sub` of the unit: batch element, time step, validity, output offset
+      const int tile0 = unit * MS, b0 = tile0 / P.mt, m0 = tile0 - b0 * P.mt;      // one division per unit
       auto row_of = [&](int sub, int& b, int& t, size_t& o) -> bool {
-        const int tile = unit * MS + sub;
-        b = tile / P.mt;
-        t = (tile - b * P.mt) * BM + quarter * 32 + lane;
+        int m = m0 + sub;
+        b = b0;
+        while (m >= P.mt) { m -= P.mt; ++b; }
+        t = m * BM + quarter * 32 + lane;
         o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off + n0;
-        return tile < P.n_mtiles && t < ep.Tout;
+        return tile0 + sub < P.n_mtiles && t < ep.Tout;
       };
       EpiPre pre[2];
       {
