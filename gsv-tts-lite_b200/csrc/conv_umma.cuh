@@ -371,14 +371,10 @@ __device__ __forceinline__ void epi_apply16(const ConvArgs<T>& a, int b, int t, 
     if (n8 > 1) stg256(a.out32 + o + 8, v + 8);
   }
   if (a.outT) {
-    // every activation here is max(v, slope * v) with 0 <= slope <= 1 (identity 1, leaky-ReLU 0.1 / 0.01, ReLU 0): two
-    // instructions per value instead of a chain of compares on the activation code
-    const float slope = a.act == ACT_NONE ? 1.f : (a.act == ACT_LRELU_01 ? 0.1f : (a.act == ACT_LRELU_001 ? 0.01f : 0.f));
-    const float zero = a.act == ACT_RELU ? 0.f : -0.f;      // x + (-0) is x for every x; ReLU's 0 * negative = -0 becomes +0 as fmaxf(v, 0) gives
+    const Act act(a.act);
     uint32_t u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      u[j] = Elem<T>::from_f2(fmaxf(v[2 * j], slope * v[2 * j]) + zero, fmaxf(v[2 * j + 1], slope * v[2 * j + 1]) + zero);
+    for (int j = 0; j < 8; ++j) u[j] = Elem<T>::from_f2(act(v[2 * j]), act(v[2 * j + 1]));
     if (n8 > 1 && (a.o_ld & 15) == 0) stg256u(a.outT + o, u);           // 16-bit rows of 24 channels are only 16-byte aligned
     else {
       *reinterpret_cast<uint4*>(a.outT + o) = make_uint4(u[0], u[1], u[2], u[3]);

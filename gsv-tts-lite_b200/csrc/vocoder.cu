@@ -65,12 +65,18 @@ struct ConvArgs {
   int o_ld, o_off, o_rev;
 };
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == ACT_LRELU_01) return v > 0.f ? v : 0.1f * v;
-  if (act == ACT_LRELU_001) return v > 0.f ? v : 0.01f * v;
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  return v;
-}
+// Every activation here is max(v, slope * v) with 0 <= slope <= 1 (identity 1, leaky-ReLU 0.1 / 0.01, ReLU 0): two
+// instructions per value with slope decoded ONCE per epilogue call, instead of a chain of compares on the activation code
+// per value (30 % of the stall samples of a persistent-kernel epilogue).  `+ zero`: x + (-0) is x for every x, and ReLU's
+// 0 * negative = -0 becomes the +0 that fmaxf(v, 0) gives.
+struct Act {
+  float slope, zero;
+  __device__ __forceinline__ explicit Act(int act)
+      : slope(act == ACT_NONE ? 1.f : (act == ACT_LRELU_01 ? 0.1f : (act == ACT_LRELU_001 ? 0.01f : 0.f))),
+        zero(act == ACT_RELU ? 0.f : -0.f) {}
+  __device__ __forceinline__ float operator()(float v) const { return fmaxf(v, slope * v) + zero; }
+};
+__device__ __forceinline__ float act_apply(float v, int act) { return Act(act)(v); }
 
 template <typename T>
 __device__ __forceinline__ void conv_epilogue(const ConvArgs<T>& a, int b, int t, int co, float v) {
@@ -133,8 +139,9 @@ __device__ __forceinline__ void conv_epilogue_row8(const ConvArgs<T>& a, int b, 
     *reinterpret_cast<float4*>(a.out32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
   }
   if (a.outT) {
+    const Act act(a.act);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], a.act);
+    for (int j = 0; j < 8; ++j) v[j] = act(v[j]);
     *reinterpret_cast<uint4*>(a.outT + o) = pack8<T>(v);
   }
 }
