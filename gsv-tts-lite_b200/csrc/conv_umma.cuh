@@ -609,6 +609,223 @@ __global__ void __launch_bounds__(64 + 128 * NACC, 1) conv_umma_ws_kernel(const 
   }
 }
 
+// ---- one ResBlock unit in one persistent kernel ----------------------------------------------------------------------------
+//   xt = lrelu(conv_d(x_act) + b1);  x = conv_1(xt) + b2 + x        (modules.py:190-203, one iteration of the loop)
+// The persistent kernel above runs the two convolutions of a unit as two launches: the first one (16-bit in, 16-bit out) is
+// bound by accumulator hand-overs, and its output makes a round trip through HBM (4 of the 16 bytes a unit moves per
+// value).  Here the intermediate never leaves the SM: a tile computes 128 intermediate rows (MMA 1 over the dilated taps),
+// the four E1 warps add the bias, apply the leaky ReLU, zero the rows outside the signal (the second convolution's zero
+// padding) and write them as 16-bit K-major rows -- in the shared-memory swizzle the tensor core expects -- into one of two
+// staging tiles; MMA 2 reads that tile through row-shifted descriptors (taps of the dilation-1 convolution) and yields
+// R = 128 - (KW - 1) output rows, which the eight E2 warps (two accumulator sets) finish like any second convolution
+// (bias, fp32 residual, fp32 + activated 16-bit outputs).  Both weight sets stay resident; the MMA thread issues MMA 1 of
+// tile i + 1 before MMA 2 of tile i, so E1 of tile i overlaps it.  Tiles advance by R rows; channels C = Cin = Cout <= 64.
+template <typename T>
+struct ParamsRU {
+  CUtensorMap tm_a;      // activated input (C, T, B), box (BK, a_rows, 1)
+  CUtensorMap tm_w1;     // first convolution's weights (Cin, Cout, KW), box (BK, C, 1)
+  CUtensorMap tm_w2;     // second convolution's
+  int KW, dil;           // taps of both; dilation of the first (the second has dilation 1)
+  int Tn;                // time steps per batch element
+  int R;                 // output rows per tile = 128 - (KW - 1)
+  int mt, n_tiles;       // tiles per batch element, B * mt
+  int a_rows, a_stage_bytes, sa;
+  int a2_bytes;          // one staging tile: (128 + 16) rows of C channels, rounded up to 1024
+  const T* bias1;
+  int act1;              // activation between the two convolutions
+  ConvArgs<T> ep;        // the second convolution's epilogue
+};
+
+// BK = channels per K chunk = row width of the operand tiles: C for 64 / 32 / 16 channels; 64 for C = 48 (TMA zero-fills the
+// missing input channels, the staging tiles keep theirs at the zero they are initialised with).
+template <typename T, int C, int BK>
+__global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __grid_constant__ ParamsRU<T> P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int ROW_BYTES = BK * 2, W_BYTES = C * ROW_BYTES;
+  constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
+  constexpr int G = C / 16;
+  constexpr int TMEM_COLS = WsTmem<4 * C>::cols;
+  constexpr uint32_t SWZ = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);     // 16-byte chunk index ^= (offset >> 7) & SWZ
+  __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2],
+      w_full;
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t base_u = smem_u32(smem_raw);
+  const uint32_t tiles_w1 = base_u + ((1024u - (base_u & 1023u)) & 1023u);
+  const uint32_t tiles_w2 = tiles_w1 + (uint32_t)(P.KW * W_STAGE);
+  const uint32_t tiles_a = tiles_w2 + (uint32_t)(P.KW * W_STAGE);
+  const uint32_t tiles_a2 = tiles_a + (uint32_t)(P.sa * P.a_stage_bytes);
+  uint8_t* const a2_ptr = smem_raw + (tiles_a2 - base_u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SA = P.sa;
+  const int p2 = (P.KW - 1) / 2, p1 = (P.KW - 1) * P.dil / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], 4);
+      mbar_init(&a2_full[s], 4); mbar_init(&a2_empty[s], 1);
+      mbar_init(&acc2_full[s], 1); mbar_init(&acc2_empty[s], 4);
+    }
+    mbar_init(&w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.tm_w2) : "memory");
+  }
+  // rows 128.. of the staging tiles are read by the last taps of MMA 2 (their products only reach discarded output rows):
+  // keep them finite
+  for (int i = threadIdx.x; i < 2 * P.a2_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(a2_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: both weight sets once, then one activation box per tile ----
+      mbar_expect_tx(&w_full, (unsigned)(2 * P.KW * W_BYTES));
+      for (int j = 0; j < P.KW; ++j) {
+        tma_load_3d(tiles_w1 + (uint32_t)(j * W_STAGE), &P.tm_w1, &w_full, 0, 0, j);
+        tma_load_3d(tiles_w2 + (uint32_t)(j * W_STAGE), &P.tm_w2, &w_full, 0, 0, j);
+      }
+      pdl_wait();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / P.mt, m = tile - b * P.mt;
+        const int s = it % SA;
+        if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
+        mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
+        tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.ep.in_off, m * P.R - p2 - p1, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer: MMA 1 of tile lt, then MMA 2 of tile lt - 1 ----
+      constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(C >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+      auto mma2 = [&](int u) {
+        const int buf = u & 1;
+        mbar_wait(&a2_full[buf], (u >> 1) & 1);
+        if (u >= 2) mbar_wait(&acc2_empty[buf], ((u >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t a_base = tiles_a2 + (uint32_t)(buf * P.a2_bytes);
+        const uint32_t d = tmem_d + (uint32_t)(2 * C + buf * C);
+        for (int j = 0; j < P.KW; ++j) {
+          const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * ROW_BYTES));
+          const uint64_t bd = smem_desc<BK>(tiles_w2 + (uint32_t)(j * W_STAGE));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&a2_empty[buf]);
+        tc_commit(&acc2_full[buf]);
+      };
+      mbar_wait(&w_full, 0);
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1, s = lt % SA;
+        if (lt >= 2) mbar_wait(&acc1_empty[buf], ((lt >> 1) - 1) & 1);
+        mbar_wait(&a_full[s], (lt / SA) & 1);
+        tc_fence_after();
+        const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
+        const uint32_t d = tmem_d + (uint32_t)(buf * C);
+        for (int j = 0; j < P.KW; ++j) {
+          const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
+          const uint64_t bd = smem_desc<BK>(tiles_w1 + (uint32_t)(j * W_STAGE));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&a_empty[s]);
+        tc_commit(&acc1_full[buf]);
+        if (lt >= 1) mma2(lt - 1);
+      }
+      if (lt >= 1) mma2(lt - 1);
+      pdl_launch_dependents();
+    }
+  } else if (warp < 6) {
+    // ---- E1: intermediate rows -> bias, leaky ReLU, zero outside the signal, 16-bit, swizzled K-major staging tile ----
+    const int quarter = warp & 3, r = quarter * 32 + lane;
+    const Act act(P.act1);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int b = tile / P.mt, m = tile - b * P.mt;
+      const int t_int = m * P.R - p2 + r;
+      const bool inside = t_int >= 0 && t_int < P.Tn;
+      mbar_wait(&acc1_full[buf], (lt >> 1) & 1);
+      if (lt >= 2) mbar_wait(&a2_empty[buf], ((lt >> 1) - 1) & 1);      // MMA 2 of tile lt - 2 has read this staging tile
+      tc_fence_after();
+      uint8_t* const tile_ptr = a2_ptr + (size_t)buf * P.a2_bytes;
+      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        uint32_t v[16];
+        tc_ld16(tbase + (uint32_t)(g * 16), v);
+        tc_ld_wait();
+        uint32_t bw[8], u[8];
+        ldg256u(P.bias1 + g * 16, bw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 f = Elem<T>::to_f2(bw[j]);
+          const float x0 = act(__uint_as_float(v[2 * j]) + f.x), x1 = act(__uint_as_float(v[2 * j + 1]) + f.y);
+          u[j] = inside ? Elem<T>::from_f2(x0, x1) : 0u;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t off = (uint32_t)(r * ROW_BYTES + (g * 2 + h) * 16);
+          off ^= ((off >> 7) & SWZ) << 4;
+          *reinterpret_cast<uint4*>(tile_ptr + off) = make_uint4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&a2_full[buf]); mbar_arrive(&acc1_empty[buf]); }
+    }
+  } else {
+    // ---- E2: the second convolution's epilogue on R output rows per tile; two accumulator sets ----
+    const int set = (warp - 6) >> 2, quarter = warp & 3, r = quarter * 32 + lane;
+    const ConvArgs<T>& ep = P.ep;
+    pdl_wait();
+    int use = 0;
+    for (int lt = set;; lt += 2, ++use) {
+      const int tile = blockIdx.x + lt * gridDim.x;
+      if (tile >= P.n_tiles) break;
+      const int b = tile / P.mt, m = tile - b * P.mt;
+      const int t = m * P.R + r;
+      const bool ok = r < P.R && t < P.Tn;
+      const size_t o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off;
+      EpiPre pre[2];
+      if (ok) epi_prefetch16<T>(ep, o, 2, pre[0]);
+      mbar_wait(&acc2_full[set], use & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * C + set * C);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (g + 1 < G && ok) epi_prefetch16<T>(ep, o + (g + 1) * 16, 2, pre[(g + 1) & 1]);
+        uint32_t v[16];
+        tc_ld16(tbase + (uint32_t)(g * 16), v);
+        tc_ld_wait();
+        if (ok) epi_apply16<T>(ep, b, t, g * 16, o + g * 16, v, pre[g & 1], 2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty[set]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host: tensor-map encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

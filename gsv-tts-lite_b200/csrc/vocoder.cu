@@ -437,6 +437,7 @@ struct gsv_voc_ctx {
   size_t op_index;
   int use_umma;                           // GSV_VOC_IMPL=cuda disables the tensor-core path (A/B checks)
   int use_ws;                             // GSV_VOC_WS=0 disables the weight-stationary persistent kernel (A/B checks)
+  int use_fuse;                           // GSV_VOC_FUSE=0: the two convolutions of a ResBlock unit as two launches; 2: fused on small grids too (tests)
   cudaStream_t side[2];                   // the three ResBlocks of an MRF stage run as three concurrent chains
   cudaEvent_t ev_fork, ev_join[2];
   int mrf_streams;                        // GSV_VOC_MRF=serial: one chain after the other on the caller's stream
@@ -712,6 +713,84 @@ int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const Con
 #undef GSV_WS
   if (rc) return rc;
   GSV_CHECK_LAUNCH();
+  return GSV_OK;
+}
+
+// ---- one ResBlock unit (two convolutions) in one persistent kernel (conv_umma.cuh, resunit_umma_kernel) ---------------------
+template <typename T, int C, int BK>
+int launch_ru_inst(const umma::ParamsRU<T>& P, int grid, size_t smem, cudaStream_t st) {
+  static unsigned long long attr_set = 0ull;        // one bit per device
+  int dev = 0;
+  GSV_CUDA(cudaGetDevice(&dev));
+  if (!((attr_set >> (dev & 63)) & 1ull)) {
+    GSV_CUDA(cudaFuncSetAttribute(umma::resunit_umma_kernel<T, C, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsBudget));
+    attr_set |= 1ull << (dev & 63);
+  }
+  static int use_pdl = -1;
+  if (use_pdl < 0) { const char* e = getenv("GSV_PDL"); use_pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 128 * 3); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::resunit_umma_kernel<T, C, BK>, P));
+  return GSV_OK;
+}
+
+// a1: xt = act(conv_d(in) + b1) -> 16-bit; a2: x = conv_1(xt) + b2 (+ residual ...), reading a1's output.  Returns GSV_OK and
+// sets *done when the pair was launched as one kernel; leaves *done = false when the shapes do not qualify (the caller then
+// launches the two convolutions).  a2.outT must not alias a1.in (tiles read their neighbours' input rows).
+template <typename T>
+int launch_resunit(gsv_voc_ctx* ctx, const ConvArgs<T>& a1, const ConvArgs<T>& a2, cudaStream_t st, bool* done) {
+  *done = false;
+  const int C = a1.Cin, KW = a1.KW;
+  if (!ctx->use_umma || !ctx->use_fuse || !(C == 64 || C == 48 || C == 32 || C == 16) || a1.Cout != C || a2.Cin != C || a2.Cout != C ||
+      a2.KW != KW || a2.dil != 1 || a1.stride != 1 || a2.stride != 1 || (KW & 1) == 0 || KW > 15 || a1.in_ld != C || a1.in_off != 0 ||
+      a1.in_rev || a1.o_rev || a2.in_rev || a2.o_rev || a2.in != a1.outT || a1.add || a1.res32 || a1.acc32 || a1.mask || a1.out32 ||
+      a2.mask || a2.add || a2.o_ld != C || a2.o_off != 0 || a1.Tout != a2.Tout || a1.Tin != a1.Tout || (KW - 1) * a1.dil > 120 ||
+      (const void*)a2.outT == (const void*)a1.in)
+    return GSV_OK;
+  const int Tn = a1.Tout, R = umma::BM - (KW - 1);
+  const int mt = (Tn + R - 1) / R;
+  const long long n_tiles = (long long)a1.B * mt;
+  if (ctx->use_fuse != 2 && n_tiles < 2LL * ctx->num_sms) return GSV_OK;
+  const int bk = C == 48 ? 64 : C;          // channels per K chunk = row width of the operand tiles
+  const int a_rows = umma::BM + (KW - 1) * a1.dil;
+  const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
+  const int w_stage = (C * bk * 2 + 1023) & ~1023;
+  const int a2_bytes = ((umma::BM + 16) * bk * 2 + 1023) & ~1023;
+  const size_t fixed = (size_t)2 * KW * w_stage + (size_t)2 * a2_bytes + 1024;
+  int sa = 4;
+  while (sa > 2 && fixed + (size_t)sa * a_stage > kWsBudget) --sa;
+  if (fixed + (size_t)sa * a_stage > kWsBudget) return GSV_OK;
+  umma::ParamsRU<T> P;
+  const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
+  int rc = umma::make_map(&P.tm_a, bf16, a1.in, (uint64_t)C, (uint64_t)Tn, (uint64_t)a1.B, (uint64_t)C * 2, (uint64_t)Tn * C * 2,
+                          (uint32_t)bk, (uint32_t)a_rows);
+  if (rc) return rc;
+  if ((rc = umma::make_map(&P.tm_w1, bf16, a1.w, (uint64_t)C, (uint64_t)C, (uint64_t)KW, (uint64_t)C * 2, (uint64_t)a1.w_tap * 2,
+                           (uint32_t)bk, (uint32_t)C)))
+    return rc;
+  if ((rc = umma::make_map(&P.tm_w2, bf16, a2.w, (uint64_t)C, (uint64_t)C, (uint64_t)KW, (uint64_t)C * 2, (uint64_t)a2.w_tap * 2,
+                           (uint32_t)bk, (uint32_t)C)))
+    return rc;
+  P.KW = KW; P.dil = a1.dil; P.Tn = Tn; P.R = R; P.mt = mt; P.n_tiles = (int)n_tiles;
+  P.a_rows = a_rows; P.a_stage_bytes = a_stage; P.sa = sa; P.a2_bytes = a2_bytes;
+  P.bias1 = a1.bias; P.act1 = a1.act;
+  P.ep = a2;
+  const int grid = n_tiles < ctx->num_sms ? (int)n_tiles : ctx->num_sms;
+  const size_t smem = fixed + (size_t)sa * a_stage;
+  if (C == 64) rc = launch_ru_inst<T, 64, 64>(P, grid, smem, st);
+  else if (C == 48) rc = launch_ru_inst<T, 48, 64>(P, grid, smem, st);
+  else if (C == 32) rc = launch_ru_inst<T, 32, 32>(P, grid, smem, st);
+  else rc = launch_ru_inst<T, 16, 16>(P, grid, smem, st);
+  if (rc) return rc;
+  GSV_CHECK_LAUNCH();
+  ctx->op_index += 2;                       // the two call sites' tensor-map cache slots stay theirs
+  ctx->launches += 1;
+  *done = true;
   return GSV_OK;
 }
 
@@ -996,27 +1075,40 @@ int flow_dec_impl(gsv_voc_ctx* ctx, const void* z_p_, const void* mask_, const v
       const int k = D.resblock_kernel_sizes[j];
       const std::string R = "dec.resblocks." + std::to_string(i * NK + j) + ".";
       cudaStream_t sj = (fork && j > 0) ? ctx->side[j - 1] : st;
+      T* cur = XA0;
       for (int c = 0; c < 3; ++c) {
         const int dl = D.resblock_dilations[j][c];
         Weight w1, w2;
         if ((rc = W(R + "convs1." + std::to_string(c), w1))) return rc;
         if ((rc = W(R + "convs2." + std::to_string(c), w2))) return rc;
-        {   // xt = lrelu(conv_d(lrelu(x)))
-          ConvArgs<T> a = base_args();
-          a.in = c == 0 ? XA0 : XAJ[j]; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k; a.dil = dl;
-          a.w = reinterpret_cast<const T*>(w1.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w1.b);
-          a.outT = TA[j]; a.act = ACT_LRELU_01; a.o_ld = ch;
-          if ((rc = launch_conv<T>(ctx, a, sj))) return rc;
+        // The 16-bit activated copy of x lives in `cur` (the stage input XA0, then TA[j] or XAJ[j]).  A fused unit writes the
+        // new copy to the other buffer (its tiles read their neighbours' input rows); the two-launch path needs a buffer for
+        // the intermediate and may write the new copy back in place (its second convolution does not read `cur`).
+        T* const f1 = cur == TA[j] ? XAJ[j] : TA[j];
+        T* const f2 = cur == XA0 ? XAJ[j] : nullptr;                  // a second free buffer exists only while cur is the stage input
+        ConvArgs<T> a1 = base_args();                                 // xt = lrelu(conv_d(lrelu(x)))
+        a1.in = cur; a1.in_ld = ch; a1.Tin = a1.Tout = Tcur; a1.Cin = ch; a1.Cout = ch; a1.KW = k; a1.dil = dl;
+        a1.w = reinterpret_cast<const T*>(w1.w); a1.w_tap = (long long)ch * ch; a1.bias = reinterpret_cast<const T*>(w1.b);
+        a1.outT = f1; a1.act = ACT_LRELU_01; a1.o_ld = ch;
+        ConvArgs<T> a2 = base_args();                                 // x = conv_1(xt) + x (the last one leaves the ResBlock's output in its fp32 stream)
+        a2.in = f1; a2.in_ld = ch; a2.Tin = a2.Tout = Tcur; a2.Cin = ch; a2.Cout = ch; a2.KW = k;
+        a2.w = reinterpret_cast<const T*>(w2.w); a2.w_tap = (long long)ch * ch; a2.bias = reinterpret_cast<const T*>(w2.b);
+        a2.res32 = c == 0 ? X0 : XJ[j]; a2.o_ld = ch;
+        a2.out32 = XJ[j];
+        T* next_cur = cur;
+        bool fused = false;
+        {
+          ConvArgs<T> f = a2;                                         // fused: intermediate in shared memory, new copy -> f1
+          if (c < 2) { f.outT = f1; f.act = ACT_LRELU_01; }
+          if ((rc = launch_resunit<T>(ctx, a1, f, sj, &fused))) return rc;
+          if (fused) next_cur = f1;
         }
-        {   // x = conv_1(xt) + x   (the last one leaves the ResBlock's output in its fp32 stream)
-          ConvArgs<T> a = base_args();
-          a.in = TA[j]; a.in_ld = ch; a.Tin = a.Tout = Tcur; a.Cin = ch; a.Cout = ch; a.KW = k;
-          a.w = reinterpret_cast<const T*>(w2.w); a.w_tap = (long long)ch * ch; a.bias = reinterpret_cast<const T*>(w2.b);
-          a.res32 = c == 0 ? X0 : XJ[j]; a.o_ld = ch;
-          a.out32 = XJ[j];
-          if (c < 2) { a.outT = XAJ[j]; a.act = ACT_LRELU_01; }
-          if ((rc = launch_conv<T>(ctx, a, sj))) return rc;
+        if (!fused) {
+          if (c < 2) { a2.outT = f2 ? f2 : cur; a2.act = ACT_LRELU_01; next_cur = a2.outT; }
+          if ((rc = launch_conv<T>(ctx, a1, sj))) return rc;
+          if ((rc = launch_conv<T>(ctx, a2, sj))) return rc;
         }
+        cur = next_cur;
       }
       if (fork && j > 0) {
         GSV_CUDA(cudaEventRecord(ctx->ev_join[j - 1], sj));
@@ -1073,6 +1165,8 @@ extern "C" int gsv_voc_create(const gsv_voc_dims* dims, gsv_voc_ctx** out) {
     ctx->use_umma = (e && strcmp(e, "cuda") == 0) ? 0 : 1;
     const char* eg = getenv("GSV_VOC_GRAPH");
     ctx->use_graph = (eg && eg[0] == '0') ? 0 : 1;
+    const char* ef = getenv("GSV_VOC_FUSE");
+    ctx->use_fuse = (ef && ef[0] == '0') ? 0 : ((ef && ef[0] == '2') ? 2 : 1);
     const char* ews = getenv("GSV_VOC_WS");
     ctx->use_ws = (ews && ews[0] == '0') ? 0 : ((ews && ews[0] == '2') ? 2 : 1);   // 2: also on small grids (tests)
   }

@@ -172,3 +172,43 @@ def test_streaming_chunk_graph_replay_equals_kernel_launches(dev, monkeypatch):
     assert fd.launch_count() - l0 == plain.launch_count()           # a replay counts the kernels it runs
     from gsv_tts import _native as N
     assert N.lib().gsv_voc_graph_count(fd._ctx) == 1 and N.lib().gsv_voc_graph_count(plain._ctx) == 0   # T=50 re-captured after the T=200 call; 55 not yet
+
+
+@pytest.mark.parametrize("name,key", [("tiny", "tiny"), ("v2pro", "v2Pro"), ("v2proplus", "v2ProPlus")])
+def test_fused_resblock_unit_forced_matches_golden(dev, name, key, monkeypatch):
+    """GSV_VOC_FUSE=2 runs every ResBlock unit with 64 / 48 / 32 / 16 channels as ONE persistent kernel (first convolution, leaky
+    ReLU and zero padding of the intermediate in shared memory, second convolution + residual), small grids included: same
+    goldens, same bounds."""
+    from tests import gpu_harness as H
+    monkeypatch.setenv("GSV_VOC_FUSE", "2")
+    dtype = torch.float16
+    e = H.vocoder_error(name, key, dtype, dev)
+    print(name, {k: v for k, v in e.items()})
+    tol_golden = TOL_AUDIO[dtype]
+    if e["ref16_vs_golden"] is not None:
+        tol_golden = max(tol_golden, e["ref16_vs_golden"])
+    assert e["launches"] < 178                      # some pairs of launches became one
+    assert e["audio_vs_golden"] < tol_golden
+    assert e["audio_vs_oracle"] < TOL_AUDIO[dtype]
+
+
+@pytest.mark.parametrize("T", [1, 7, 129, 200])
+def test_fused_resblock_unit_edges_equal_two_launches(dev, T, monkeypatch):
+    """Ragged lengths (tiles advance by 128 - (k - 1) rows; rows outside the signal are the second convolution's zero padding):
+    the fused unit issues the same MMAs per output as the two-launch path, so the two are bit-equal."""
+    from tests import gpu_harness as H
+    g = torch.Generator().manual_seed(300 + T)
+    model = syn.SOVITS_MODEL["v2Pro"]
+    z_p = torch.randn(2, 192, T, generator=g).to(dev)
+    mask = torch.ones(2, 1, T, device=dev)
+    if T > 2:
+        mask[1, :, T - T // 3:] = 0
+    ge = torch.randn(2, model["gin_channels"], 1, generator=g).to(dev)
+    out = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("GSV_VOC_FUSE", mode)
+        fd, _, _ = H.build_vocoder("v2Pro", torch.float16, dev)
+        out[mode] = fd.flow_dec(z_p, mask, ge).float().clone()
+    err = float((out["0"] - out["2"]).abs().max())
+    print("T", T, "max|fused - two launches|", err)
+    assert torch.isfinite(out["2"]).all() and err == 0.0
