@@ -392,6 +392,7 @@ def main():
         return float(t.item()), wall, launches
 
     for _ in range(args.warmup):                             # both input kinds: host inputs allocate their own device copies
+        flush.zero_()                                        # (first touch of the flush buffer belongs to the warm-up too)
         utterance(dev_in)
         utterance(host_in)
     sampler.on = not os.environ.get("BENCH_NO_SAMPLER")
