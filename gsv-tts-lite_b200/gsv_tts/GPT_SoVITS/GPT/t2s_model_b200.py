@@ -287,6 +287,17 @@ class Text2SemanticDecoder(nn.Module):
                                      self._h_tokens.data_ptr() if tokens else None, 0, n_slots, self._stream()))
         torch.cuda.current_stream(self._device).synchronize()
 
+    def _read_enqueue(self, n_slots: int):
+        """Asynchronous half of ``_read``: the copies into the pinned host buffers are enqueued on the current stream and an
+        event is recorded behind them; ``_read_wait`` blocks on that event only, so launches enqueued after this call run on."""
+        N.check(N.lib().gsv_gpt_read(self._ctx, self._h_ngen.data_ptr(), self._h_active.data_ptr(), self._h_tokens.data_ptr(),
+                                     0, n_slots, self._stream()))
+        self._read_event = torch.cuda.Event()
+        self._read_event.record(torch.cuda.current_stream(self._device))
+
+    def _read_wait(self):
+        self._read_event.synchronize()
+
     def _release_all(self):
         for s in range(self._max_slots):
             N.check(N.lib().gsv_gpt_release_slot(self._ctx, s, self._stream()))
@@ -350,21 +361,33 @@ class Text2SemanticDecoder(nn.Module):
             self._single_setup(x, y, bert_feature, top_k, top_p, temperature, repetition_penalty,
                                initial_suppression_steps, force_steps)
         first, pre_chunk, idx = True, None, 0
+        launched = 0                                  # decode steps enqueued so far
 
-        def launch(done: int) -> bool:
+        def launch() -> bool:
+            nonlocal launched
             n = stream_chunk
             if force_steps is not None:
-                n = min(n, force_steps - done)
+                n = min(n, force_steps - launched)
             if n <= 0:
                 return False
             with self._on_stream(hp):
                 self._decode(n)
+            launched += n
             return True
 
-        more = launch(0)
-        while more:
+        def enqueue_read():
             with self._on_stream(hp):
-                self._read(1)
+                self._read_enqueue(1)
+
+        # Two launches are kept in the stream: while launch k runs, launch k+1 is already queued behind the copy of k's
+        # results, so the GPU never waits for the host between chunks (a launch that finds its sequence stopped returns at
+        # once).  Stream order: decode 1, read 1, decode 2 | read 2, decode 3 | ...
+        in_flight = launch()
+        if in_flight:
+            enqueue_read()
+            queued = launch()
+        while in_flight:
+            self._read_wait()
             n_gen = int(self._h_ngen[0])            # s0 + decode steps so far
             active = int(self._h_active[0])
             toks = self._h_tokens[0, :n_gen].to(torch.int64)
@@ -380,10 +403,14 @@ class Text2SemanticDecoder(nn.Module):
             if idx % stream_chunk == 0 and idx > 0:
                 chunk = toks[1:idx + 1].to(self._device).view(1, 1, -1)
                 self._mark_chunk_ready()
-            # the next chunk is launched BEFORE this one is handed out: whatever the caller does with it (prior encoder and
-            # vocoder, on its own stream after `chunk_ready` and `hold_until_decode_resident`) overlaps the decode instead of
-            # delaying it.  The single-sequence kernel occupies 64 SMs; the other 84 are the caller's.
-            more = bool(active) and launch(idx)
+            in_flight = bool(active) and queued
+            if in_flight:
+                enqueue_read()                        # behind the launch already queued
+            # The chunk is handed out with the next launch running or queued: whatever the caller does with it (prior encoder
+            # and vocoder, on its own stream after `chunk_ready` and `hold_until_decode_resident`) overlaps the decode instead
+            # of delaying it.  The launch after that is queued when the caller comes back -- after it has taken its residency
+            # hold, which must not wait for a launch that cannot start yet.  The single-sequence kernel occupies 64 SMs; the
+            # other 84 are the caller's.
             if chunk is not None:
                 if pre_chunk is not None:
                     yield pre_chunk, False
@@ -392,8 +419,11 @@ class Text2SemanticDecoder(nn.Module):
                     first = False
                     yield pre_chunk, False
                     pre_chunk = None
-        with self._on_stream(hp):
-            self._read(1)
+            if in_flight:
+                queued = launch()
+        if not launched:                              # nothing to decode (force_steps = 0): the first sampled token alone
+            enqueue_read()
+            self._read_wait()
         n_gen = int(self._h_ngen[0])
         toks = self._h_tokens[0, :n_gen].to(torch.int64)
         out = toks[1:].to(self._device).view(1, 1, -1)

@@ -80,6 +80,8 @@ def make_model(script, n_iter, log):
     m._single_setup = rt.single_setup
     m._decode = rt.decode
     m._read = rt.read
+    m._read_enqueue = lambda n_slots: (rt.read(n_slots), log.append(("read",)))      # snapshot at its place in the stream order
+    m._read_wait = lambda: None
     m._mark_chunk_ready = lambda: log.append(("ready",))
     # stream plumbing of the real class (a high-priority CUDA stream for the decode launches): no-ops here
     import contextlib
@@ -120,7 +122,7 @@ def test_infer_stream_yields_match_reference_loop(boost, eos_at, n_iter, force):
     assert got == want
 
 
-def test_next_chunk_is_launched_before_the_previous_one_is_handed_out():
+def test_two_launches_stay_in_flight_and_chunks_are_handed_out_behind_them():
     chunk = 10
     script = scripted(64, 45, 3)
     log = []
@@ -129,13 +131,20 @@ def test_next_chunk_is_launched_before_the_previous_one_is_handed_out():
     for t, f in m.infer_stream(x, x, torch.zeros(1, 4, 1024), stream_chunk=chunk):
         log.append(("yield", t.numel(), f))
     kinds = [e[0] for e in log]
-    # every chunk (the boosted first one, and the later ones handed out one chunk late as the reference does) is handed out
-    # only after the next decode launch is in flight: the single-sequence kernel takes its 64 SMs first, the caller's
-    # vocoder stream is held until it has them (gsv_gpt_wait_resident)
-    assert kinds[:4] == ["decode", "ready", "decode", "yield"]
+    # stream order: decode 1, read 1, decode 2 | read 2, <chunk handed out>, decode 3 | ...: while launch k runs, launch k+1 is
+    # queued behind the copy of k's results, so the GPU never waits for the host; a chunk is handed out with the next launch
+    # running (its read already enqueued) and the one after that is queued when the caller comes back -- after the caller's
+    # residency hold (gsv_gpt_wait_resident), which must not wait for a launch that cannot start yet
+    assert kinds[:7] == ["decode", "read", "decode", "ready", "read", "yield", "decode"]
     ys = [i for i, k in enumerate(kinds) if k == "yield"]
-    for i in ys[1:-1]:
-        assert kinds[i - 1] == "decode" and kinds[i - 2] == "ready"
-    # the final chunk arrives with nothing in flight
-    assert kinds[-2:] == ["ready", "yield"] and log[-1][2] is True and "decode" not in kinds[ys[-2] + 1:]
-    assert sum(1 for k in kinds if k == "decode") == 5            # 45 steps in launches of 10
+    for i in ys[:-1]:
+        n_dec = kinds[:i].count("decode")
+        n_chunks_done = kinds[:i].count("ready")
+        assert n_dec == n_chunks_done + 1                          # exactly one launch beyond the chunks already complete
+        assert kinds[i + 1] == "decode"                            # the next one is queued as soon as the caller returns
+    # a read is always enqueued between two launches (results of launch k are copied before launch k+1 may change them)
+    for a, b in zip([i for i, k in enumerate(kinds) if k == "decode"][:-1], [i for i, k in enumerate(kinds) if k == "decode"][1:]):
+        assert "read" in kinds[a:b]
+    # EOS at step 45: five launches of 10 steps do the work, the sixth was queued speculatively and finds the sequence stopped
+    assert sum(1 for k in kinds if k == "decode") == 6
+    assert kinds[-2:] == ["ready", "yield"] and log[-1][2] is True
