@@ -494,19 +494,50 @@ class Text2SemanticDecoder(nn.Module):
         side = self._side_stream() if self.overlap_refill else None
         to_begin = []                     # (slot, request) freed at the last read: their prompts start behind the next decode launch
         pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
-        while any(o >= 0 for o in owner) or pending or to_begin:
+        def harvest(skip):
+            nonlocal nxt
+            for s in range(slots):
+                if s in skip or owner[s] < 0 or int(self._h_active[s]):
+                    continue
+                n_gen = int(self._h_ngen[s])
+                toks = self._h_tokens[s, 1:n_gen].to(torch.int64)
+                if toks.numel() and int(toks[-1]) == self.EOS:
+                    toks = toks[:-1]
+                results.append(toks.to(self._device))
+                order.append(owner[s])
+                if on_finish is not None:
+                    on_finish(owner[s], results[-1])
+                owner[s] = FREE
+                if nxt < B:
+                    if side is None:
+                        start(s, nxt)
+                        owner[s] = nxt
+                    else:
+                        to_begin.append((s, nxt))
+                        owner[s] = REFILLING
+                    nxt += 1
+
+        # With the overlapped refill the loop is pipelined one launch deep: launch k+1 is enqueued BEFORE the results of launch
+        # k are waited for (stream order: decode k, read k, decode k+1, read k+1, ...), so the GPU does not idle while the host
+        # harvests.  A launch enqueued over slots that turn out to have finished simply skips them (the kernels look at
+        # `active` on the device); a slot published behind launch k+1 is not in the copy of launch k's results (`fresh`).
+        read_pending = False
+        keep_alive = None                 # prompt tensors of refills published one iteration ago (needed until that launch ran)
+        while any(o >= 0 for o in owner) or pending or to_begin or read_pending:
             launched = any(o >= 0 for o in owner)
             if launched:
                 self._decode(interval)
             # second half of the refills begun one launch ago: behind the decode launch just enqueued, so their prompts were
             # computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
+            fresh = set()
             for slot, r, keep, ev in pending:
                 self._wait_on_current_stream(ev)
                 audit(slot, r)
                 self._prefill_finish(slot, keep[1], sampling(r))
                 owner[slot] = r
+                fresh.add(slot)
             done_refills, pending = pending, []
-            # first half of the refills freed at the last read, on the second stream -- held until the decode launch above
+            # first half of the refills freed at the last harvest, on the second stream -- held until the decode launch above
             # has its clusters resident (hold_until_decode_resident): a stream of small prompt kernels must not be what a
             # 16-CTA cluster waits behind
             if to_begin:
@@ -519,25 +550,17 @@ class Text2SemanticDecoder(nn.Module):
                 to_begin = []
             if on_launch is not None:
                 on_launch(launched)
-            self._read(slots)
-            del done_refills              # their prompt tensors were needed until the second half had run
-            for s in range(slots):
-                if owner[s] >= 0 and not int(self._h_active[s]):
-                    n_gen = int(self._h_ngen[s])
-                    toks = self._h_tokens[s, 1:n_gen].to(torch.int64)
-                    if toks.numel() and int(toks[-1]) == self.EOS:
-                        toks = toks[:-1]
-                    results.append(toks.to(self._device))
-                    order.append(owner[s])
-                    if on_finish is not None:
-                        on_finish(owner[s], results[-1])
-                    owner[s] = FREE
-                    if nxt < B:
-                        if side is None:
-                            start(s, nxt)
-                            owner[s] = nxt
-                        else:
-                            to_begin.append((s, nxt))
-                            owner[s] = REFILLING
-                        nxt += 1
+            if side is None:
+                self._read(slots)
+                del done_refills          # their prompt tensors were needed until the second half had run
+                harvest(())
+            else:
+                if read_pending:
+                    self._read_wait()     # results of the PREVIOUS launch; the one enqueued above is running or queued
+                    keep_alive = None
+                    harvest(fresh)
+                keep_alive, done_refills = done_refills, None
+                read_pending = launched
+                if launched:
+                    self._read_enqueue(slots)          # behind the launch and the publications enqueued above
         return results, torch.tensor(order, device=self._device)
