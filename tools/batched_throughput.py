@@ -18,6 +18,8 @@ for r in range(R):
     xs.append(torch.randint(0, 732, (nx,), generator=g)); ys.append(torch.randint(0, 1024, (ny,), generator=g))
     bs.append(torch.zeros(nx, 1024)); mx.append(int(torch.randint(50, 251, (1,), generator=g)))
 xs = [t.to(dev) for t in xs]; ys = [t.to(dev) for t in ys]; bs = [t.to(dev, torch.bfloat16) for t in bs]
+if os.environ.get('GSV_BATCH_INTERVAL'):
+    m.BATCH_INTERVAL = int(os.environ['GSV_BATCH_INTERVAL'])
 m.debug_seed = 5
 m.infer_batched(xs[:40], ys[:40], bs[:40], max_new=[20] * 40)          # warm-up (kernel selection, weight re-tiling)
 torch.cuda.synchronize()
@@ -33,3 +35,34 @@ for overlap in (True, False):
     print(f"{R} requests, 32 slots, refill prompts {'on a second stream' if overlap else 'between decode launches'}: {tok} tokens in "
           f"{dt*1e3:.1f} ms -> {tok/dt:.0f} tok/s, {tok*0.04/dt:.0f} audio-s/s (GPT stage), "
           f"{int(N.lib().gsv_gpt_launch_count(m._ctx)) - l0} launches; mean length {tok/R:.1f}")
+
+if os.environ.get("GSV_BATCH_TRACE"):
+    # where the time of the overlapped run goes: launches, live slots per launch, device time of the decode launches
+    m.overlap_refill = True
+    m.debug_seed = 5
+    stats = {"launch": 0, "live": [], "ev": []}
+    dec, rd = m._decode, m._read_enqueue
+
+    def decode(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream(dev)); dec(n); b.record(torch.cuda.current_stream(dev))
+        stats["launch"] += 1; stats["ev"].append((a, b))
+
+    def read_enqueue(k):
+        rd(k)
+    m._decode, m._read_enqueue = decode, read_enqueue
+    wait = m._read_wait
+
+    def read_wait():
+        wait(); stats["live"].append(int(m._h_active[:32].sum()))
+    m._read_wait = read_wait
+    t0 = time.perf_counter()
+    outs, order = m.infer_batched(xs, ys, bs, max_new=mx)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ms = [a.elapsed_time(b) for a, b in stats["ev"]]
+    print(f"trace: {dt*1e3:.1f} ms wall, {stats['launch']} decode launches of {m.BATCH_INTERVAL} steps, device time in decode launches {sum(ms):.1f} ms "
+          f"(mean {sum(ms)/len(ms):.2f} ms, max {max(ms):.2f}), mean live slots at harvest {sum(stats['live'])/len(stats['live']):.1f}")
+    import collections
+    print("live histogram:", sorted(collections.Counter(stats["live"]).items()))
+    print("launch ms deciles:", [round(sorted(ms)[int(len(ms) * q / 10)], 2) for q in range(10)])
