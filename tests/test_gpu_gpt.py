@@ -409,3 +409,62 @@ def test_single_sequence_decode_is_bit_deterministic_and_chunk_invariant(dev):
         outs.append(m.infer(x, y, bert, force_steps=60)[0, 0].cpu().tolist())
     assert len(outs[0]) == 60
     assert outs[0] == outs[1] == outs[2]
+
+
+def test_stacked_prefill_pass_equals_single_prefills_and_rejects_bad_arguments(dev):
+    """gsv_gpt_prefill_begin_many: three ragged prompts stacked into one pass give the same first tokens and the
+    same teacher-forced logits as three single-prompt prefills (their rows only meet inside 128-row tensor-core tiles, never
+    in a reduction); a slot named twice, a pass over the row capacity and an over-long prompt are argument errors."""
+    import ctypes as C
+    from tests import gpu_harness as H
+    from gsv_tts import _native as N
+    cfg = syn.GPT_CONFIG_TINY
+    sd = syn.gpt_state_dict(cfg, 0, 6.0)
+    g = torch.Generator().manual_seed(77)
+    lens = [(9, 14), (30, 41), (17, 5)]
+    xs = [torch.randint(0, 732, (nx,), generator=g) for nx, _ in lens]
+    ys = [torch.randint(0, 1024, (ny,), generator=g) for _, ny in lens]
+    bs = [torch.randn(nx, 1024, generator=g) for nx, _ in lens]
+    V = cfg["model"]["vocab_size"]
+    n_steps = 6
+    forced = torch.randint(0, 1000, (n_steps,), generator=g).to(torch.int32).to(dev)
+
+    def run(stacked):
+        m = H.build_gpt(cfg, sd, torch.float16, dev, [(4, 256)])
+        lib = N.lib()
+        m._release_all()
+        samp = [N.GptSampling(top_k=15, top_p=1.0, temperature=1.0, repetition_penalty=1.0, suppress_steps=0, max_new_tokens=0,
+                              mask_eos=1, max_kv=256, suppress_first=0, seed=100 + i) for i in range(3)]
+        traces = [torch.zeros(n_steps + 1, V, dtype=torch.float32, device=dev) for _ in range(3)]
+        for i in range(3):
+            N.check(lib.gsv_gpt_set_slot_hooks(m._ctx, i, None, 0, forced.data_ptr(), n_steps, traces[i].data_ptr(), n_steps + 1, m._stream()))
+        if stacked:
+            keeps = m._prefill_begin_many([(i, xs[i], ys[i], bs[i]) for i in range(3)])
+        else:
+            keeps = [m._prefill_begin(i, xs[i], ys[i], bs[i]) for i in range(3)]
+        for i in range(3):
+            m._prefill_finish(i, keeps[i][1], samp[i])
+        m._decode(n_steps)
+        m._read(3)
+        toks = m._h_tokens[:3, :n_steps + 1].clone()
+        return m, toks, [t.cpu() for t in traces]
+
+    m, t_stacked, l_stacked = run(True)
+    _, t_single, l_single = run(False)
+    assert torch.equal(t_stacked, t_single)
+    for a, b in zip(l_stacked, l_single):
+        assert torch.equal(a, b)                                   # same kernels, same per-row arithmetic: bit-equal logits
+    lib = N.lib()
+    cap = int(lib.gsv_gpt_prefill_capacity(m._ctx))
+    assert cap >= 256
+    x = xs[0].to(dev); y = ys[0].to(dev); b = bs[0].to(dev, torch.float16)
+
+    def many(slots, nxs, nys):
+        n = len(slots)
+        return lib.gsv_gpt_prefill_begin_many(m._ctx, n, (C.c_int * n)(*slots), (C.c_void_p * n)(*[x.data_ptr()] * n), (C.c_int * n)(*nxs),
+                                              (C.c_void_p * n)(*[y.data_ptr()] * n), (C.c_int * n)(*nys), (C.c_void_p * n)(*[b.data_ptr()] * n),
+                                              m._stream())
+    assert many([1, 1], [9, 9], [14, 14]) != 0                     # a slot named twice
+    assert many([0], [9], [400]) != 0                              # prompt does not fit the cache
+    assert many([0, 1, 2, 3], [9] * 4, [14] * 4) == 0
+    torch.cuda.synchronize()
