@@ -266,7 +266,12 @@ extern "C" int gsv_gpt_state_ptrs(gsv_gpt_ctx* ctx, int32_t** dev_tokens, int32_
 }
 
 extern "C" int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream) {
-  GSV_ARG(ctx && slot >= 0 && slot < ctx->p.slots);
+  GSV_ARG(ctx && slot >= -1 && slot < ctx->p.slots);
+  if (slot < 0) {                          // every slot: one memset instead of one per slot at the start of every request
+    GSV_CUDA(cudaMemsetAsync(ctx->p.active, 0, sizeof(int) * (size_t)ctx->p.slots, (cudaStream_t)stream));
+    for (int i = 0; i < ctx->p.slots; ++i) ctx->slot_live[i] = 0;
+    return GSV_OK;
+  }
   GSV_CUDA(cudaMemsetAsync(ctx->p.active + slot, 0, sizeof(int), (cudaStream_t)stream));
   ctx->slot_live[slot] = 0;
   return GSV_OK;

@@ -299,8 +299,7 @@ class Text2SemanticDecoder(nn.Module):
         self._read_event.synchronize()
 
     def _release_all(self):
-        for s in range(self._max_slots):
-            N.check(N.lib().gsv_gpt_release_slot(self._ctx, s, self._stream()))
+        N.check(N.lib().gsv_gpt_release_slot(self._ctx, -1, self._stream()))
 
     def _single_setup(self, x, y, bert, top_k, top_p, temperature, repetition_penalty, suppress_steps,
                       force_steps: Optional[int]):

@@ -150,6 +150,7 @@ int gsv_gpt_read(gsv_gpt_ctx* ctx, int32_t* host_n_gen, int32_t* host_active, in
                  int first_slot, int n_slots, void* stream);
 /* Device pointers to the same state (for zero-copy consumers on the GPU). */
 int gsv_gpt_state_ptrs(gsv_gpt_ctx* ctx, int32_t** dev_tokens, int32_t** dev_n_gen, int32_t** dev_active);
+/* Make a slot idle (its sequence is dropped); slot = -1 releases every slot. */
 int gsv_gpt_release_slot(gsv_gpt_ctx* ctx, int slot, void* stream);
 
 /* ---- parity hooks (used by tests/; they do not change the arithmetic) ------------------- */
