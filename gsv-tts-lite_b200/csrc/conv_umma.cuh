@@ -375,7 +375,7 @@ __device__ __forceinline__ void epi_apply16(const ConvArgs<T>& a, int b, int t, 
     uint32_t u[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) u[j] = Elem<T>::from_f2(act(v[2 * j]), act(v[2 * j + 1]));
-    if (n8 > 1 && (a.o_ld & 15) == 0) stg256u(a.outT + o, u);           // 16-bit rows of 24 channels are only 16-byte aligned
+    if (n8 > 1 && ((a.o_ld | a.o_off) & 15) == 0) stg256u(a.outT + o, u);   // 16-bit rows of 24 channels are only 16-byte aligned
     else {
       *reinterpret_cast<uint4*>(a.outT + o) = make_uint4(u[0], u[1], u[2], u[3]);
       if (n8 > 1) *reinterpret_cast<uint4*>(a.outT + o + 8) = make_uint4(u[4], u[5], u[6], u[7]);

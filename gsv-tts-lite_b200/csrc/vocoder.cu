@@ -576,7 +576,9 @@ inline int ws_nacc(int bn) { return bn >= 64 ? 2 : 3; }
 // (all taps) stay in shared memory or are streamed through a ring (conv_umma.cuh).
 template <typename T>
 bool conv_ws_plan(const ConvArgs<T>& a, int num_sms, bool need_large, WsPlan& pl) {
-  if (a.stride != 1 || a.in_rev || a.o_rev || a.Cin < 16 || a.Cin % 8 || a.in_ld % 8 || a.Cout % 8 || a.KW > 16 ||
+  // (the epilogue moves 8 fp32 / 16 sixteen-bit channels per access: rows and channel offsets must keep them 32-byte aligned)
+  if (a.stride != 1 || a.in_rev || a.o_rev || a.Cin < 16 || a.Cin % 8 || a.in_ld % 8 || a.Cout % 8 || a.KW > 16 || a.o_ld % 8 || a.o_off % 8 ||
+      (a.add && a.add_ld % 8) ||
       (a.KW - 1) * a.dil > 120 || (reinterpret_cast<uintptr_t>(a.in) & 15) || (reinterpret_cast<uintptr_t>(a.w) & 15) || (a.w_tap % 8))
     return false;
   const int mt = (a.Tout + umma::BM - 1) / umma::BM;
