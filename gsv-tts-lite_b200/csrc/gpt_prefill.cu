@@ -5,9 +5,9 @@
 // sequence is the slot-refill path of infer_batched, :696-722, which the reference runs one request at a time).
 //
 // Several prompts share one pass: their rows are stacked into one [sum n_i][d] matrix, so the four linears of a layer
-// are ONE tcgen05 launch each over all prompts (rows of the same 128-row tiles) and the per-row kernels (K/V scatter,
-// masked attention, add + LayerNorm) find their prompt through a small segment table passed by value.  The launch count
-// of a pass does not depend on the number of prompts (8 per layer).
+// are ONE tcgen05 launch each over all prompts (rows of the same 128-row tiles) and the per-row kernels (masked attention,
+// which also files K/V in the cache, add + LayerNorm) find their prompt through a small segment table passed by value.  The
+// launch count of a pass does not depend on the number of prompts (7 per layer).
 #include "gpt_sample.cuh"
 
 namespace {
@@ -109,26 +109,13 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const T* __restrict__ A, i
   }
 }
 
-// ---- K,V of the prompt into the cache slot: kc[l][slot][h][t][32] ----------------------------------------
-template <typename T>
-__global__ void kv_scatter_kernel(const GptParams p, int layer, const PfSegs segs, const T* __restrict__ qkv) {
-  const int row = blockIdx.x, d = p.d;
-  const int sg = pf_seg_of(segs, row);
-  const int slot = segs.slot[sg], t = row - segs.row0[sg];
-  T* kc = reinterpret_cast<T*>(p.kc);
-  T* vc = reinterpret_cast<T*>(p.vc);
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    const size_t a = (((size_t)(layer * p.slots + slot) * p.H + (c >> 5)) * p.S + t) * GSV_HEAD_DIM + (c & 31);
-    kc[a] = qkv[(size_t)row * 3 * d + d + c];
-    vc[a] = qkv[(size_t)row * 3 * d + 2 * d + c];
-  }
-}
-
 // ---- masked prompt attention (A.2 mask): text row -> all text; audio row i -> keys 0..i -----------------
-// one warp per (query row, head); 4 lanes x 8 dims per key, 8 keys per pass
+// one warp per (query row, head); 4 lanes x 8 dims per key, 8 keys per pass.  The warp also files its row's K and V of this
+// head in the slot's cache, kc[l][slot][h][t][32] (process_prompt writes K/V [:, :, :L], t2s_model.py:44-47): no separate
+// scatter launch.
 template <typename T>
-__global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__ qkv_all, T* __restrict__ out_all, const PfSegs segs,
-                                                           int n_tot, int d, int H) {
+__global__ void __launch_bounds__(128) prefill_attn_kernel(const GptParams p, int layer, const T* __restrict__ qkv_all,
+                                                           T* __restrict__ out_all, const PfSegs segs, int n_tot, int d, int H) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * 4 + warp;
   if (item >= n_tot * H) return;
@@ -139,6 +126,12 @@ __global__ void __launch_bounds__(128) prefill_attn_kernel(const T* __restrict__
   const T* qkv = qkv_all + (size_t)base * 3 * d;
   T* out = out_all + (size_t)base * d;
   const int lim = i < nx ? nx : i + 1;
+  if (lane < 8) {                                               // 4 lanes x 16 bytes = the 32 K values of (row, head); 4 more for V
+    const int which = lane >> 2, part = lane & 3;
+    const size_t a = (((size_t)(layer * p.slots + segs.slot[sg]) * H + h) * p.S + i) * GSV_HEAD_DIM + part * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (size_t)i * 3 * d + (1 + which) * d + h * GSV_HEAD_DIM + part * 8);
+    *reinterpret_cast<uint4*>(reinterpret_cast<T*>(which ? p.vc : p.kc) + a) = v;
+  }
   const int sub = lane & 3, pg = lane >> 2;
   const float qscale = rsqrtf((float)GSV_HEAD_DIM) * 1.4426950408889634f;
   float q[8];
@@ -326,9 +319,8 @@ int prefill_body(gsv_gpt_ctx* ctx, int n_prompts, const int* slots, const int64_
     const T* wqkv = reinterpret_cast<const T*>(p.w_qkv) + (size_t)l * 3 * d * d;
     const T* bqkv = reinterpret_cast<const T*>(p.b_qkv) + (size_t)l * 3 * d;
     if ((rc = gemm<T>(X, d, wqkv, bqkv, QKV, 3 * d, n, 3 * d, d, false, st, ctx->launches, ctx, (size_t)l * 4 + 0, cap))) return rc;
-    kv_scatter_kernel<T><<<n, 128, 0, st>>>(p, l, segs, QKV);
-    prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(QKV, ATT, segs, n, d, p.H);
-    ctx->launches += 2;
+    prefill_attn_kernel<T><<<(n * p.H + 3) / 4, 128, 0, st>>>(p, l, QKV, ATT, segs, n, d, p.H);
+    ctx->launches += 1;
     GSV_CHECK_LAUNCH();
     if ((rc = gemm<T>(ATT, d, reinterpret_cast<const T*>(p.w_o) + (size_t)l * d * d,
                       reinterpret_cast<const T*>(p.b_o) + (size_t)l * d, TMP, d, n, d, d, false, st, ctx->launches, ctx,
