@@ -234,10 +234,14 @@ extern "C" int gsv_gpt_decode(gsv_gpt_ctx* ctx, int n_steps, void* stream) {
   }
   if ((ctx->use_cl8 || (!explicit_impl && !ctx->use_cl && live >= 2)) && gsv_gpt_cl_supported(ctx, live) && ctx->p.H >= 8)
     return gsv_gpt_decode_cl8_launch(ctx, live, n_steps, (cudaStream_t)stream);
-  if ((ctx->use_cl || (!explicit_impl && live >= 2 && live <= 7)) && gsv_gpt_cl_supported(ctx, live))      // models with fewer than 8 heads
+  // (the kernels below rank the first 32 slots only; slots 32.. exist for requests that wait prefilled beside a full batch)
+  bool hi = false;
+  for (int i = 32; i < ctx->p.slots; ++i) hi = hi || ctx->slot_live[i];
+  if (!hi && (ctx->use_cl || (!explicit_impl && live >= 2 && live <= 7)) && gsv_gpt_cl_supported(ctx, live))   // models with fewer than 8 heads
     return gsv_gpt_decode_cl_launch(ctx, live, n_steps, (cudaStream_t)stream);
-  if (ctx->force_gemm || (live > 4 && !ctx->force_barrier_kernel && ctx->use_umma_linear))
+  if (ctx->force_gemm || ((live > 4 || hi) && !ctx->force_barrier_kernel && ctx->use_umma_linear))
     return gsv_gpt_decode_gemm_launch(ctx, n_steps, (cudaStream_t)stream);
+  if (hi) { gsv_set_error("gsv_gpt_decode: live slots beyond 32 need the cluster kernels or the multi-kernel step"); return GSV_ERR_STATE; }
   if (!ctx->force_barrier_kernel && gsv_gpt_ll_supported(ctx, live, n_steps))
     return gsv_gpt_decode_ll_launch(ctx, live, n_steps, (cudaStream_t)stream);
   return gsv_gpt_decode_launch(ctx, n_steps, (cudaStream_t)stream);

@@ -162,13 +162,20 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
 
   // ---- which sequences: the active slots are dealt round-robin over the clusters (balanced attention / sampling work) ----
   if (tid < 32) {
+    // slot table of up to 64: lane t looks at slots t and t + 32
     const int flag = tid < p.slots ? ld_cg(p.active + tid) : 0;
+    const int flag2 = tid + 32 < p.slots ? ld_cg(p.active + tid + 32) : 0;
     const unsigned m = __ballot_sync(0xffffffffu, flag != 0);
-    const int rk = __popc(m & ((1u << tid) - 1u));        // rank of this slot among the live ones
+    const unsigned m2 = __ballot_sync(0xffffffffu, flag2 != 0);
+    const unsigned below = (1u << tid) - 1u;
+    const int rk = __popc(m & below);                     // rank of a slot among the live ones
+    const int rk2 = __popc(m) + __popc(m2 & below);
     const int pos = (flag && rk % ncl == cid) ? rk / ncl : -1;
+    const int pos2 = (flag2 && rk2 % ncl == cid) ? rk2 / ncl : -1;
     if (tid < NB8) { sh.slot[tid] = -1; sh.kv[tid] = 0; sh.alive[tid] = 0.f; }
     __syncwarp();
     if (pos >= 0 && pos < NB8) { sh.slot[pos] = tid; sh.kv[pos] = ld_cg(p.kv_len + tid); sh.alive[pos] = 1.f; }
+    if (pos2 >= 0 && pos2 < NB8) { sh.slot[pos2] = tid + 32; sh.kv[pos2] = ld_cg(p.kv_len + tid + 32); sh.alive[pos2] = 1.f; }
   }
   // zero the staged operands once: columns of sequences that are not live must hold finite values
   for (int i = tid; i < (NB8 * LDX * 2 + NB8 * LDH) / 2; i += NT) reinterpret_cast<unsigned*>(xa)[i] = 0u;

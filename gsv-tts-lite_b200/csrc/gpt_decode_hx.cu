@@ -208,10 +208,13 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
   // ---- which sequence: the first active slot ----
   if (tid < 32) {
     const int flag = tid < p.slots ? ld_cg(p.active + tid) : 0;
+    const int flag2 = tid + 32 < p.slots ? ld_cg(p.active + tid + 32) : 0;        // slot table of up to 64
     const unsigned m = __ballot_sync(0xffffffffu, flag != 0);
+    const unsigned m2 = __ballot_sync(0xffffffffu, flag2 != 0);
     if (tid == 0) {
-      sh.slot = m ? (__ffs(m) - 1) : -1;
-      sh.kv = m ? ld_cg(p.kv_len + (__ffs(m) - 1)) : 0;
+      const int first = m ? (__ffs(m) - 1) : (m2 ? 32 + __ffs(m2) - 1 : -1);
+      sh.slot = first;
+      sh.kv = first >= 0 ? ld_cg(p.kv_len + first) : 0;
     }
   }
   __syncthreads();

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-#define GSV_MAX_SLOTS 32
+#define GSV_MAX_SLOTS 64      // device slot table; the cluster decode kernels (hx, cl8) rank all 64, the others the first 32
 #define GSV_SLOT_TILE 8          // slots whose activations are staged in shared memory together
 #define GSV_NSPLIT_MAX 16        // split-KV factor upper bound
 #define GSV_PART_STRIDE 36       // floats per attention partial: m, l, pad, pad, o[32]

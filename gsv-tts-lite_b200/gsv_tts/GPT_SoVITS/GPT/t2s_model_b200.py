@@ -73,6 +73,7 @@ class Text2SemanticDecoder(nn.Module):
     N_POS = 4000                      # t2s_model.py:212-213
     DECODE_CHUNK = 32                 # decode steps per persistent launch in infer()
     BATCH_INTERVAL = 8                # decode steps between harvest/refill points in infer_batched()
+    SPARE_SLOTS = 8                   # infer_batched: requests kept prefilled beside a full batch (slots beyond the batch size)
     _slot_audit = None                # test hook: callable(slot, request) -> (noise, forced, trace) device tensors or None
                                       # each; attached to the slot right before the request's first sample (infer_batched)
 
@@ -120,6 +121,8 @@ class Text2SemanticDecoder(nn.Module):
         for b in self._buckets:
             self._buckets[b].sort()
         max_slots = max(self._buckets)
+        if max_slots >= 8:                                  # room for prefilled requests beside a full batch (infer_batched)
+            max_slots = min(64, max_slots + self.SPARE_SLOTS)
         max_seq = max(max(v) for v in self._buckets.values())
         d, L = self.model_dim, self.num_layers
         blk = self.t2s_transformer.blocks
@@ -248,6 +251,9 @@ class Text2SemanticDecoder(nn.Module):
         ev = torch.cuda.Event()
         ev.record(stream)
         return ev
+
+    def _event_done(self, ev) -> bool:
+        return ev.query()
 
     def _hold_side_stream(self, stream):
         self.hold_until_decode_resident(stream)
@@ -471,7 +477,11 @@ class Text2SemanticDecoder(nn.Module):
             self._prefill(slot, x[r], y[r], bert_feature[r], sampling(r))
 
         FREE, REFILLING = -1, -2
-        owner = [FREE] * slots
+        # Physical slots: `slots` of them decode at a time (the configured batch); with the overlapped refill up to SPARE_SLOTS
+        # more hold requests whose prompts are already computed, so that a slot freed at one harvest is replaced at the next
+        # launch boundary instead of after a prompt pass (~190 dependent launches beside the decode kernel).
+        total = min(self._max_slots, slots + self.SPARE_SLOTS) if self.overlap_refill else slots
+        owner = [FREE] * total
         nxt = 0
         n0 = min(slots, B)
         if self.overlap_refill:
@@ -483,6 +493,9 @@ class Text2SemanticDecoder(nn.Module):
                 owner[s] = s
             del keeps
             nxt = n0
+            # the passes above ran on THIS stream and share their scratch with the passes of the second stream: a real
+            # dependency (the residency hold below is a bounded wait, a scheduling hint, not an ordering)
+            first_wave = self._record_event(torch.cuda.current_stream(self._device) if self._device.type == "cuda" else None)
         else:
             for s in range(n0):
                 start(s, nxt)
@@ -491,11 +504,12 @@ class Text2SemanticDecoder(nn.Module):
         results, order = [], []
         interval = max(int(check_interval), self.BATCH_INTERVAL)
         side = self._side_stream() if self.overlap_refill else None
-        to_begin = []                     # (slot, request) freed at the last read: their prompts start behind the next decode launch
-        pending = []                      # refills whose first half is running on `side`: (slot, request, tensors, event)
+        pending = []                      # prompts being computed on `side`: (slot, request, tensors, event)
+        ready = []                        # prompts computed, waiting for a place in the batch: (slot, request, tensors, event)
+
         def harvest(skip):
             nonlocal nxt
-            for s in range(slots):
+            for s in range(total):
                 if s in skip or owner[s] < 0 or int(self._h_active[s]):
                     continue
                 n_gen = int(self._h_ngen[s])
@@ -507,59 +521,77 @@ class Text2SemanticDecoder(nn.Module):
                 if on_finish is not None:
                     on_finish(owner[s], results[-1])
                 owner[s] = FREE
-                if nxt < B:
-                    if side is None:
-                        start(s, nxt)
-                        owner[s] = nxt
-                    else:
-                        to_begin.append((s, nxt))
-                        owner[s] = REFILLING
+                if side is None and nxt < B:
+                    start(s, nxt)
+                    owner[s] = nxt
                     nxt += 1
 
-        # With the overlapped refill the loop is pipelined one launch deep: launch k+1 is enqueued BEFORE the results of launch
-        # k are waited for (stream order: decode k, read k, decode k+1, read k+1, ...), so the GPU does not idle while the host
-        # harvests.  A launch enqueued over slots that turn out to have finished simply skips them (the kernels look at
-        # `active` on the device); a slot published behind launch k+1 is not in the copy of launch k's results (`fresh`).
-        read_pending = False
-        keep_alive = None                 # prompt tensors of refills published one iteration ago (needed until that launch ran)
-        while any(o >= 0 for o in owner) or pending or to_begin or read_pending:
-            launched = any(o >= 0 for o in owner)
-            if launched:
+        if side is None:
+            # the reference's order: launch, wait, harvest, prefill the successors between two launches
+            while any(o >= 0 for o in owner):
                 self._decode(interval)
-            # second half of the refills begun one launch ago: behind the decode launch just enqueued, so their prompts were
-            # computed (on the SMs the decode kernel leaves free) while the other slots kept stepping
-            fresh = set()
-            for slot, r, keep, ev in pending:
+                if on_launch is not None:
+                    on_launch(True)
+                self._read(total)
+                harvest(())
+            return results, torch.tensor(order, device=self._device)
+
+        # Overlapped refill, pipelined one launch deep: launch k+1 is enqueued BEFORE the results of launch k are waited for
+        # (stream order: decode k, read k, decode k+1, read k+1, ...), so the GPU does not idle while the host harvests.  A
+        # launch enqueued over slots that turn out to have finished simply skips them (the kernels look at `active` on the
+        # device); a slot published behind launch k+1 is not in the copy of launch k's results (`fresh`).
+        read_pending = False
+        keep_alive = []                   # prompt tensors of published requests, until the publication has certainly run
+        while any(o >= 0 for o in owner) or pending or ready or read_pending or nxt < B:
+            # publication first -- behind the launch in flight, before the next one: computed prompts take the places the last
+            # harvest freed and decode from the very next launch (a pass still running is not waited for, unless nothing else
+            # is left to run)
+            idle = not any(o >= 0 for o in owner) and not read_pending
+            ready += [q for q in pending if idle or self._event_done(q[3])]
+            pending = [q for q in pending if q not in ready]
+            fresh, published = set(), []
+            n_live = sum(1 for o in owner if o >= 0)
+            while ready and n_live < slots:
+                slot, r, keep, ev = ready.pop(0)
                 self._wait_on_current_stream(ev)
                 audit(slot, r)
                 self._prefill_finish(slot, keep[1], sampling(r))
                 owner[slot] = r
                 fresh.add(slot)
-            done_refills, pending = pending, []
-            # first half of the refills freed at the last harvest, on the second stream -- held until the decode launch above
-            # has its clusters resident (hold_until_decode_resident): a stream of small prompt kernels must not be what a
-            # 16-CTA cluster waits behind
-            if to_begin:
+                published.append(keep)
+                n_live += 1
+            launched = n_live > 0
+            if launched:
+                self._decode(interval)
+            # new prompt passes on the second stream for the requests that will be needed next: enough to fill the batch plus
+            # the spare pool -- held until the launch just enqueued has its clusters resident (hold_until_decode_resident): a stream
+            # of small prompt kernels must not be what a 16-CTA cluster waits behind
+            want = (slots - n_live) + (total - slots) - len(ready) - len(pending)
+            free = [s for s in range(total) if owner[s] == FREE]
+            n_new = min(want, len(free), B - nxt)
+            if n_new > 0:
+                batch = []
+                for s in free[:n_new]:
+                    batch.append((s, nxt))
+                    owner[s] = REFILLING
+                    nxt += 1
                 with self._on_stream(side):
+                    if first_wave is not None:
+                        self._wait_on_current_stream(first_wave)
+                        first_wave = None
                     self._hold_side_stream(side)
-                    keeps = self._prefill_begin_many([(slot, x[r], y[r], bert_feature[r]) for slot, r in to_begin])
+                    keeps = self._prefill_begin_many([(slot, x[r], y[r], bert_feature[r]) for slot, r in batch])
                     ev = self._record_event(side)
-                    for (slot, r), keep in zip(to_begin, keeps):
+                    for (slot, r), keep in zip(batch, keeps):
                         pending.append((slot, r, keep, ev))
-                to_begin = []
             if on_launch is not None:
                 on_launch(launched)
-            if side is None:
-                self._read(slots)
-                del done_refills          # their prompt tensors were needed until the second half had run
-                harvest(())
-            else:
-                if read_pending:
-                    self._read_wait()     # results of the PREVIOUS launch; the one enqueued above is running or queued
-                    keep_alive = None
-                    harvest(fresh)
-                keep_alive, done_refills = done_refills, None
-                read_pending = launched
-                if launched:
-                    self._read_enqueue(slots)          # behind the launch and the publications enqueued above
+            if read_pending:
+                self._read_wait()         # results of the PREVIOUS launch; the one enqueued above is running or queued
+                keep_alive = keep_alive[-1:]
+                harvest(fresh)
+            keep_alive.append(published)
+            read_pending = launched
+            if launched:
+                self._read_enqueue(total)              # behind the launch and the publications enqueued above
         return results, torch.tensor(order, device=self._device)

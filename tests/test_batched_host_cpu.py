@@ -12,6 +12,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gsv-tts-lite_b200"))
 
 EOS = 1024
+SPARE = 8            # Text2SemanticDecoder.SPARE_SLOTS
 
 
 class FakeRuntime:
@@ -20,7 +21,7 @@ class FakeRuntime:
 
     def __init__(self, m, lengths, slots, log):
         self.m, self.lengths, self.log = m, lengths, log
-        self.slot = [None] * slots                  # dict(r, toks, active, limit) once live
+        self.slot = [None] * (slots + SPARE)        # dict(r, toks, active, limit) once live; physical slots incl. the spare pool
         self.begun = {}                             # slot -> request whose first half has run
         self.stream = "main"
 
@@ -63,6 +64,9 @@ class FakeRuntime:
             self.log.append(("idle_decode", n))
             return
         self.log.append(("decode", n))
+        n_active = sum(1 for st in self.slot if st is not None and st["active"])
+        assert n_active <= len(self.slot) - SPARE, "more live sequences than the configured batch"
+        self.max_active = max(getattr(self, "max_active", 0), n_active)
         for _ in range(n):
             for st in self.slot:
                 if st is None or not st["active"]:
@@ -115,9 +119,10 @@ def make_model(lengths, slots, log, overlap):
     m._ctx = None
     m.debug_seed = 1
     m.overlap_refill = overlap
-    m._h_ngen = torch.zeros(slots, dtype=torch.int32)
-    m._h_active = torch.zeros(slots, dtype=torch.int32)
-    m._h_tokens = torch.zeros(slots, 256, dtype=torch.int32)
+    m._max_slots = slots + SPARE
+    m._h_ngen = torch.zeros(slots + SPARE, dtype=torch.int32)
+    m._h_active = torch.zeros(slots + SPARE, dtype=torch.int32)
+    m._h_tokens = torch.zeros(slots + SPARE, 256, dtype=torch.int32)
     rt = FakeRuntime(m, lengths, slots, log)
     m._release_all = rt.release_all
     m._prefill = rt.prefill
@@ -131,6 +136,7 @@ def make_model(lengths, slots, log, overlap):
     m._side_stream = lambda: "side"
     m._on_stream = rt.on_stream
     m._record_event = rt.record_event
+    m._event_done = lambda ev: True
     m._wait_on_current_stream = rt.wait
     m._hold_side_stream = lambda stream: log.append(("hold",))       # the second stream waits for the decode launch to be resident
     return m, N

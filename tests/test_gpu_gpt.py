@@ -468,3 +468,31 @@ def test_stacked_prefill_pass_equals_single_prefills_and_rejects_bad_arguments(d
     assert many([0], [9], [400]) != 0                              # prompt does not fit the cache
     assert many([0, 1, 2, 3], [9] * 4, [14] * 4) == 0
     torch.cuda.synchronize()
+
+
+def test_batched_schedules_agree_with_a_long_first_wave_and_spare_slots(dev):
+    """Full-size model, 32 slots + the spare pool, 44 requests with long prompts: the first wave is several stacked passes
+    (~10 ms) on the caller's stream, the spare pool's pass starts on the second stream right behind the first decode launch and
+    shares the prompt scratch with them -- ordered by an event (the residency hold is a bounded wait, not an ordering).  Every
+    request gets the tokens of the reference order, run after run."""
+    from tests import gpu_harness as H
+    cfg = syn.GPT_CONFIG
+    m = H.build_gpt(cfg, syn.gpt_state_dict(cfg, 0), torch.bfloat16, dev, [(32, 512)])
+    assert m._max_slots == 32 + m.SPARE_SLOTS
+    g = torch.Generator().manual_seed(4321)
+    R = 44
+    xs = [torch.randint(0, 732, (int(torch.randint(90, 121, (1,), generator=g)),), generator=g).to(dev) for _ in range(R)]
+    ys = [torch.randint(0, 1024, (int(torch.randint(180, 251, (1,), generator=g)),), generator=g).to(dev) for _ in range(R)]
+    bs = [torch.zeros(x.numel(), 1024, device=dev, dtype=torch.bfloat16) for x in xs]
+    mx = [int(torch.randint(8, 40, (1,), generator=g)) for _ in range(R)]
+    runs = []
+    for overlap in (True, True, False, True):
+        m.overlap_refill = overlap
+        m.debug_seed = 9
+        outs, order = m.infer_batched(xs, ys, bs, max_new=mx)
+        torch.cuda.synchronize()
+        assert sorted(order.tolist()) == list(range(R))
+        runs.append({r: t.cpu().tolist() for t, r in zip(outs, order.tolist())})
+    for i in (0, 1, 3):
+        bad = [r for r in range(R) if runs[i][r] != runs[2][r]]
+        assert not bad, (i, bad[:10])

@@ -54,7 +54,7 @@ if os.environ.get("GSV_BATCH_TRACE"):
     wait = m._read_wait
 
     def read_wait():
-        wait(); stats["live"].append(int(m._h_active[:32].sum()))
+        wait(); stats["live"].append(int(m._h_active.sum()))
     m._read_wait = read_wait
     t0 = time.perf_counter()
     outs, order = m.infer_batched(xs, ys, bs, max_new=mx)
