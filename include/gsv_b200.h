@@ -51,7 +51,7 @@ typedef struct {
   int32_t d_bert;      /* 1024 (t2s_model.py:172)                            */
   int32_t n_pos;       /* rows of the positional tables (4000, :212-213)     */
   int32_t dtype;       /* gsv_dtype                                          */
-  int32_t max_slots;   /* max batch size over gpt_cache   (<= 32)            */
+  int32_t max_slots;   /* KV-cache slots: max batch size over gpt_cache + the spare slots of infer_batched (<= 64) */
   int32_t max_seq;     /* max sequence length over gpt_cache                 */
 } gsv_gpt_dims;
 
