@@ -187,7 +187,9 @@ class SynthesizerTrn(FlowDecoder):
     ``decode`` (codes -> waveform: quantizer lookup, prior encoder ``enc_p``, prior sample, reverse flow, HiFi-GAN),
     ``flow_dec``, ``initialize_runtime``, ``samples_per_frame``, ``enc_p.y_overlap``.  Everything between the semantic
     tokens and the waveform runs in ``libgsv_b200.so`` (csrc/encp.cu, csrc/vocoder.cu).  ``get_ge`` / ``extract_latent``
-    (reference-audio featurisers run once per cached prompt, TTS.py:1374, 1567) are not part of the hot path and not here."""
+    (reference-audio featurisers, run once per cached speaker / prompt, TTS.py:1374, 1567) are not on the hot path: they are
+    kept for the drop-in as plain tensor expressions over the checkpoint's own ``ref_enc`` / ``sv_emb`` / ``ssl_proj`` /
+    codebook tensors (no kernels of this library, nothing to measure)."""
 
     def __init__(self, spec_channels=1025, segment_size=32, inter_channels=192, hidden_channels=192, filter_channels=768, n_heads=2,
                  n_layers=6, kernel_size=3, p_dropout=0.0, n_speakers=0, gin_channels=512, semantic_frame_rate="25hz", version="v2",
@@ -206,12 +208,75 @@ class SynthesizerTrn(FlowDecoder):
         super().load_state_dict(state_dict, strict)
         keep = ("enc_p.", "ge_to512.", "quantizer.vq.layers.0._codebook.embed")
         self._enc_raw = {k: v.detach().float() for k, v in state_dict.items() if k.startswith(keep)}
+        aux = ("ref_enc.", "sv_emb.", "prelu.", "ssl_proj.")
+        self._aux_raw = {k: v.detach().float() for k, v in state_dict.items() if k.startswith(aux)}
         return self
 
     def state_dict(self, *a, **k):
         sd = super().state_dict()
         sd.update(self._enc_raw)
+        sd.update(getattr(self, "_aux_raw", {}))
         return sd
+
+    # ---- once per cached speaker / prompt (reference models.py:371-378, 431-434): tensor expressions, not kernels ------------
+    def _aux(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        raw = getattr(self, "_aux_raw", {})
+        if name not in raw:
+            raise KeyError(f"this SoVITS checkpoint carries no '{name}': get_ge / extract_latent need ref_enc.*, sv_emb.*, ssl_proj.*")
+        cache = self.__dict__.setdefault("_aux_cache", {})
+        key = (name, like.device, like.dtype)
+        if key not in cache:
+            cache[key] = raw[name].to(device=like.device, dtype=like.dtype)
+        return cache[key]
+
+    @torch.inference_mode()
+    def get_ge(self, refer: torch.Tensor, sv_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """models.py:371-378: refer [1, spec, T] (linear spectrogram of the speaker reference) [, sv_emb [1, 20480]] ->
+        ge [1, gin, 1].  ``ref_enc`` is MelStyleEncoder(704) (module/modules.py:367-446): two Linear + Mish, two Conv1dGLU
+        (k = 5), one 2-head self-attention with a residual (scores / sqrt(d_model)), Linear, mean over time; for v2Pro the
+        speaker-verification embedding is added through ``sv_emb`` and a PReLU."""
+        F = torch.nn.functional
+        w = lambda n: self._aux(n, refer)
+        x = refer[:, :704].transpose(1, 2)                                     # [1, T, 704]
+        mish = lambda t: t * torch.tanh(F.softplus(t))
+        x = mish(F.linear(x, w("ref_enc.spectral.0.fc.weight"), w("ref_enc.spectral.0.fc.bias")))
+        x = mish(F.linear(x, w("ref_enc.spectral.3.fc.weight"), w("ref_enc.spectral.3.fc.bias")))
+        x = x.transpose(1, 2)                                                  # [1, 128, T]
+        for i in range(2):
+            cw, cb = w(f"ref_enc.temporal.{i}.conv1.conv.weight"), w(f"ref_enc.temporal.{i}.conv1.conv.bias")
+            h = F.conv1d(x, cw, cb, padding=(cw.shape[-1] - 1) // 2)
+            a, g = torch.split(h, x.shape[1], dim=1)
+            x = x + a * torch.sigmoid(g)
+        x = x.transpose(1, 2)                                                  # [1, T, 128]
+        n_head = 2
+        d_model = x.shape[-1]
+        dk = d_model // n_head
+        b, t, _ = x.shape
+        q = F.linear(x, w("ref_enc.slf_attn.w_qs.weight"), w("ref_enc.slf_attn.w_qs.bias")).view(b, t, n_head, dk).permute(2, 0, 1, 3)
+        k = F.linear(x, w("ref_enc.slf_attn.w_ks.weight"), w("ref_enc.slf_attn.w_ks.bias")).view(b, t, n_head, dk).permute(2, 0, 1, 3)
+        v = F.linear(x, w("ref_enc.slf_attn.w_vs.weight"), w("ref_enc.slf_attn.w_vs.bias")).view(b, t, n_head, dk).permute(2, 0, 1, 3)
+        attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) / (d_model ** 0.5), dim=-1)
+        o = torch.matmul(attn, v).permute(1, 2, 0, 3).reshape(b, t, d_model)
+        x = F.linear(o, w("ref_enc.slf_attn.fc.weight"), w("ref_enc.slf_attn.fc.bias")) + x
+        x = F.linear(x, w("ref_enc.fc.fc.weight"), w("ref_enc.fc.fc.bias"))
+        ge = x.float().div(t).sum(dim=1).to(x.dtype).unsqueeze(-1)             # temporal_avg_pool with an all-ones mask
+        if self.is_v2pro and sv_emb is not None:
+            ge = ge + F.linear(sv_emb.to(ge.dtype), w("sv_emb.weight"), w("sv_emb.bias")).unsqueeze(-1)
+            ge = F.prelu(ge, w("prelu.weight"))
+        return ge
+
+    @torch.inference_mode()
+    def extract_latent(self, x: torch.Tensor) -> torch.Tensor:
+        """models.py:431-434: HuBERT features [1, 768, T] -> semantic codes [1, 1, T // 2] (the prompt tokens): ``ssl_proj``
+        (Conv1d k = 2, stride 2) and the nearest codebook row (module/core_vq.py:124-128: arg-max of the negated squared
+        distance, expanded as the reference expands it)."""
+        F = torch.nn.functional
+        ssl = F.conv1d(x, self._aux("ssl_proj.weight", x), self._aux("ssl_proj.bias", x), stride=2)
+        embed = self._enc_raw["quantizer.vq.layers.0._codebook.embed"].to(device=x.device, dtype=x.dtype).t()    # [768, 1024]
+        flat = ssl.transpose(1, 2).reshape(-1, ssl.shape[1])
+        dist = -(flat.pow(2).sum(1, keepdim=True) - 2 * flat @ embed + embed.pow(2).sum(0, keepdim=True))
+        codes = dist.max(dim=-1).indices.view(ssl.shape[0], -1)               # [B, T']
+        return codes.unsqueeze(0).transpose(0, 1)                              # [n_q = 1, B, T'] -> transpose(0, 1), as the reference returns it
 
     @torch.inference_mode()
     def initialize_runtime(self, dtype, device, sovits_cache=None):

@@ -223,3 +223,31 @@ def sovits_encp_state_dict(model: dict, seed: int = 0) -> Dict[str, torch.Tensor
         lin("ge_to512", 512, model["gin_channels"])
         sd["ge_to512.weight"] = sd["ge_to512.weight"][:, :, 0].contiguous()
     return sd
+
+
+def sovits_aux_state_dict(model: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """fp32 tensors with the key set and shapes of the reference's ``ref_enc.*`` (MelStyleEncoder(704), modules.py:367-409),
+    ``sv_emb`` / ``prelu`` (v2Pro, models.py:316-318) and the top-level ``ssl_proj`` (Conv1d(768, 768, 2, stride 2), :310):
+    what ``SynthesizerTrn.get_ge`` / ``extract_latent`` read."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    gin = model["gin_channels"]
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, out_c, in_c):
+        sd[name + ".weight"] = _randn(g, out_c, in_c, std=in_c ** -0.5)
+        sd[name + ".bias"] = _randn(g, out_c, std=0.05)
+
+    lin("ref_enc.spectral.0.fc", 128, 704)
+    lin("ref_enc.spectral.3.fc", 128, 128)
+    for i in range(2):
+        sd[f"ref_enc.temporal.{i}.conv1.conv.weight"] = _randn(g, 256, 128, 5, std=(128 * 5) ** -0.5)
+        sd[f"ref_enc.temporal.{i}.conv1.conv.bias"] = _randn(g, 256, std=0.05)
+    for nm in ("w_qs", "w_ks", "w_vs", "fc"):
+        lin(f"ref_enc.slf_attn.{nm}", 128, 128)
+    lin("ref_enc.fc.fc", gin, 128)
+    sd["ssl_proj.weight"] = _randn(g, 768, 768, 2, std=(768 * 2) ** -0.5)
+    sd["ssl_proj.bias"] = _randn(g, 768, std=0.05)
+    if model.get("version") in ("v2Pro", "v2ProPlus"):
+        lin("sv_emb", gin, 20480)
+        sd["prelu.weight"] = 0.25 + _randn(g, gin, std=0.05)
+    return sd

@@ -247,9 +247,31 @@ def make_glue():
           "tail", int(out["tail_offset"]), "sola offset", int(out["sola_offset"]))
 
 
+def make_sovits_aux():
+    """get_ge / extract_latent of the reference's own SynthesizerTrn (models.py:371-378, 431-434) on the tiny synthetic
+    checkpoint (v2 and v2Pro): tests/golden/sovits_aux.npz, read by tests/test_aux_cpu.py."""
+    M = ref_shim.sovits_models()
+    g = torch.Generator().manual_seed(17)
+    refer, sv, ssl = torch.randn(1, 1025, 37, generator=g), torch.randn(1, 20480, generator=g) * 0.1, torch.randn(1, 768, 46, generator=g)
+    out = {}
+    for version in ("v2", "v2Pro"):
+        model = dict(syn.SOVITS_MODEL["tiny"], version=version)
+        sd = dict(syn.sovits_flow_dec_state_dict(model, 0))
+        sd.update(syn.sovits_encp_state_dict(model, 0))
+        sd.update(syn.sovits_aux_state_dict(model, 0))
+        sd["quantizer.vq.layers.0._codebook.inited"] = torch.Tensor([True])    # a trained checkpoint: no k-means re-initialisation
+        ref = M.SynthesizerTrn(1025, 32, n_speakers=300, **model).eval()
+        ref.load_state_dict(sd, strict=False)
+        out[f"ge_{version}"] = ref.get_ge(refer, sv if version == "v2Pro" else None).numpy()
+        out[f"codes_{version}"] = ref.extract_latent(ssl).numpy()
+    np.savez_compressed(os.path.join(OUT, "sovits_aux.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["gpt", "batched", "voc", "encp", "glue"]
+    which = sys.argv[1:] or ["gpt", "batched", "voc", "encp", "glue", "aux"]
+    if "aux" in which:
+        make_sovits_aux()
     if "glue" in which:
         make_glue()
     if "gpt" in which:
