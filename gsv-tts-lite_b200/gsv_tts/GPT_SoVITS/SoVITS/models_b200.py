@@ -27,6 +27,14 @@ def fold_weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     return g * v / n
 
 
+class _FoldedWeightNorm:
+    """``vq_model.dec`` as the reference's loader touches it (Loader.py:73, 95: ``vq_model.dec.remove_weight_norm()``): the
+    weight-norm pairs of a checkpoint are folded by ``load_state_dict`` here, so the call has nothing left to do."""
+
+    def remove_weight_norm(self):
+        return None
+
+
 class FlowDecoder(nn.Module):
     """``flow`` + ``dec`` of SynthesizerTrn on the native path.  Parameters are kept as a plain
     name -> tensor table in the reference's key space (``flow.flows.0.pre.weight`` ...)."""
@@ -36,6 +44,7 @@ class FlowDecoder(nn.Module):
                  upsample_initial_channel=512, upsample_kernel_sizes=(16, 16, 8, 2, 2), gin_channels=512,
                  version="v2", **_ignored):
         super().__init__()
+        self.dec = _FoldedWeightNorm()
         if str(resblock) != "1":
             raise ValueError("only ResBlock1 generators exist in the reference (models.py:85)")
         self.inter_channels = inter_channels

@@ -161,3 +161,19 @@ def test_to_safetensors_round_trip(tmp_path):
     assert sorted(sa) == sorted(sb) and all(torch.allclose(sa[k].float(), sb[k].float(), atol=1e-6) for k in sa)
     with pytest.raises(ValueError):
         Loader.to_safetensors(str(tmp_path / "x.bin"))
+
+
+def test_native_sovits_class_survives_the_reference_loader_call_sequence():
+    """Reference Loader.py:87-99 with only the class swapped: ctor keywords, load_state_dict(strict=False),
+    dec.remove_weight_norm(), .to(device, dtype), .eval() (initialize_runtime needs the GPU and is covered there)."""
+    from gsv_tts.GPT_SoVITS.SoVITS.models_b200 import SynthesizerTrn
+    model = dict(syn.SOVITS_MODEL["tiny"], version="v2Pro")
+    sd = dict(syn.sovits_flow_dec_state_dict(model, 0))
+    sd.update(syn.sovits_encp_state_dict(model, 0))
+    sd.update(syn.sovits_aux_state_dict(model, 0))
+    vq = SynthesizerTrn(2048 // 2 + 1, 20480 // 640, n_speakers=300, **model)
+    vq.load_state_dict(sd, strict=False)
+    vq.dec.remove_weight_norm()
+    assert vq.to("cpu", torch.float16) is vq and vq.eval() is vq
+    assert vq.samples_per_frame == 640 and vq.enc_p.y_overlap is None
+    assert set(k.split(".")[0] for k in vq.state_dict()) >= {"flow", "dec", "enc_p", "quantizer", "ref_enc", "ssl_proj", "sv_emb"}
