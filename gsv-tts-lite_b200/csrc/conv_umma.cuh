@@ -637,14 +637,18 @@ struct ParamsRU {
 };
 
 // BK = channels per K chunk = row width of the operand tiles: C for 64 / 32 / 16 channels; 64 for C = 48 (TMA zero-fills the
-// missing input channels, the staging tiles keep theirs at the zero they are initialised with).
-template <typename T, int C, int BK>
+// missing input channels, the staging tiles keep theirs at the zero they are initialised with).  MS consecutive tiles form
+// one unit (one hand-over chain MMA 1 -> E1 -> MMA 2 -> E2 per unit): with 16 / 32 channels a tile is 2-4 K outputs and
+// the chain's fixed latencies, not its work, set the pace.
+template <typename T, int C, int BK, int MS>
 __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __grid_constant__ ParamsRU<T> P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int ROW_BYTES = BK * 2, W_BYTES = C * ROW_BYTES;
   constexpr int W_STAGE = (W_BYTES + 1023) & ~1023;
   constexpr int G = C / 16;
-  constexpr int TMEM_COLS = WsTmem<4 * C>::cols;
+  constexpr int UC = MS * C;                               // accumulator columns of one unit
+  constexpr int TMEM_COLS = WsTmem<4 * UC>::cols;
+  static_assert(4 * UC <= 512, "two first-convolution and two second-convolution accumulator sets fit tensor memory");
   constexpr uint32_t SWZ = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);     // 16-byte chunk index ^= (offset >> 7) & SWZ
   __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], acc1_full[2], acc1_empty[2], a2_full[2], a2_empty[2], acc2_full[2], acc2_empty[2],
       w_full;
@@ -653,12 +657,13 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
   const uint32_t tiles_w1 = base_u + ((1024u - (base_u & 1023u)) & 1023u);
   const uint32_t tiles_w2 = tiles_w1 + (uint32_t)(P.KW * W_STAGE);
   const uint32_t tiles_a = tiles_w2 + (uint32_t)(P.KW * W_STAGE);
-  const uint32_t tiles_a2 = tiles_a + (uint32_t)(P.sa * P.a_stage_bytes);
+  const uint32_t tiles_a2 = tiles_a + (uint32_t)(P.sa * P.a_stage_bytes);      // [2 buffers][MS tiles][a2_bytes]
   uint8_t* const a2_ptr = smem_raw + (tiles_a2 - base_u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SA = P.sa;
   const int p2 = (P.KW - 1) / 2, p1 = (P.KW - 1) * P.dil / 2;
+  const int n_units = (P.n_tiles + MS - 1) / MS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
   }
   // rows 128.. of the staging tiles are read by the last taps of MMA 2 (their products only reach discarded output rows):
   // keep them finite
-  for (int i = threadIdx.x; i < 2 * P.a2_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(a2_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * MS * P.a2_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(a2_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -685,6 +690,7 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
+  auto n_sub = [&](int unit) { return P.n_tiles - unit * MS < MS ? P.n_tiles - unit * MS : MS; };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -696,55 +702,65 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
       }
       pdl_wait();
       int it = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-        const int b = tile / P.mt, m = tile - b * P.mt;
-        const int s = it % SA;
-        if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
-        mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
-        tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.ep.in_off, m * P.R - p2 - p1, b);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int ns = n_sub(unit);
+        for (int sub = 0; sub < ns; ++sub, ++it) {
+          const int tile = unit * MS + sub;
+          const int b = tile / P.mt, m = tile - b * P.mt;
+          const int s = it % SA;
+          if (it >= SA) mbar_wait(&a_empty[s], ((it / SA) - 1) & 1);
+          mbar_expect_tx(&a_full[s], (unsigned)(P.a_rows * ROW_BYTES));
+          tma_load_3d(tiles_a + (uint32_t)(s * P.a_stage_bytes), &P.tm_a, &a_full[s], P.ep.in_off, m * P.R - p2 - p1, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---- MMA issuer: MMA 1 of tile lt, then MMA 2 of tile lt - 1 ----
+      // ---- MMA issuer: MMA 1 of unit lt, then MMA 2 of unit lt - 1 ----
       constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(C >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
-      auto mma2 = [&](int u) {
+      auto mma2 = [&](int u, int ns) {
         const int buf = u & 1;
         mbar_wait(&a2_full[buf], (u >> 1) & 1);
         if (u >= 2) mbar_wait(&acc2_empty[buf], ((u >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t a_base = tiles_a2 + (uint32_t)(buf * P.a2_bytes);
-        const uint32_t d = tmem_d + (uint32_t)(2 * C + buf * C);
-        for (int j = 0; j < P.KW; ++j) {
-          const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * ROW_BYTES));
-          const uint64_t bd = smem_desc<BK>(tiles_w2 + (uint32_t)(j * W_STAGE));
+        for (int sub = 0; sub < ns; ++sub) {
+          const uint32_t a_base = tiles_a2 + (uint32_t)((buf * MS + sub) * P.a2_bytes);
+          const uint32_t d = tmem_d + (uint32_t)(2 * UC + buf * UC + sub * C);
+          for (int j = 0; j < P.KW; ++j) {
+            const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * ROW_BYTES));
+            const uint64_t bd = smem_desc<BK>(tiles_w2 + (uint32_t)(j * W_STAGE));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+          }
         }
         tc_commit(&a2_empty[buf]);
         tc_commit(&acc2_full[buf]);
       };
       mbar_wait(&w_full, 0);
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
-        const int buf = lt & 1, s = lt % SA;
+      int lt = 0, it = 0, ns_prev = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++lt) {
+        const int buf = lt & 1, ns = n_sub(unit);
         if (lt >= 2) mbar_wait(&acc1_empty[buf], ((lt >> 1) - 1) & 1);
-        mbar_wait(&a_full[s], (lt / SA) & 1);
-        tc_fence_after();
-        const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
-        const uint32_t d = tmem_d + (uint32_t)(buf * C);
-        for (int j = 0; j < P.KW; ++j) {
-          const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
-          const uint64_t bd = smem_desc<BK>(tiles_w1 + (uint32_t)(j * W_STAGE));
+        for (int sub = 0; sub < ns; ++sub, ++it) {
+          const int s = it % SA;
+          mbar_wait(&a_full[s], (it / SA) & 1);
+          tc_fence_after();
+          const uint32_t a_base = tiles_a + (uint32_t)(s * P.a_stage_bytes);
+          const uint32_t d = tmem_d + (uint32_t)(buf * UC + sub * C);
+          for (int j = 0; j < P.KW; ++j) {
+            const uint64_t ad = smem_desc<BK>(a_base + (uint32_t)(j * P.dil * ROW_BYTES));
+            const uint64_t bd = smem_desc<BK>(tiles_w1 + (uint32_t)(j * W_STAGE));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) tc_mma(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&a_empty[s]);
         }
-        tc_commit(&a_empty[s]);
         tc_commit(&acc1_full[buf]);
-        if (lt >= 1) mma2(lt - 1);
+        if (lt >= 1) mma2(lt - 1, ns_prev);
+        ns_prev = ns;
       }
-      if (lt >= 1) mma2(lt - 1);
+      if (lt >= 1) mma2(lt - 1, ns_prev);
       pdl_launch_dependents();
     }
   } else if (warp < 6) {
@@ -752,34 +768,38 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
     const int quarter = warp & 3, r = quarter * 32 + lane;
     const Act act(P.act1);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const int b = tile / P.mt, m = tile - b * P.mt;
-      const int t_int = m * P.R - p2 + r;
-      const bool inside = t_int >= 0 && t_int < P.Tn;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++lt) {
+      const int buf = lt & 1, ns = n_sub(unit);
       mbar_wait(&acc1_full[buf], (lt >> 1) & 1);
-      if (lt >= 2) mbar_wait(&a2_empty[buf], ((lt >> 1) - 1) & 1);      // MMA 2 of tile lt - 2 has read this staging tile
+      if (lt >= 2) mbar_wait(&a2_empty[buf], ((lt >> 1) - 1) & 1);      // MMA 2 of unit lt - 2 has read these staging tiles
       tc_fence_after();
-      uint8_t* const tile_ptr = a2_ptr + (size_t)buf * P.a2_bytes;
-      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * C);
+#pragma unroll 1
+      for (int sub = 0; sub < ns; ++sub) {
+        const int tile = unit * MS + sub;
+        const int b = tile / P.mt, m = tile - b * P.mt;
+        const int t_int = m * P.R - p2 + r;
+        const bool inside = t_int >= 0 && t_int < P.Tn;
+        uint8_t* const tile_ptr = a2_ptr + (size_t)(buf * MS + sub) * P.a2_bytes;
+        const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * UC + sub * C);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        uint32_t v[16];
-        tc_ld16(tbase + (uint32_t)(g * 16), v);
-        tc_ld_wait();
-        uint32_t bw[8], u[8];
-        ldg256u(P.bias1 + g * 16, bw);
+        for (int g = 0; g < G; ++g) {
+          uint32_t v[16];
+          tc_ld16(tbase + (uint32_t)(g * 16), v);
+          tc_ld_wait();
+          uint32_t bw[8], u[8];
+          ldg256u(P.bias1 + g * 16, bw);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 f = Elem<T>::to_f2(bw[j]);
-          const float x0 = act(__uint_as_float(v[2 * j]) + f.x), x1 = act(__uint_as_float(v[2 * j + 1]) + f.y);
-          u[j] = inside ? Elem<T>::from_f2(x0, x1) : 0u;
-        }
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = Elem<T>::to_f2(bw[j]);
+            const float x0 = act(__uint_as_float(v[2 * j]) + f.x), x1 = act(__uint_as_float(v[2 * j + 1]) + f.y);
+            u[j] = inside ? Elem<T>::from_f2(x0, x1) : 0u;
+          }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t off = (uint32_t)(r * ROW_BYTES + (g * 2 + h) * 16);
-          off ^= ((off >> 7) & SWZ) << 4;
-          *reinterpret_cast<uint4*>(tile_ptr + off) = make_uint4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t off = (uint32_t)(r * ROW_BYTES + (g * 2 + h) * 16);
+            off ^= ((off >> 7) & SWZ) << 4;
+            *reinterpret_cast<uint4*>(tile_ptr + off) = make_uint4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
@@ -794,24 +814,48 @@ __global__ void __launch_bounds__(64 + 128 * 3, 1) resunit_umma_kernel(const __g
     pdl_wait();
     int use = 0;
     for (int lt = set;; lt += 2, ++use) {
-      const int tile = blockIdx.x + lt * gridDim.x;
-      if (tile >= P.n_tiles) break;
-      const int b = tile / P.mt, m = tile - b * P.mt;
-      const int t = m * P.R + r;
-      const bool ok = r < P.R && t < P.Tn;
-      const size_t o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off;
+      const int unit = blockIdx.x + lt * gridDim.x;
+      if (unit >= n_units) break;
+      const int ns = n_sub(unit);
+      auto row_of = [&](int sub, int& b, int& t, size_t& o) -> bool {
+        const int tile = unit * MS + sub;
+        b = tile / P.mt;
+        t = (tile - b * P.mt) * P.R + r;
+        o = ((size_t)b * ep.Tout + t) * ep.o_ld + ep.o_off;
+        return sub < ns && r < P.R && t < P.Tn;
+      };
       EpiPre pre[2];
-      if (ok) epi_prefetch16<T>(ep, o, 2, pre[0]);
+      {
+        int b, t;
+        size_t o;
+        if (row_of(0, b, t, o)) epi_prefetch16<T>(ep, o, 2, pre[0]);
+      }
       mbar_wait(&acc2_full[set], use & 1);
       tc_fence_after();
-      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * C + set * C);
+      const uint32_t tbase = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * UC + set * UC);
+      // an even number of 16-channel groups per iteration, so that the two prefetch buffers alternate at compile time across
+      // iterations (a single-tile unit has one iteration: nothing to alternate across)
+      constexpr int SU = (G % 2 == 1 && MS > 1) ? 2 : 1;
+      static_assert(MS % SU == 0, "sub-tiles pair up when a tile has an odd number of 16-channel groups");
+#pragma unroll 1
+      for (int s0 = 0; s0 < MS; s0 += SU) {
+        if (s0 >= ns) break;
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        if (g + 1 < G && ok) epi_prefetch16<T>(ep, o + (g + 1) * 16, 2, pre[(g + 1) & 1]);
-        uint32_t v[16];
-        tc_ld16(tbase + (uint32_t)(g * 16), v);
-        tc_ld_wait();
-        if (ok) epi_apply16<T>(ep, b, t, g * 16, o + g * 16, v, pre[g & 1], 2);
+        for (int u = 0; u < SU * G; ++u) {
+          const int sub = s0 + u / G, c0 = (u % G) * 16;
+          {
+            const int sub1 = (u + 1 < SU * G) ? s0 + (u + 1) / G : s0 + SU, c1 = (u + 1 < SU * G) ? ((u + 1) % G) * 16 : 0;
+            int b1, t1;
+            size_t o1;
+            if (sub1 < MS && row_of(sub1, b1, t1, o1)) epi_prefetch16<T>(ep, o1 + c1, 2, pre[(u + 1) & 1]);
+          }
+          uint32_t v[16];
+          tc_ld16(tbase + (uint32_t)(sub * C + c0), v);
+          tc_ld_wait();
+          int b, t;
+          size_t o;
+          if (row_of(sub, b, t, o)) epi_apply16<T>(ep, b, t, c0, o + c0, v, pre[u & 1], 2);
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -719,13 +719,13 @@ int launch_conv_ws(std::vector<MapCacheEntry>& map_cache, int num_sms, const Con
 }
 
 // ---- one ResBlock unit (two convolutions) in one persistent kernel (conv_umma.cuh, resunit_umma_kernel) ---------------------
-template <typename T, int C, int BK>
+template <typename T, int C, int BK, int MS>
 int launch_ru_inst(const umma::ParamsRU<T>& P, int grid, size_t smem, cudaStream_t st) {
   static unsigned long long attr_set = 0ull;        // one bit per device
   int dev = 0;
   GSV_CUDA(cudaGetDevice(&dev));
   if (!((attr_set >> (dev & 63)) & 1ull)) {
-    GSV_CUDA(cudaFuncSetAttribute(umma::resunit_umma_kernel<T, C, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsBudget));
+    GSV_CUDA(cudaFuncSetAttribute(umma::resunit_umma_kernel<T, C, BK, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWsBudget));
     attr_set |= 1ull << (dev & 63);
   }
   static int use_pdl = -1;
@@ -737,7 +737,7 @@ int launch_ru_inst(const umma::ParamsRU<T>& P, int grid, size_t smem, cudaStream
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::resunit_umma_kernel<T, C, BK>, P));
+  GSV_CUDA(cudaLaunchKernelEx(&cfg, umma::resunit_umma_kernel<T, C, BK, MS>, P));
   return GSV_OK;
 }
 
@@ -763,9 +763,10 @@ int launch_resunit(gsv_voc_ctx* ctx, const ConvArgs<T>& a1, const ConvArgs<T>& a
   const int a_stage = (a_rows * bk * 2 + 1023) & ~1023;
   const int w_stage = (C * bk * 2 + 1023) & ~1023;
   const int a2_bytes = ((umma::BM + 16) * bk * 2 + 1023) & ~1023;
-  const size_t fixed = (size_t)2 * KW * w_stage + (size_t)2 * a2_bytes + 1024;
-  int sa = 4;
-  while (sa > 2 && fixed + (size_t)sa * a_stage > kWsBudget) --sa;
+  const int ms = C <= 32 ? 4 : 1;           // tiles per hand-over chain (resunit_umma_kernel)
+  const size_t fixed = (size_t)2 * KW * w_stage + (size_t)2 * ms * a2_bytes + 1024;
+  int sa = 2 * ms < 4 ? 4 : 2 * ms;
+  while (sa > ms + 1 && sa > 2 && fixed + (size_t)sa * a_stage > kWsBudget) --sa;
   if (fixed + (size_t)sa * a_stage > kWsBudget) return GSV_OK;
   umma::ParamsRU<T> P;
   const bool bf16 = std::is_same<T, __nv_bfloat16>::value;
@@ -782,12 +783,13 @@ int launch_resunit(gsv_voc_ctx* ctx, const ConvArgs<T>& a1, const ConvArgs<T>& a
   P.a_rows = a_rows; P.a_stage_bytes = a_stage; P.sa = sa; P.a2_bytes = a2_bytes;
   P.bias1 = a1.bias; P.act1 = a1.act;
   P.ep = a2;
-  const int grid = n_tiles < ctx->num_sms ? (int)n_tiles : ctx->num_sms;
+  const long long n_units = (n_tiles + ms - 1) / ms;
+  const int grid = n_units < ctx->num_sms ? (int)n_units : ctx->num_sms;
   const size_t smem = fixed + (size_t)sa * a_stage;
-  if (C == 64) rc = launch_ru_inst<T, 64, 64>(P, grid, smem, st);
-  else if (C == 48) rc = launch_ru_inst<T, 48, 64>(P, grid, smem, st);
-  else if (C == 32) rc = launch_ru_inst<T, 32, 32>(P, grid, smem, st);
-  else rc = launch_ru_inst<T, 16, 16>(P, grid, smem, st);
+  if (C == 64) rc = launch_ru_inst<T, 64, 64, 1>(P, grid, smem, st);
+  else if (C == 48) rc = launch_ru_inst<T, 48, 64, 1>(P, grid, smem, st);
+  else if (C == 32) rc = launch_ru_inst<T, 32, 32, 4>(P, grid, smem, st);
+  else rc = launch_ru_inst<T, 16, 16, 4>(P, grid, smem, st);
   if (rc) return rc;
   GSV_CHECK_LAUNCH();
   ctx->op_index += 2;                       // the two call sites' tensor-map cache slots stay theirs
