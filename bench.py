@@ -460,7 +460,7 @@ def main():
     if rank == 0:
         n_chunks = N_TOK // CHUNK
         h2d = sum(t.numel() * t.element_size() for t in host_in.values()) + (NX + N_TEXT) * 8
-        d2h = 2 * N_TOK * 640 * 4 + n_chunks * (512 * 4 + 8) + n_chunks * 3 * 4       # audio (fp32), tokens + state per chunk, glue offsets
+        d2h = (2 * N_TOK + 5 * (n_chunks - 1)) * 640 * 4 + n_chunks * (512 * 4 + 8) + n_chunks * 2 * 4   # audio buffers (fp32, whole, cut on the host), tokens + state per chunk, glue offsets
         ref_gpu = None
         try:
             with open(os.path.join(ROOT, "profiles", "r02_ref_gpu_baseline.json")) as f:

@@ -278,8 +278,10 @@ struct gsv_encp_ctx {
   int num_sms;
   void* scratch;
   size_t scratch_bytes;
-  void* overlap;              // y_overlap [ov][C] T
+  void* overlap;              // y_overlap: two buffers [2][64][C] T; a streaming call reads [ov_cur] and writes [ov_cur ^ 1]
+  int ov_cur;
   int overlap_len;            // 0: none (first chunk / after reset)
+  int overlap_len_prev;       // state before the last streaming call (gsv_encp_stream_rollback); -1: nothing to undo
   long long launches;
   size_t op;                  // call-site counter of the tensor-core launches of one forward
   std::vector<void*> owned;
@@ -436,10 +438,15 @@ int encp_forward_t(gsv_encp_ctx* ctx, const int64_t* codes, int n_codes, const i
   int Tc = Tn;
   if (stream_mode) {
     const bool has_prev = ctx->overlap_len == overlap_len && ctx->overlap != nullptr;
-    if (!ctx->overlap) GSV_CUDA(cudaMalloc(&ctx->overlap, (size_t)64 * C * el));
+    if (!ctx->overlap) GSV_CUDA(cudaMalloc(&ctx->overlap, (size_t)2 * 64 * C * el));
     Tc = Tn - valid_start;
-    stream_fade_kernel<T><<<Tc, 64, 0, st>>>(y, valid_start, Tn, C, overlap_len, reinterpret_cast<T*>(ctx->overlap), has_prev ? 1 : 0, y3);
-    keep_tail_kernel<T><<<overlap_len, 64, 0, st>>>(y3, Tc, C, overlap_len, reinterpret_cast<T*>(ctx->overlap));
+    // the previous tail is left intact (the new one goes to the other buffer): one call can be undone, in stream order
+    T* ov_prev = reinterpret_cast<T*>(ctx->overlap) + (size_t)ctx->ov_cur * 64 * C;
+    T* ov_next = reinterpret_cast<T*>(ctx->overlap) + (size_t)(ctx->ov_cur ^ 1) * 64 * C;
+    stream_fade_kernel<T><<<Tc, 64, 0, st>>>(y, valid_start, Tn, C, overlap_len, ov_prev, has_prev ? 1 : 0, y3);
+    keep_tail_kernel<T><<<overlap_len, 64, 0, st>>>(y3, Tc, C, overlap_len, ov_next);
+    ctx->overlap_len_prev = ctx->overlap_len;
+    ctx->ov_cur ^= 1;
     ctx->overlap_len = overlap_len;
     ctx->launches += 2;
     cur = y3;
@@ -471,7 +478,7 @@ extern "C" int gsv_encp_create(const gsv_encp_dims* dims, gsv_encp_ctx** out) {
   gsv_encp_ctx* ctx = new (std::nothrow) gsv_encp_ctx();
   GSV_ARG(ctx != nullptr);
   ctx->dims = *dims;
-  ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->overlap = nullptr; ctx->overlap_len = 0; ctx->launches = 0; ctx->op = 0;
+  ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->overlap = nullptr; ctx->ov_cur = 0; ctx->overlap_len = 0; ctx->overlap_len_prev = -1; ctx->launches = 0; ctx->op = 0;
   GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
   ctx->umma = gsv_umma_cache_create(ctx->num_sms);
   *out = ctx;
@@ -497,6 +504,18 @@ extern "C" int gsv_encp_destroy(gsv_encp_ctx* ctx) {
 extern "C" int gsv_encp_reset_stream(gsv_encp_ctx* ctx) {
   GSV_ARG(ctx);
   ctx->overlap_len = 0;
+  ctx->overlap_len_prev = -1;
+  return GSV_OK;
+}
+
+// Undo the last streaming call's effect on the cross-chunk state (a chunk computed ahead of time that the stream then
+// merged into its final chunk, TTS.infer_phones_stream): the previous tail is still in its buffer.  One level.
+extern "C" int gsv_encp_stream_rollback(gsv_encp_ctx* ctx) {
+  GSV_ARG(ctx);
+  if (ctx->overlap_len_prev < 0) { gsv_set_error("gsv_encp_stream_rollback: no streaming call to undo"); return GSV_ERR_STATE; }
+  ctx->ov_cur ^= 1;
+  ctx->overlap_len = ctx->overlap_len_prev;
+  ctx->overlap_len_prev = -1;
   return GSV_OK;
 }
 

@@ -356,10 +356,14 @@ class Text2SemanticDecoder(nn.Module):
     def infer_stream(self, x, y, bert_feature, top_k: int = 15, top_p: float = 1.0, temperature: float = 1.0,
                      repetition_penalty: float = 1.35, initial_suppression_steps: int = 10, stream_chunk: int = 25,
                      boost_first_chunk: bool = True, debug: bool = True,
-                     force_steps: Optional[int] = None) -> Iterator[Tuple[torch.Tensor, bool]]:
+                     force_steps: Optional[int] = None, on_chunk_held=None) -> Iterator[Tuple[torch.Tensor, bool]]:
         """t2s_model.py:466-553: yields (tokens so far [1,1,n], is_final) every ``stream_chunk`` tokens,
         one chunk late unless ``boost_first_chunk``; the final yield after an EOS break carries the
-        first sampled token (the reference slices ``[-idx:]`` with idx one past the appended count)."""
+        first sampled token (the reference slices ``[-idx:]`` with idx one past the appended count).
+        ``on_chunk_held(tokens)`` (not in the reference) is called with a chunk the moment it is complete when the
+        reference's order holds it back until the next one exists -- the same tensor object is yielded later, or never (the
+        stream ended first and the final yield covers it); it is not called for a chunk that is already known to be
+        dropped.  A consumer may start that chunk's work early, speculatively."""
         hp = self._high_priority_stream()
         self._stream_waits_for_current(hp)                                # inputs produced on the caller's stream
         with self._on_stream(hp):
@@ -424,6 +428,8 @@ class Text2SemanticDecoder(nn.Module):
                     first = False
                     yield pre_chunk, False
                     pre_chunk = None
+                elif in_flight and on_chunk_held is not None:
+                    on_chunk_held(pre_chunk)
             if in_flight:
                 queued = launch()
         if not launched:                              # nothing to decode (force_steps = 0): the first sampled token alone

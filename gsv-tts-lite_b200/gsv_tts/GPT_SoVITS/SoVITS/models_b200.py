@@ -190,6 +190,11 @@ class _PriorEncoderState:
         if self._owner._enc_ctx is not None:
             N.check(N.lib().gsv_encp_reset_stream(self._owner._enc_ctx))
 
+    def rollback(self):
+        """Undo the last ``decode(stream_mode=True)``'s update of the cross-chunk state (one level): for a chunk that was
+        decoded ahead of time and then dropped (``TTS.infer_phones_stream``)."""
+        N.check(N.lib().gsv_encp_stream_rollback(self._owner._enc_ctx))
+
 
 class SynthesizerTrn(FlowDecoder):
     """``SynthesizerTrn`` as ``Loader.get_sovits_weights`` builds it (reference SoVITS/models.py:235-429), inference half:

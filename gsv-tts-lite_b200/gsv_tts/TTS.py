@@ -321,7 +321,8 @@ class TTS:
         N.check(N.lib().gsv_glue_viterbi_monotonic(attn.data_ptr(), H, T, Nn, work.data_ptr(), assign.data_ptr(), st))
         return assign.to(torch.int64)
 
-    def _silence_offset(self, audio: torch.Tensor, tail: bool, threshold, frame_length, hop_length, search_len, margin) -> int:
+    def _silence_offset_enqueue(self, audio: torch.Tensor, tail: bool, threshold, frame_length, hop_length, search_len, margin) -> torch.Tensor:
+        """The search kernel enqueued on the current stream; the offset stays on the device (int32 [1])."""
         import ctypes as C
         N, code = self._native_dtype(audio)
         audio = audio.contiguous()
@@ -330,7 +331,10 @@ class TTS:
         st = C.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)
         N.check(N.lib().gsv_glue_silence_offset(audio.data_ptr(), audio.numel(), code, 1 if tail else 0, float(threshold), frame_length,
                                                 hop_length, search_len, margin, work.data_ptr(), out.data_ptr(), st))
-        return int(out.item())
+        return out
+
+    def _silence_offset(self, audio: torch.Tensor, tail: bool, threshold, frame_length, hop_length, search_len, margin) -> int:
+        return int(self._silence_offset_enqueue(audio, tail, threshold, frame_length, hop_length, search_len, margin).item())
 
     def _find_head_threshold_offsets(self, audio, threshold=0.02, frame_length=512, hop_length=256, search_len=64000, margin=3200):
         """TTS.py:1630-1645 (frame RMS in fp32 here; the reference squares and averages in the 16-bit storage type)."""
@@ -340,8 +344,9 @@ class TTS:
         """TTS.py:1647-1662."""
         return self._silence_offset(audio, True, threshold, frame_length, hop_length, search_len, margin)
 
-    def _sola_algorithm(self, f1_overlap, f2, overlap_len, search_len: int = 320):
-        """TTS.py:1612-1628: f1_overlap [1,1,ov], f2 [1,1,n] -> (f2 aligned and cross-faded [1,1,n - offset], offset tensor)."""
+    def _sola_enqueue(self, f1_overlap, f2, overlap_len, search_len: int = 320):
+        """The SOLA kernels enqueued on the current stream, nothing read back: -> (buffer [n2] whose first n2 - offset samples
+        are f2 aligned and cross-faded, offset int32 [1] on the device)."""
         import ctypes as C
         N, code = self._native_dtype(f2)
         f1, f2c = f1_overlap.reshape(-1).contiguous(), f2.reshape(-1).contiguous()
@@ -352,8 +357,13 @@ class TTS:
         st = C.c_void_p(torch.cuda.current_stream(f2.device).cuda_stream)
         N.check(N.lib().gsv_glue_sola(f1.data_ptr(), f2c.data_ptr(), n2, int(overlap_len), int(search_len), code, work.data_ptr(),
                                       off.data_ptr(), out.data_ptr(), st))
+        return out, off
+
+    def _sola_algorithm(self, f1_overlap, f2, overlap_len, search_len: int = 320):
+        """TTS.py:1612-1628: f1_overlap [1,1,ov], f2 [1,1,n] -> (f2 aligned and cross-faded [1,1,n - offset], offset tensor)."""
+        out, off = self._sola_enqueue(f1_overlap, f2, overlap_len, search_len)
         k = int(off.item())
-        return out[: n2 - k].view(1, 1, -1), off
+        return out[: out.numel() - k].view(1, 1, -1), off
 
     def _get_subtitles(self, word2ph, assign, speed, last_end_s=0):
         """TTS.py:1664-1707: frame alignment -> word timings (host arithmetic on T small integers)."""
@@ -427,12 +437,20 @@ class TTS:
                             bert2: torch.Tensor, ge: torch.Tensor, stream_chunk: int = 25, overlap_len: int = 5,
                             boost_first_chunk: bool = True, cut_mute: float = 0.4, top_k: int = 15, top_p: float = 1.0,
                             temperature: float = 1.0, repetition_penalty: float = 1.35, noise_scale: float = 0.5, speed: float = 1.0,
-                            gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, force_steps: Optional[int] = None):
+                            gpt_model: Optional[str] = None, sovits_model: Optional[str] = None, force_steps: Optional[int] = None,
+                            decode_ahead: bool = True):
         """One text cut of ``TTS.infer_stream`` (TTS.py:402-498): every ``stream_chunk`` semantic tokens the whole prefix goes
         through ``vq_model.decode(stream_mode=True)``; chunks are spliced with SOLA over ``overlap_len`` frames, the first one
         loses its leading silence, the last one gets ``cut_mute`` seconds of silence.  Yields one ``AudioClip`` per chunk.
         The decode of chunk c+1 is already in flight on the GPT's SMs while chunk c goes through the prior encoder and the
-        vocoder on a second stream."""
+        vocoder on a second stream.
+
+        The reference hands a chunk to the SoVITS stage one chunk late (t2s_model.py:540-547: only when the next one exists,
+        so that a short remainder is merged into the last full chunk).  ``decode_ahead`` keeps that order of clips but starts
+        a held-back chunk's SoVITS stage the moment its tokens exist (``on_chunk_held`` of ``infer_stream``), without any host
+        synchronisation; when the stream yields the chunk its clip is already in pinned host memory.  If the stream ends
+        before the next boundary the chunk decoded ahead is dropped and the cross-chunk state (``enc_p.y_overlap``, the SOLA
+        tail, ``valid_start_idx``) is rolled back -- the clips are the same as with ``decode_ahead=False`` (tested)."""
         gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
         vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         dev = self.tts_config.device
@@ -443,9 +461,59 @@ class TTS:
             ph2 = torch.tensor(list(phones2), dtype=torch.int64, device=dev).unsqueeze(0)
             ge = ge.to(dev)
         overlap_samples = overlap_len * vq.samples_per_frame
-        audio_len_s, last_overlap, valid_start, chunk_idx = 0.0, None, 0, 0
+        st = {"last_overlap": None, "valid_start": 0, "chunk_idx": 0}       # cross-chunk state of the SoVITS stage
+        held = {}                                                             # id(tokens) -> (tokens, staged work, state before it)
+
+        def stage(pred, is_final):
+            """The SoVITS stage of one chunk enqueued on the side stream; nothing is read back here.  Offsets (SOLA alignment,
+            leading silence) stay on the device: the buffers travel to pinned host memory whole and are cut in ``collect``."""
+            with torch.inference_mode(), torch.cuda.stream(side):
+                side.wait_event(gpt.chunk_ready)
+                gpt.hold_until_decode_resident(side)
+                pred.record_stream(side)
+                audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed, stream_mode=True,
+                                        valid_start_idx=st["valid_start"], overlap_len=overlap_len)
+                flat = audio.reshape(-1)
+                n2 = flat.numel()
+                meta = torch.zeros(2, dtype=torch.int32, device=dev)          # SOLA offset, leading-silence offset
+                if st["last_overlap"] is not None:
+                    flat, off = self._sola_enqueue(st["last_overlap"], flat, overlap_samples)
+                    meta[0:1].copy_(off)
+                    tail = (n2 - overlap_samples) - off.to(torch.int64) + torch.arange(overlap_samples, device=dev)
+                    st["last_overlap"] = flat[tail]                          # the last overlap_samples of the n2 - offset valid ones
+                else:
+                    st["last_overlap"] = flat[n2 - overlap_samples:].clone()
+                if not is_final:
+                    st["valid_start"] = attn.shape[1] - overlap_len
+                if st["chunk_idx"] == 0:                                     # never spliced: its length is known here
+                    body = flat if is_final else flat[: n2 - overlap_samples]
+                    meta[1:2].copy_(self._silence_offset_enqueue(body, False, 0.02, 512, 256, 64000, 3200))
+                st["chunk_idx"] += 1
+                host = torch.empty(n2, dtype=torch.float32, pin_memory=True)
+                host.copy_(flat, non_blocking=True)
+                host_meta = torch.empty(2, dtype=torch.int32, pin_memory=True)
+                host_meta.copy_(meta, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return host, host_meta, ev, n2, is_final
+
+        def collect(work) -> np.ndarray:
+            host, host_meta, ev, n2, is_final = work
+            ev.synchronize()
+            end = n2 - int(host_meta[0]) - (0 if is_final else overlap_samples)
+            out = host[int(host_meta[1]):end].numpy().copy()
+            if is_final:
+                out = np.concatenate([out, np.zeros(int(cut_mute * self.samplerate), dtype=out.dtype)])
+            return out
+
+        def on_held(pred):
+            before = dict(st)
+            held[id(pred)] = (pred, stage(pred, False), before)
+
+        audio_len_s = 0.0
         it = gpt.infer_stream(ids, prompt, bert, top_k=top_k, top_p=top_p, temperature=temperature, repetition_penalty=repetition_penalty,
-                              stream_chunk=stream_chunk, boost_first_chunk=boost_first_chunk, force_steps=force_steps)
+                              stream_chunk=stream_chunk, boost_first_chunk=boost_first_chunk, force_steps=force_steps,
+                              on_chunk_held=on_held if decode_ahead else None)
         try:
             while True:
                 with torch.inference_mode():
@@ -453,26 +521,17 @@ class TTS:
                         pred, is_final = next(it)
                     except StopIteration:
                         break
-                    with torch.cuda.stream(side):
-                        side.wait_event(gpt.chunk_ready)
-                        gpt.hold_until_decode_resident(side)
-                        pred.record_stream(side)
-                        audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed, stream_mode=True,
-                                                valid_start_idx=valid_start, overlap_len=overlap_len)
-                        if last_overlap is not None:
-                            audio, _ = self._sola_algorithm(last_overlap, audio, overlap_samples)
-                        last_overlap = audio[:, :, -overlap_samples:].clone()
-                        if not is_final:
-                            audio = audio[:, :, :-overlap_samples]
-                            valid_start = attn.shape[1] - overlap_len
-                        audio = audio[0, 0, :]
-                        if chunk_idx == 0:
-                            audio = audio[self._find_head_threshold_offsets(audio):]
-                        if is_final:
-                            audio = torch.cat([audio, torch.zeros(int(cut_mute * self.samplerate), dtype=audio.dtype, device=dev)])
-                        out = audio.float().cpu().numpy()
+                ahead = held.pop(id(pred), None)
+                if ahead is not None:
+                    work = ahead[1]
+                else:
+                    if held:                                   # the stream ended before the next boundary: drop the chunk decoded ahead
+                        _, (_p, _w, before) = held.popitem()
+                        st.update(before)
+                        vq.enc_p.rollback()
+                    work = stage(pred, is_final)
+                out = collect(work)
                 audio_len_s += len(out) / self.samplerate
-                chunk_idx += 1
                 yield AudioClip(out, self.samplerate, audio_len_s=audio_len_s)
         finally:
             vq.enc_p.y_overlap = None                      # TTS.py:498

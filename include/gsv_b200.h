@@ -289,6 +289,10 @@ int gsv_encp_forward(gsv_encp_ctx* ctx, const int64_t* dev_codes, int n_codes, c
                      const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p, float* dev_logs_p,
                      float* dev_attn, int* out_frames, void* stream);
 int gsv_encp_reset_stream(gsv_encp_ctx* ctx);
+/* Undo the last stream_mode call's update of the cross-chunk state (one level; the previous tail is kept in a second
+ * buffer): TTS.infer_phones_stream computes a held-back chunk ahead of time and drops it when the stream ends before the
+ * next chunk boundary (the reference never decodes that chunk: t2s_model.py:540-553 merges it into the final one). */
+int gsv_encp_stream_rollback(gsv_encp_ctx* ctx);
 int64_t gsv_encp_launch_count(gsv_encp_ctx* ctx);
 
 /* ======================================================================================

@@ -152,3 +152,25 @@ def test_infer_phones_stream_splices_chunks_like_the_reference(tts):
     for c, a in zip(clips, want):
         assert float(np.abs(c.audio_data - a).max()) < 5e-3      # the kernel cross-fades in the 16-bit storage type
     assert abs(clips[-1].audio_len_s - sum(len(a) for a in want) / 32000) < 1e-6
+
+
+@pytest.mark.parametrize("force", [34, 40, 30, 9, None])
+def test_chunks_decoded_ahead_give_the_same_clips(tts, force):
+    """``decode_ahead`` starts a held-back chunk's SoVITS stage early and rolls the cross-chunk state back when the stream
+    ends before the next boundary (34: the chunk of 30 is dropped; 40 / 30: ends on a boundary; 9: shorter than a chunk; None:
+    until EOS or the cache cap): the clips must be the ones of the one-chunk-late order, bit for bit."""
+    fe = StandInFrontEnd(512)
+    gpt = next(iter(tts.gpt_models.values())).t2s_model
+    vq = next(iter(tts.sovits_models.values())).vq_model
+    phones2, _, bert2, _ = fe.phones_and_bert("a streaming sentence, decoded ahead.")
+    runs = []
+    for ahead in (False, True):
+        gpt.debug_seed, vq.debug_seed = 43, 11
+        runs.append(list(tts.infer_phones_stream(fe.phones1, fe.bert1, fe.prompt_tokens, phones2, bert2, fe.ge, stream_chunk=10,
+                                                 overlap_len=5, force_steps=force, decode_ahead=ahead)))
+    a, b = runs
+    assert len(a) == len(b) and len(a) >= 1
+    for ca, cb in zip(a, b):
+        assert ca.audio_data.shape == cb.audio_data.shape
+        assert float(np.abs(ca.audio_data - cb.audio_data).max()) == 0.0 if ca.audio_data.size else True
+        assert abs(ca.audio_len_s - cb.audio_len_s) < 1e-9
