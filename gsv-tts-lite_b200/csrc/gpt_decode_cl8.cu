@@ -571,6 +571,8 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
     // ================= sampling: CTA n samples sequence n; next inputs and alive flags pushed to every CTA ==================
     if ((int)rank < NB8 && ((livemask >> rank) & 1u)) {
       const int n = (int)rank;
+      SamplePre pre;                                     // the sampler's own global reads overlap the wait for the logits
+      sample_prefetch<T>(p, sh.slot[n], sh.kv[n] + 1, pre);
       mbar_wait(&sh.xbar[3], parL); parL ^= 1u;          // all V logits of sequence n have arrived
       SampleLL io;
       io.preloaded = true;
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_cl8_kernel(const GptParams p
       io.kv_len = sh.kv[n] + 1;
       io.xin_smem = xin_s;
       io.alive_smem = &sh.alive_i;
-      sample_slot<T>(p, sh.slot[n], samp, &io);
+      sample_slot<T>(p, sh.slot[n], samp, &io, &pre);
       __syncthreads();
       const bool still = sh.alive_i != 0;
       if (tid == 0 && still) mbar_expect_tx(&sh.xbar[3], (unsigned)V * 4u);           // re-armed before anyone can refill it

@@ -646,6 +646,9 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
     const unsigned tag_logits = tag;
     tag += 1;
     if (j == 0) {
+      mark_sampler(p, 58);
+      SamplePre pre;                          // the sampler's own global reads, issued before the wait for the logits
+      sample_prefetch<T>(p, slot, kv + 1, pre);
       {                                       // every word of this thread in flight (GSV_VOCAB_MAX / NT = 4)
         uint2 w[GSV_VOCAB_MAX / NT];
 #pragma unroll
@@ -663,6 +666,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
         for (int u = 0; u < GSV_VOCAB_MAX / NT; ++u) if (tid + u * NT < V) samp[tid + u * NT] = __uint_as_float(w[u].x);
       }
       __syncthreads();
+      mark_sampler(p, 59);
       SampleLL io;
       io.preloaded = true;
       io.xin_ll = LLxin;
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(NT, 1) gpt_decode_hx_kernel(const GptParams p,
       io.kv_len = kv + 1;
       io.xin_smem = nullptr;
       io.alive_smem = nullptr;
-      sample_slot<T>(p, slot, samp, &io);
+      sample_slot<T>(p, slot, samp, &io, &pre);
     }
     if (tid == 0) sh.alive = ll_wait(LLstat, tag) != 0.f ? 1 : 0;
     __syncthreads();

@@ -81,20 +81,77 @@ __device__ __forceinline__ float ll_wait(const uint2* p, unsigned tag) {
   return __uint_as_float(v.x);
 }
 
+// What sample_slot reads from global memory before it can touch a logit: a caller that has to wait for the logits anyway
+// (the single-sequence kernel polls them out of L2) issues these loads first and hands them over, so that their L2 round
+// trips overlap the wait instead of following it.
+struct SamplePre {
+  gsv_gpt_sampling sp;
+  int ngen;
+  unsigned long long cnt;
+  unsigned seen[GSV_VOCAB_MAX / GSV_DECODE_THREADS];      // bitmap word of each of this thread's columns (tid + i * 512)
+  int x_len;
+  int pe_pos;                                             // row of the positional table the next input will use (-1: not fetched)
+  float pe;                                               // ... and its element threadIdx.x
+};
+// kv_len: the slot's cache length AFTER the step being sampled (what SampleLL.kv_len will carry), or -1 if unknown
 template <typename T>
-__device__ void sample_slot(const GptParams& p, int slot, float* sm, const SampleLL* ll = nullptr) {
+__device__ __forceinline__ void sample_prefetch(const GptParams& p, int slot, int kv_len, SamplePre& o) {
+  o.x_len = ld_cg(p.x_len + slot);
+  o.sp = p.samp[slot];
+  o.ngen = ld_cg(p.n_gen + slot);
+  o.cnt = __ldcg(p.samp_count + slot);
+  const unsigned* seen = p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32);
+#pragma unroll
+  for (int i = 0; i < GSV_VOCAB_MAX / GSV_DECODE_THREADS; ++i) {
+    const int v = threadIdx.x + i * GSV_DECODE_THREADS;
+    o.seen[i] = v < p.V ? __ldcg(seen + (v >> 5)) : 0u;
+  }
+  o.pe_pos = -1;
+  o.pe = 0.f;
+  if (kv_len >= 0 && (int)threadIdx.x < p.d) {
+    o.pe_pos = max(0, min(kv_len - o.x_len, p.n_pos - 1));
+    o.pe = Elem<T>::to_f(reinterpret_cast<const T*>(p.pe_audio)[(size_t)o.pe_pos * p.d + threadIdx.x]);
+  }
+}
+
+// Timeline of the sampler (tuning builds, -DGSV_TIMELINE; tools/hx_timeline.py): {id, globaltimer} records of thread 0 in the
+// region behind the per-CTA regions of the kernel's own markers.
+__device__ __forceinline__ void mark_sampler(const GptParams& p, int id) {
+#ifdef GSV_TIMELINE
+  if (p.prof != nullptr && threadIdx.x == 0) {
+    long long* rec = p.prof + (size_t)gridDim.x * 2 * p.prof_max;
+    const long long n = rec[0];
+    if (n + 1 < p.prof_max) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      rec[2 * (n + 1)] = id;
+      rec[2 * (n + 1) + 1] = (long long)gt;
+      rec[0] = n + 1;
+    }
+  }
+#else
+  (void)p; (void)id;
+#endif
+}
+
+// Candidates the fast top-k path keeps in shared memory before it falls back to the radix select
+#define GSV_SAMPLE_CAND_MAX 256
+
+template <typename T>
+__device__ void sample_slot(const GptParams& p, int slot, float* sm, const SampleLL* ll = nullptr, const SamplePre* pre = nullptr) {
   float* lg = sm;                                         // [GSV_VOCAB_MAX] working logits
   int* sidx = reinterpret_cast<int*>(sm + GSV_VOCAB_MAX); // [GSV_VOCAB_MAX] sort indices (top-p only)
   float* kbuf = sm + 2 * GSV_VOCAB_MAX;                   // [GSV_VOCAB_MAX] exp() in sorted order (top-p only)
   float* red_v = sm + 3 * GSV_VOCAB_MAX;                  // [32]
   int* red_i = reinterpret_cast<int*>(red_v + 32);        // [32]
   const int tid = threadIdx.x, NT = blockDim.x;
-  const gsv_gpt_sampling sp = p.samp[slot];
-  const int ngen = ld_cg(p.n_gen + slot);
+  const gsv_gpt_sampling sp = pre ? pre->sp : p.samp[slot];
+  const int ngen = pre ? pre->ngen : ld_cg(p.n_gen + slot);
   const bool first = ngen == 0;
   const int Vv = first ? p.V - 1 : p.V;                   // first sample: EOS column sliced off (:417)
-  const unsigned long long cnt = __ldcg(p.samp_count + slot);
+  const unsigned long long cnt = pre ? pre->cnt : __ldcg(p.samp_count + slot);
   __syncthreads();
+  mark_sampler(p, 60);
 
   // raw logits (+ optional trace of the slot for the teacher-forced / audited parity tests)
   GptSlotHooks* const hk = p.hooks ? p.hooks + slot : nullptr;     // CTA-uniform
@@ -111,6 +168,163 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
     }
   }
   const bool preloaded = ll != nullptr && ll->preloaded;
+  const bool suppress = first ? (sp.suppress_first != 0) : (ngen < sp.suppress_steps);
+  const float rp = sp.repetition_penalty;
+  const bool ext = hk_noise != nullptr && cnt < (unsigned long long)hk_noise_rows;
+  const uint2 key = make_uint2((uint32_t)sp.seed, (uint32_t)(sp.seed >> 32));
+  int tok = -1;
+
+  // ---- fast path: no top-p, 1 <= top_k <= 32 (the reference's defaults: top_k 15, top_p 1) ------------------------------
+  // Same arithmetic per column as the general path below, but nothing is sorted or histogrammed: every thread keeps its
+  // columns in registers through the masks, the repetition penalty and the temperature; the 32 half-warps publish their
+  // maxima, whose k-th largest L is a lower bound of the top-k pivot (k disjoint groups hold a value >= L); the few
+  // columns >= L (about k ln(32/k) + k of them) are compacted into shared memory, the pivot is the candidate with fewer
+  // than k candidates above it and at least k at or above it (ties counted, as torch.topk's k-th value), and ONE warp
+  // finishes: exp, sum, Exp(1) noise for the survivors only (a column with probability 0 cannot win the arg-max: q > 0),
+  // arg-max with ties to the lower index.  5 block barriers instead of ~25 and no contended shared-memory atomics (the
+  // top byte of the radix keys -- sign and exponent -- put nearly all 1025 columns into 2-3 bins).
+  const int kk = min(sp.top_k, Vv);
+  if (sp.top_p >= 1.0f && sp.top_k > 0 && kk <= 32 && NT == GSV_DECODE_THREADS) {
+    constexpr int PER = GSV_VOCAB_MAX / GSV_DECODE_THREADS;
+    float* cand_v = kbuf;                                 // [GSV_SAMPLE_CAND_MAX]
+    int* cand_i = sidx;                                   // [GSV_SAMPLE_CAND_MAX]
+    int* n_cand = red_i;                                  // red_i[0]: candidates, red_i[1]: token
+    float* pivot_s = red_v + 40;                          // (red_v[0..31]: group maxima; 32 floats past them belong to red_i)
+    const int lane = tid & 31, warp = tid >> 5;
+    const float temp = fmaxf(sp.temperature, 1e-5f);
+    const unsigned* seen = p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32);
+    float x[PER];
+    float gm = GSV_NEG_INF;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int v = tid + i * GSV_DECODE_THREADS;
+      float l = GSV_NEG_INF;
+      if (v < p.V) {
+        l = preloaded ? lg[v] : ld_cg(p.logits + (size_t)slot * GSV_VOCAB_MAX + v);
+        if (trow >= 0) hk_trace[(size_t)trow * p.V + v] = l;
+        if (v >= Vv) l = GSV_NEG_INF;
+        if (suppress && (v == 280 || v == 486 || v == p.eos)) l = GSV_NEG_INF;
+        if (sp.mask_eos && v == p.eos) l = GSV_NEG_INF;
+        if (rp != 1.0f && v < Vv) {
+          const unsigned word = pre ? pre->seen[i] : __ldcg(seen + (v >> 5));
+          if ((word >> (v & 31)) & 1u) l = l < 0.f ? l * rp : l / rp;
+        }
+        if (temp != 1.0f && v < Vv) l = l / temp;
+      }
+      x[i] = l;
+      lg[v] = l;                                          // the general path's input, should the candidates overflow
+      gm = fmaxf(gm, l);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    if ((lane & 15) == 0) red_v[2 * warp + (lane >> 4)] = gm;
+    if (tid == 0) {
+      n_cand[0] = 0;
+      if (trow >= 0) st_cg(&hk->trace_pos, trow + 1);
+    }
+    __syncthreads();
+    mark_sampler(p, 61);
+    // every warp: the k-th largest of the 32 group maxima (lane = group) and the overall maximum
+    float L, mx;
+    {
+      const float g = red_v[lane];
+      int gt = 0, ge = 0;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 o = reinterpret_cast<const float4*>(red_v)[j4];
+        gt += (o.x > g) + (o.y > g) + (o.z > g) + (o.w > g);
+        ge += (o.x >= g) + (o.y >= g) + (o.z >= g) + (o.w >= g);
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, gt < kk && kk <= ge);
+      L = __shfl_sync(0xffffffffu, g, __ffs(hit) - 1);
+      mx = warp_max(g);
+    }
+    // compaction of the columns >= L: one shared-memory atomic per warp
+    {
+      unsigned m[PER];
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        m[i] = __ballot_sync(0xffffffffu, tid + i * GSV_DECODE_THREADS < Vv && x[i] >= L);
+        n += __popc(m[i]);
+      }
+      int base = 0;
+      if (lane == 0 && n > 0) base = atomicAdd(n_cand, n);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        if ((m[i] >> lane) & 1u) {
+          const int pos = base + __popc(m[i] & below);
+          if (pos < GSV_SAMPLE_CAND_MAX) { cand_v[pos] = x[i]; cand_i[pos] = tid + i * GSV_DECODE_THREADS; }
+        }
+        base += __popc(m[i]);
+      }
+    }
+    __syncthreads();
+    mark_sampler(p, 62);
+    const int C = n_cand[0];
+    if (C <= GSV_SAMPLE_CAND_MAX && L > GSV_NEG_INF) {
+      // pivot: candidate c with  #(candidates > c) < k <= #(candidates >= c)
+      if (tid < C) {
+        const float c = cand_v[tid];
+        int gt = 0, ge = 0;
+        for (int j = 0; j < C; ++j) {
+          const float o = cand_v[j];
+          gt += o > c;
+          ge += o >= c;
+        }
+        if (gt < kk && kk <= ge) *pivot_s = c;            // every hit holds the same value
+      }
+      __syncthreads();
+      mark_sampler(p, 63);
+      if (warp == 0) {
+        const float pivot = *pivot_s;
+        float part = 0.f;
+        for (int c = lane; c < C; c += 32) {
+          const float xv = cand_v[c];
+          if (xv >= pivot) part += __expf(xv - mx);
+        }
+        const float total = warp_sum(part);
+        const float inv_total = 1.0f / total;
+        ArgMax best;
+        best.v = -1.0f; best.i = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+          const float xv = cand_v[c];
+          if (xv >= pivot) {
+            const int v = cand_i[c];
+            float q;
+            if (ext) {
+              q = hk_noise[(size_t)cnt * p.V + v];
+            } else {
+              uint4 r = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)(v >> 2), 0u), key);
+              uint32_t bits = (v & 3) == 0 ? r.x : (v & 3) == 1 ? r.y : (v & 3) == 2 ? r.z : r.w;
+              q = exp1_from_bits(bits);
+            }
+            ArgMax b;
+            b.v = (__expf(xv - mx) * inv_total) / q;
+            b.i = v;
+            best = amax2(best, b);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          ArgMax b;
+          b.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+          b.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+          best = amax2(best, b);
+        }
+        if (lane == 0) n_cand[1] = best.i;
+      }
+      __syncthreads();
+      mark_sampler(p, 64);
+      tok = n_cand[1];
+    } else {
+      tok = -2;                                           // overflow (or fewer than k finite columns): general path from the top-k on
+    }
+  }
+
+  if (tok == -1) {
   for (int v = tid; v < GSV_VOCAB_MAX; v += NT) {
     float l = GSV_NEG_INF;
     if (v < p.V) {
@@ -123,7 +337,6 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   __syncthreads();
   // the first sample of infer / infer_stream masks the suppressed tokens whatever initial_suppression_steps is
   // (t2s_model.py:415); infer_batched never does (:613)
-  const bool suppress = first ? (sp.suppress_first != 0) : (ngen < sp.suppress_steps);
   if (tid == 0) {
     if (trow >= 0) st_cg(&hk->trace_pos, trow + 1);
     if (suppress) {                                       // suppressed_tokens = [280, 486, EOS] (:170)
@@ -137,7 +350,6 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
 
   // (1) repetition penalty over the set of previous tokens (utils.py:20-27; duplicates in
   //     previous_tokens gather the same original score, so a set is equivalent)
-  const float rp = sp.repetition_penalty;
   if (rp != 1.0f) {
     const unsigned* seen = p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32);
     for (int v = tid; v < Vv; v += NT) {
@@ -210,7 +422,9 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
       for (int v = tid; v < Vv; v += NT) lg[v] = lg[v] / t;
     __syncthreads();
   }
+  }   // tok == -1: the general path's steps before the top-k
 
+  if (tok < 0) {
   // (4) top-k pivot = k-th largest value with multiplicity (utils.py:43-46); ties with the pivot survive.
   //     Exact radix select on an order-preserving integer image of the floats: 4 passes of 8 bits, each a
   //     256-bin block histogram (instead of k rounds of block arg-max).
@@ -290,8 +504,6 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   // (6) token = argmax(p / q), q ~ Exp(1) i.i.d. per column (utils.py:5-9)
   ArgMax best;
   best.v = -1.0f; best.i = 0x7fffffff;
-  const bool ext = hk_noise != nullptr && cnt < (unsigned long long)hk_noise_rows;
-  const uint2 key = make_uint2((uint32_t)sp.seed, (uint32_t)(sp.seed >> 32));
   for (int v = tid; v < Vv; v += NT) {
     float q;
     if (ext) {
@@ -307,7 +519,8 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
     best = amax2(best, b);
   }
   best = block_argmax(best, red_v, red_i);
-  int tok = best.i;
+  tok = best.i;
+  }   // tok < 0: general top-k / softmax / arg-max
 
   // bookkeeping by one thread; every value other CTAs read later goes through st.cg
   const int kvl = ll ? ll->kv_len : ld_cg(p.kv_len + slot);
@@ -328,6 +541,7 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
     __stcg(p.samp_count + slot, cnt + 1);
     if (tok < GSV_VOCAB_MAX) atomicOr(p.seen + (size_t)slot * (GSV_VOCAB_MAX / 32) + (tok >> 5), 1u << (tok & 31));
     if (stop) st_cg(p.active + slot, 0);
+    mark_sampler(p, 65);
     if (ll) {
       st_cg(p.kv_len + slot, kvl);
       if (ll->status_ll) ll_store(ll->status_ll, stop ? 0.f : 1.f, ll->tag);
@@ -337,16 +551,18 @@ __device__ void sample_slot(const GptParams& p, int slot, float* sm, const Sampl
   // next input: emb_audio[tok] * x_scale(=1) + (alpha*pe)[kv_len - Nx]  (:455-456, :727-728)
   if (!stop) {
     const T* emb = reinterpret_cast<const T*>(p.emb_audio) + (size_t)tok * p.d;
-    int pos = kvl - ld_cg(p.x_len + slot);
+    int pos = kvl - (pre ? pre->x_len : ld_cg(p.x_len + slot));
     pos = max(0, min(pos, p.n_pos - 1));
     const T* pe = reinterpret_cast<const T*>(p.pe_audio) + (size_t)pos * p.d;
     for (int c = tid; c < p.d; c += NT) {
+      const float pe_c = (pre && pre->pe_pos == pos && c == tid) ? pre->pe : Elem<T>::to_f(pe[c]);
       // the reference adds two T values and rounds to T
-      float s = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(emb[c]) + Elem<T>::to_f(pe[c])));
+      float s = Elem<T>::to_f(Elem<T>::from_f(Elem<T>::to_f(emb[c]) + pe_c));
       st_cg(p.xin + (size_t)slot * p.d + c, s);
       if (ll && ll->xin_ll) ll_store(ll->xin_ll + c, s, ll->tag);
       if (ll && ll->xin_smem) ll->xin_smem[c] = s;
     }
   }
+  mark_sampler(p, 66);
   __syncthreads();
 }

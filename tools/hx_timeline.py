@@ -19,10 +19,11 @@ m.debug_seed = 1
 m._single_setup(x, y, torch.zeros(1, 64, 1024), 15, 1.0, 1.0, 1.35, 10, 400)
 m._decode(25); torch.cuda.synchronize()
 G, MAXR = 64, 2048
-rec = torch.zeros(G * 2 * MAXR, dtype=torch.int64, device=dev)
+rec = torch.zeros((G + 1) * 2 * MAXR, dtype=torch.int64, device=dev)      # + the sampler's own region
 N.check(N.lib().gsv_gpt_set_timeline(m._ctx, rec.data_ptr(), MAXR, 0))
 m._decode(3); torch.cuda.synchronize()
-r = rec.cpu().numpy().reshape(G, MAXR, 2)
+rs = rec.cpu().numpy().reshape(G + 1, MAXR, 2)[G]
+r = rec.cpu().numpy().reshape(G + 1, MAXR, 2)[:G]
 names = {40: "  (attn: warp partial in smem)", 41: "  (attn: barrier passed)", 42: "  (attn: CTA partial merged)", 43: "  (all-read: poll done)",
          44: "  (all-read: barrier passed)", 45: "  (y1 inbox full)", 30: " S0 landed", 31: " S2 landed", 1: "layer start", 2: " qkv rows done, pushed", 3: " q/k/v gathered", 4: " attention done, pushed", 5: " att merged",
          6: " O partial published", 7: " all-read 1 done, pushed", 8: " y1 gathered, LN1 done", 9: " MLP-up done", 10: " MLP-down done, pushed",
@@ -47,3 +48,14 @@ print("head + sampling:")
 for k in range(k0, hi):
     v = T[:, k] - t0
     print(f"  {names.get(int(ids[k]), ids[k]):34s} {v.min():7d} {int(np.median(v)):7d} {v.max():7d}")
+
+# the sampler CTA's own markers (gpt_sample.cuh mark_sampler): one token's worth, ns after its head rows were published
+snames = {58: "sampler CTA: head rows published", 59: "logits polled out of L2", 60: "sample_slot entered", 61: "columns in registers, group maxima published",
+          62: "candidates compacted", 63: "pivot known", 64: "token known (warp 0: exp, sum, noise, arg-max)", 65: "bookkeeping stored", 66: "next input published"}
+ns = int(rs[0, 0])
+sid, st = rs[1:ns + 1, 0], rs[1:ns + 1, 1]
+b = np.where(sid == 58)[0]
+if len(b) >= 2:
+    print("sampler (second token of the launch):")
+    for k in range(b[1], b[2] if len(b) > 2 else ns):
+        print(f"  {snames.get(int(sid[k]), sid[k]):62s} {int(st[k] - st[b[1]]):7d}")
