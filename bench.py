@@ -339,7 +339,7 @@ def main():
     def launch_total():
         n = int(lib.gsv_gpt_launch_count(gpt._ctx)) + voc.launch_count()
         if voc._enc_ctx is not None:
-            n += int(lib.gsv_encp_launch_count(voc._enc_ctx))
+            n += voc.enc_launch_count()
         return n
 
     def barrier():

@@ -309,9 +309,14 @@ class SynthesizerTrn(FlowDecoder):
             N.check(N.lib().gsv_encp_create(C.byref(d), C.byref(ctx)))
         self._enc_ctx = ctx
 
+        self._enc_names = []
+        self._enc_dims = d
+        self._enc_lanes = {}
+
         def put(name, w, b=None):
             wd = w.to(device=self._device, dtype=dtype).contiguous()
             bd = b.to(device=self._device, dtype=dtype).contiguous() if b is not None else None
+            self._enc_names.append(name)
             self._enc_dev[name] = wd
             if bd is not None:
                 self._enc_dev[name + "#b"] = bd
@@ -347,8 +352,31 @@ class SynthesizerTrn(FlowDecoder):
         if self.is_v2pro and "ge_to512.weight" in raw:
             put("ge_to512", raw["ge_to512.weight"], raw["ge_to512.bias"])
 
+    def _lane_ctx(self, lane: int):
+        """Prior-encoder context ``lane`` (0 = the one streaming decode keeps its cross-chunk state in).  Further lanes share
+        the device weights and own only their scratch: independent utterances can go through the prior encoder on several
+        streams at once (``TTS._sovits_stage_device``) -- a single call is a chain of ~100 small dependent launches."""
+        if lane == 0:
+            return self._enc_ctx
+        if lane not in self._enc_lanes:
+            ctx = C.c_void_p()
+            with torch.cuda.device(self._device):
+                N.check(N.lib().gsv_encp_create(C.byref(self._enc_dims), C.byref(ctx)))
+            for name in self._enc_names:
+                b = self._enc_dev.get(name + "#b")
+                N.check(N.lib().gsv_encp_set_weight(ctx, name.encode(), self._enc_dev[name].data_ptr(), b.data_ptr() if b is not None else None))
+            self._enc_lanes[lane] = ctx
+        return self._enc_lanes[lane]
+
+    def enc_launch_count(self) -> int:
+        ctxs = ([self._enc_ctx] if self._enc_ctx is not None else []) + list(getattr(self, "_enc_lanes", {}).values())
+        return sum(int(N.lib().gsv_encp_launch_count(c)) for c in ctxs)
+
     def __del__(self):
         try:
+            for ctx in list(getattr(self, "_enc_lanes", {}).values()):
+                N.lib().gsv_encp_destroy(ctx)
+            self._enc_lanes = {}
             if self._enc_ctx is not None:
                 N.lib().gsv_encp_destroy(self._enc_ctx)
                 self._enc_ctx = None
@@ -358,11 +386,14 @@ class SynthesizerTrn(FlowDecoder):
 
     @torch.inference_mode()
     def prior(self, codes, text, ge, noise_scale=0.5, speed=1, stream_mode=False, valid_start_idx=None, overlap_len=None,
-              slice_indices=None, return_stats=False):
+              slice_indices=None, return_stats=False, lane: int = 0):
         """The front of ``decode`` (models.py:387-404): -> (z_p [1,inter,T'], y_mask [1,1,T'], ge for flow_dec, attn [4,T,Nt]
-        [, m_p, logs_p])."""
+        [, m_p, logs_p]).  ``lane`` picks the native context (``_lane_ctx``); streaming calls use lane 0."""
         if self._enc_ctx is None:
             raise N.NativeError("this SoVITS checkpoint carries no enc_p weights: decode() needs them")
+        if stream_mode and lane != 0:
+            raise ValueError("streaming decode keeps its cross-chunk state in lane 0")
+        enc_ctx = self._lane_ctx(lane)
         dev, dt = self._device, self._dtype
         codes = codes.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         text = text.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
@@ -376,7 +407,7 @@ class SynthesizerTrn(FlowDecoder):
         speed = float(speed)
         vs = int(valid_start_idx) if stream_mode else 0
         ov = int(overlap_len) if stream_mode else 0
-        tp = lib.gsv_encp_output_frames(self._enc_ctx, n, speed, 1 if stream_mode else 0, vs)
+        tp = lib.gsv_encp_output_frames(enc_ctx, n, speed, 1 if stream_mode else 0, vs)
         z_p = torch.empty(1, self.inter_channels, tp, device=dev, dtype=dt)
         attn = torch.empty(4, 2 * n, nt, device=dev, dtype=torch.float32)
         m_p = torch.empty(self.inter_channels, tp, device=dev, dtype=torch.float32) if return_stats else None
@@ -392,7 +423,7 @@ class SynthesizerTrn(FlowDecoder):
         seed = self.debug_seed if self.debug_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         frames = C.c_int(0)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        N.check(lib.gsv_encp_forward(self._enc_ctx, codes.data_ptr(), n, text.data_ptr(), nt, ge_c.data_ptr(), tg, speed,
+        N.check(lib.gsv_encp_forward(enc_ctx, codes.data_ptr(), n, text.data_ptr(), nt, ge_c.data_ptr(), tg, speed,
                                      1 if stream_mode else 0, vs, ov, sl.data_ptr() if sl is not None else None,
                                      sl.shape[0] if sl is not None else 0, noise.data_ptr() if noise is not None else None,
                                      float(noise_scale), seed, z_p.data_ptr(), m_p.data_ptr() if return_stats else None,

@@ -116,6 +116,14 @@ class TTS:
             cache[key] = torch.cuda.Stream(dev)
         return cache[key]
 
+    def _lane_streams(self, dev, n: int) -> List["torch.cuda.Stream"]:
+        """Streams of the prior-encoder lanes of a batched SoVITS stage (created once, like ``_side_stream``)."""
+        cache = self.__dict__.setdefault("_lane_stream_cache", {})
+        lst = cache.setdefault(str(dev), [])
+        while len(lst) < n:
+            lst.append(torch.cuda.Stream(dev))
+        return lst[:n]
+
     def _pick(self, table, path, what):
         if path is None:
             if not table:
@@ -219,29 +227,57 @@ class TTS:
         voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         return [self._clip(a.cpu().numpy()) for a in self._vocode_groups(voc, z_p, ge, max_frames)]
 
-    def _sovits_stage_device(self, vq, tokens, phones2, ge, noise_scale, speed, max_frames) -> List[torch.Tensor]:
+    PRIOR_LANES = 4
+
+    def _sovits_stage_device(self, vq, tokens, phones2, ge, noise_scale, speed, max_frames, lanes: Optional[int] = None) -> List[torch.Tensor]:
         """SoVITS stage on the CURRENT stream, no host synchronisation: the prior encoder per utterance (its attention must not
-        cross utterance boundaries), then flow + HiFi-GAN in padded, length-sorted groups; fp32 waveforms on the device."""
-        zs, gs, live = [], [], []
-        for i, (t, ph, g) in enumerate(zip(tokens, phones2, ge)):
-            if t.numel() == 0:                                   # EOS as the first token: nothing to say
-                continue
-            z_p, _mask, g2, _attn = vq.prior(t.view(1, 1, -1), ph.view(1, -1), g, noise_scale=noise_scale, speed=speed)
-            zs.append(z_p[0])
-            gs.append(g2[0])
-            live.append(i)
-        out = [torch.zeros(0, device=vq._device) for _ in tokens]
-        for i, a in zip(live, self._vocode_groups(vq, zs, gs, max_frames) if live else []):
+        cross utterance boundaries), then flow + HiFi-GAN in padded, length-sorted groups; fp32 waveforms on the device.
+        One prior-encoder call is ~100 small dependent launches (0.9-2 ms whatever the GPU could do beside it), so the
+        utterances are dealt over ``lanes`` native contexts on as many streams, forked from and joined back into the current
+        stream; per utterance the arithmetic is that of a single call (tested bit for bit against ``lanes=1``)."""
+        dev = vq._device
+        work = [i for i, t in enumerate(tokens) if t.numel() > 0]           # EOS as the first token: nothing to say
+        n_lanes = max(1, min(self.PRIOR_LANES if lanes is None else int(lanes), len(work)))
+        zs, gs = [], []
+        if n_lanes == 1:
+            for i in work:
+                z_p, _mask, g2, _attn = vq.prior(tokens[i].view(1, 1, -1), phones2[i].view(1, -1), ge[i], noise_scale=noise_scale, speed=speed)
+                zs.append(z_p[0])
+                gs.append(g2[0])
+        else:
+            cur = torch.cuda.current_stream(dev)
+            streams = self._lane_streams(dev, n_lanes)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            for lane, st in enumerate(streams):
+                st.wait_event(fork)
+            for k, i in enumerate(work):
+                lane = k % n_lanes
+                with torch.cuda.stream(streams[lane]):
+                    for t in (tokens[i], phones2[i], ge[i]):
+                        if t.is_cuda:
+                            t.record_stream(streams[lane])
+                    z_p, _mask, g2, _attn = vq.prior(tokens[i].view(1, 1, -1), phones2[i].view(1, -1), ge[i], noise_scale=noise_scale, speed=speed,
+                                                     lane=lane)
+                    for t in (z_p, g2):
+                        t.record_stream(cur)
+                zs.append(z_p[0])
+                gs.append(g2[0])
+            for st in streams:
+                cur.wait_stream(st)
+        out = [torch.zeros(0, device=dev) for _ in tokens]
+        for i, a in zip(work, self._vocode_groups(vq, zs, gs, max_frames) if work else []):
             out[i] = a
         return out
 
     @torch.inference_mode()
     def decode_batched(self, tokens: Sequence[torch.Tensor], phones2: Sequence[torch.Tensor], ge: Sequence[torch.Tensor],
-                       noise_scale: float = 0.5, speed: float = 1.0, sovits_model: Optional[str] = None, max_frames: int = 8192):
+                       noise_scale: float = 0.5, speed: float = 1.0, sovits_model: Optional[str] = None, max_frames: int = 8192,
+                       lanes: Optional[int] = None):
         """SoVITS stage of ``infer_batched`` for a list of utterances.  tokens[i] int64 [N_i], phones2[i] int64 [Nt_i],
         ge[i] [1,gin,1] -> AudioClips."""
         vq = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
-        return [self._clip(a.cpu().numpy()) for a in self._sovits_stage_device(vq, tokens, phones2, ge, noise_scale, speed, max_frames)]
+        return [self._clip(a.cpu().numpy()) for a in self._sovits_stage_device(vq, tokens, phones2, ge, noise_scale, speed, max_frames, lanes)]
 
     @torch.inference_mode()
     def infer_phones_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence, phones2: Sequence, ge: Sequence,

@@ -140,3 +140,14 @@ def test_batched_pipeline_overlap_matches_back_to_back(tmp_path):
         n = c.audio_data.shape[0] - 20 * 640                       # the tail sees the group's padded frames instead of the signal's end
         if n > 0:
             assert float(abs(c.audio_data[:n] - c0[i].audio_data[:n]).max()) < 2e-3, i
+    # the prior encoder of the utterances of one SoVITS stage dealt over several native contexts / streams: bit-equal clips
+    toks = [t for t in t0]
+    per_lane = {}
+    for lanes in (1, 3, 4):
+        vq.debug_seed = 5
+        per_lane[lanes] = tts.decode_batched(toks, ph2, ges, max_frames=1, lanes=lanes)
+    for lanes in (3, 4):
+        for i, (a, b) in enumerate(zip(per_lane[1], per_lane[lanes])):
+            assert a.audio_data.shape == b.audio_data.shape, (lanes, i)
+            assert a.audio_data.size == 0 or float(abs(a.audio_data - b.audio_data).max()) == 0.0, (lanes, i)
+
