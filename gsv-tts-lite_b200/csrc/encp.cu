@@ -285,6 +285,12 @@ struct gsv_encp_ctx {
   long long launches;
   size_t op;                  // call-site counter of the tensor-core launches of one forward
   std::vector<void*> owned;
+  // text branch of the last forward (embedding, encoder_text, MRTE text_pre and k/v projections -> ckv [Nt][2 Cm]): kept in
+  // its own buffer so that the next call on the same text can take it as is (gsv_encp_reuse_text)
+  void* text_ckv;
+  size_t text_ckv_bytes;
+  int text_n;                 // rows held (-1: none)
+  int text_reuse_next;
 };
 
 namespace {
@@ -414,17 +420,38 @@ int encp_forward_t(gsv_encp_ctx* ctx, const int64_t* codes, int n_codes, const i
   ctx->launches += 1;
   f.linear(q768, Tn, d.ssl_dim, "enc_p.ssl_proj", C, y);
   f.encoder(y, Tn, "enc_p.encoder_ssl.", L / 2, qkv, att, tmp, hid);
-  // text branch
-  const EW* emb = f.get("enc_p.text_embedding");
-  if (!emb) return f.rc;
-  embed_text_kernel<T><<<Nt, 32, 0, st>>>(text, reinterpret_cast<const T*>(emb->w), d.n_symbols, C, tx);
-  ctx->launches += 1;
-  f.encoder(tx, Nt, "enc_p.encoder_text.", L, qkv, att, tmp, hid);
+  // text branch: text -> the MRTE's keys / values ckv [Nt][2 Cm] (6 encoder layers + 2 linears = 45 launches).  It does not
+  // depend on the codes: the chunks of one streaming utterance after the first take it from the previous call.
+  const bool reuse_text = ctx->text_reuse_next && ctx->text_n == Nt && ctx->text_ckv != nullptr;
+  ctx->text_reuse_next = 0;
+  {
+    const size_t need = (size_t)Nt * 2 * Cm * el;
+    if (need > ctx->text_ckv_bytes) {
+      GSV_CUDA(cudaStreamSynchronize(st));
+      if (ctx->text_ckv) cudaFree(ctx->text_ckv);
+      ctx->text_ckv = nullptr; ctx->text_ckv_bytes = 0; ctx->text_n = -1;
+      GSV_CUDA(cudaMalloc(&ctx->text_ckv, need));
+      ctx->text_ckv_bytes = need;
+    }
+    ckv = reinterpret_cast<T*>(ctx->text_ckv);
+  }
+  if (!reuse_text || ctx->text_n != Nt) {
+    ctx->text_n = -1;
+    const EW* emb = f.get("enc_p.text_embedding");
+    if (!emb) return f.rc;
+    embed_text_kernel<T><<<Nt, 32, 0, st>>>(text, reinterpret_cast<const T*>(emb->w), d.n_symbols, C, tx);
+    ctx->launches += 1;
+    f.encoder(tx, Nt, "enc_p.encoder_text.", L, qkv, att, tmp, hid);
+    f.linear(tx, Nt, C, "enc_p.mrte.text_pre", Cm, tp);
+    f.linear(tp, Nt, Cm, "enc_p.mrte.cross_attention.kv", 2 * Cm, ckv);
+    if (f.rc) return f.rc;
+    ctx->text_n = Nt;
+  } else {
+    ctx->op += (size_t)4 * L + 2;              // the skipped call sites keep their tensor-map slots
+  }
   // MRTE (mrte_model.py:19-38)
   f.linear(y, Tn, C, "enc_p.mrte.c_pre", Cm, s);
-  f.linear(tx, Nt, C, "enc_p.mrte.text_pre", Cm, tp);
   f.linear(s, Tn, Cm, "enc_p.mrte.cross_attention.conv_q", Cm, cq);
-  f.linear(tp, Nt, Cm, "enc_p.mrte.cross_attention.kv", 2 * Cm, ckv);
   f.template attention<128>(cq, Cm, ckv, 2 * Cm, ckv + Cm, 2 * Cm, ca, Cm, Tn, Nt, d.mrte_heads, nullptr, nullptr, slices, n_slices, attn_out);
   f.linear(ca, Tn, Cm, "enc_p.mrte.cross_attention.conv_o", Cm, cx);
   if (f.rc) return f.rc;
@@ -479,6 +506,7 @@ extern "C" int gsv_encp_create(const gsv_encp_dims* dims, gsv_encp_ctx** out) {
   GSV_ARG(ctx != nullptr);
   ctx->dims = *dims;
   ctx->scratch = nullptr; ctx->scratch_bytes = 0; ctx->overlap = nullptr; ctx->ov_cur = 0; ctx->overlap_len = 0; ctx->overlap_len_prev = -1; ctx->launches = 0; ctx->op = 0;
+  ctx->text_ckv = nullptr; ctx->text_ckv_bytes = 0; ctx->text_n = -1; ctx->text_reuse_next = 0;
   GSV_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, dev));
   ctx->umma = gsv_umma_cache_create(ctx->num_sms);
   *out = ctx;
@@ -488,6 +516,14 @@ extern "C" int gsv_encp_create(const gsv_encp_dims* dims, gsv_encp_ctx** out) {
 extern "C" int gsv_encp_set_weight(gsv_encp_ctx* ctx, const char* name, const void* dev_weight, const void* dev_bias) {
   GSV_ARG(ctx && name && dev_weight);
   ctx->w[name] = EW{dev_weight, dev_bias};
+  ctx->text_n = -1;                            // whatever was computed with the old weights is stale
+  return GSV_OK;
+}
+
+// The next gsv_encp_forward call on this context carries the same text as the previous one: its text branch is reused.
+extern "C" int gsv_encp_reuse_text(gsv_encp_ctx* ctx, int on) {
+  GSV_ARG(ctx);
+  ctx->text_reuse_next = on ? 1 : 0;
   return GSV_OK;
 }
 
@@ -495,6 +531,7 @@ extern "C" int gsv_encp_destroy(gsv_encp_ctx* ctx) {
   if (!ctx) return GSV_OK;
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->overlap) cudaFree(ctx->overlap);
+  if (ctx->text_ckv) cudaFree(ctx->text_ckv);
   for (void* p : ctx->owned) cudaFree(p);
   gsv_umma_cache_destroy(ctx->umma);
   delete ctx;

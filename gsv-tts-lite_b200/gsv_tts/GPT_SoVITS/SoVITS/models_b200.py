@@ -386,9 +386,11 @@ class SynthesizerTrn(FlowDecoder):
 
     @torch.inference_mode()
     def prior(self, codes, text, ge, noise_scale=0.5, speed=1, stream_mode=False, valid_start_idx=None, overlap_len=None,
-              slice_indices=None, return_stats=False, lane: int = 0):
+              slice_indices=None, return_stats=False, lane: int = 0, text_unchanged: bool = False):
         """The front of ``decode`` (models.py:387-404): -> (z_p [1,inter,T'], y_mask [1,1,T'], ge for flow_dec, attn [4,T,Nt]
-        [, m_p, logs_p]).  ``lane`` picks the native context (``_lane_ctx``); streaming calls use lane 0."""
+        [, m_p, logs_p]).  ``lane`` picks the native context (``_lane_ctx``); streaming calls use lane 0.
+        ``text_unchanged``: the caller vouches that ``text`` holds what the previous call on this lane was given (the chunks
+        of one streaming utterance): the text branch of the encoder is not recomputed (``gsv_encp_reuse_text``)."""
         if self._enc_ctx is None:
             raise N.NativeError("this SoVITS checkpoint carries no enc_p weights: decode() needs them")
         if stream_mode and lane != 0:
@@ -423,6 +425,8 @@ class SynthesizerTrn(FlowDecoder):
         seed = self.debug_seed if self.debug_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         frames = C.c_int(0)
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if text_unchanged:
+            N.check(lib.gsv_encp_reuse_text(enc_ctx, 1))
         N.check(lib.gsv_encp_forward(enc_ctx, codes.data_ptr(), n, text.data_ptr(), nt, ge_c.data_ptr(), tg, speed,
                                      1 if stream_mode else 0, vs, ov, sl.data_ptr() if sl is not None else None,
                                      sl.shape[0] if sl is not None else 0, noise.data_ptr() if noise is not None else None,
@@ -437,8 +441,9 @@ class SynthesizerTrn(FlowDecoder):
 
     @torch.inference_mode()
     def decode(self, codes, text, ge, noise_scale=0.5, speed=1, cuda_graph=True, stream_mode=False, valid_start_idx=None,
-               overlap_len=None, slice_indices=None):
+               overlap_len=None, slice_indices=None, text_unchanged: bool = False):
         """models.py:385-429: codes [1,1,N] int64, text [1,Nt] int64, ge [1,gin,1|N] -> (audio [1,1,640 T'], attn [4,T,Nt]).
         ``cuda_graph`` is accepted for signature compatibility (the native path takes any length)."""
-        z_p, y_mask, ge2, attn = self.prior(codes, text, ge, noise_scale, speed, stream_mode, valid_start_idx, overlap_len, slice_indices)
+        z_p, y_mask, ge2, attn = self.prior(codes, text, ge, noise_scale, speed, stream_mode, valid_start_idx, overlap_len, slice_indices,
+                                            text_unchanged=text_unchanged)
         return self.flow_dec(z_p, y_mask, ge2), attn

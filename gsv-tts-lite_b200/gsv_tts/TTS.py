@@ -227,7 +227,7 @@ class TTS:
         voc = self._pick(self.sovits_models, sovits_model, "SoVITS").vq_model
         return [self._clip(a.cpu().numpy()) for a in self._vocode_groups(voc, z_p, ge, max_frames)]
 
-    PRIOR_LANES = 4
+    PRIOR_LANES = int(__import__('os').environ.get('GSV_PRIOR_LANES', '4'))
 
     def _sovits_stage_device(self, vq, tokens, phones2, ge, noise_scale, speed, max_frames, lanes: Optional[int] = None) -> List[torch.Tensor]:
         """SoVITS stage on the CURRENT stream, no host synchronisation: the prior encoder per utterance (its attention must not
@@ -508,7 +508,8 @@ class TTS:
                 gpt.hold_until_decode_resident(side)
                 pred.record_stream(side)
                 audio, attn = vq.decode(pred, ph2, ge, noise_scale=noise_scale, speed=speed, stream_mode=True,
-                                        valid_start_idx=st["valid_start"], overlap_len=overlap_len)
+                                        valid_start_idx=st["valid_start"], overlap_len=overlap_len,
+                                        text_unchanged=st["chunk_idx"] > 0)       # one utterance: the text branch of chunk 0 serves them all
                 flat = audio.reshape(-1)
                 n2 = flat.numel()
                 meta = torch.zeros(2, dtype=torch.int32, device=dev)          # SOLA offset, leading-silence offset

@@ -90,6 +90,7 @@ SYMBOLS = [
                                    _P, C.c_float, C.c_uint64, _P, _P, _P, _P, C.POINTER(C.c_int), _P]),
     ("gsv_encp_reset_stream", C.c_int, [_P]),
     ("gsv_encp_stream_rollback", C.c_int, [_P]),
+    ("gsv_encp_reuse_text", C.c_int, [_P, C.c_int]),
     ("gsv_encp_launch_count", C.c_int64, [_P]),
     ("gsv_glue_viterbi_monotonic", C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     ("gsv_glue_silence_offset", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -289,6 +289,12 @@ int gsv_encp_forward(gsv_encp_ctx* ctx, const int64_t* dev_codes, int n_codes, c
                      const float* dev_noise, float noise_scale, uint64_t seed, void* dev_z_p, float* dev_m_p, float* dev_logs_p,
                      float* dev_attn, int* out_frames, void* stream);
 int gsv_encp_reset_stream(gsv_encp_ctx* ctx);
+/* on != 0: the NEXT gsv_encp_forward call on this context carries the same dev_text contents (and n_text) as the previous
+ * one, so its text branch -- text_embedding, encoder_text, the MRTE's text_pre and k/v projections (models.py:199-204,
+ * mrte_model.py:24-25), 45 of the ~100 launches of a call, independent of the codes -- is taken from that call instead of
+ * recomputed (bit-identical: the same kernels on the same input).  The flag is consumed by the call; it is ignored when
+ * n_text differs or a weight was set in between.  TTS.infer_phones_stream sets it for every chunk after the first. */
+int gsv_encp_reuse_text(gsv_encp_ctx* ctx, int on);
 /* Undo the last stream_mode call's update of the cross-chunk state (one level; the previous tail is kept in a second
  * buffer): TTS.infer_phones_stream computes a held-back chunk ahead of time and drops it when the stream ends before the
  * next chunk boundary (the reference never decodes that chunk: t2s_model.py:540-553 merges it into the final one). */

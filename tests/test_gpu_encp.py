@@ -82,6 +82,33 @@ def test_prior_encoder_matches_oracle_and_reference_golden(dev, name, key, dtype
                                        return_stats=True)
         assert float(np.abs(m_c.cpu().numpy() - g[f"m_p_stream{i}"][0]).max()) < 1.5 * tol, i
     net.enc_p.y_overlap = None
+    # the text branch taken over from the previous call (the chunks of one utterance): bit-identical statistics; the flag is
+    # ignored when the text length differs, and a dropped chunk's state can be rolled back
+    got = {}
+    for reuse in (False, True):
+        net.enc_p.y_overlap = None
+        got[reuse] = []
+        for i, (n_codes, vs) in enumerate(g["stream_chunks"].tolist()):
+            out = net.prior(codes[:, :, :n_codes], text, ge16, stream_mode=True, valid_start_idx=vs, overlap_len=5, return_stats=True,
+                            text_unchanged=reuse and i > 0)
+            got[reuse].append((out[0].clone(), out[4].clone()))
+    for (z0, m0), (z1, m1) in zip(got[False], got[True]):
+        assert torch.equal(m0, m1)
+    shorter = text[:, :-2]
+    _, _, _, _, m_a, _ = net.prior(codes, shorter, ge16, return_stats=True, text_unchanged=True)      # stale flag: another length
+    _, _, _, _, m_b, _ = net.prior(codes, shorter, ge16, return_stats=True)
+    assert torch.equal(m_a, m_b)
+    net.enc_p.y_overlap = None
+    (n0, v0), (n1, v1) = g["stream_chunks"].tolist()[:2]
+    net.prior(codes[:, :, :n0], text, ge16, stream_mode=True, valid_start_idx=v0, overlap_len=5)
+    net.prior(codes[:, :, :n1 - 1], text, ge16, stream_mode=True, valid_start_idx=v1, overlap_len=5)   # decoded ahead, then dropped
+    net.enc_p.rollback()
+    _, _, _, _, m_r, _ = net.prior(codes[:, :, :n1], text, ge16, stream_mode=True, valid_start_idx=v1, overlap_len=5, return_stats=True,
+                                   text_unchanged=True)
+    assert torch.equal(m_r, got[False][1][1])
+    with pytest.raises(Exception):
+        net.enc_p.rollback(); net.enc_p.rollback()
+    net.enc_p.y_overlap = None
 
 
 def test_decode_is_prior_then_flow_dec_and_other_sizes(dev):
