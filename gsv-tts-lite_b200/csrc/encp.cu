@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_kernel(const T* __restrict
     rk[lane] = a;
   }
   __syncwarp();
-  // pass 1: scores, keys over lanes
+  // pass 1: scores, keys over lanes (the query in registers: read through the shared array it would be re-loaded for every
+  // product, the scores being written to the same array)
+  float qr[DK];
+#pragma unroll
+  for (int d = 0; d < DK; ++d) qr[d] = qs[d];
   float mx = -3.0e38f;
   for (int j = lane; j < Tk; j += 32) {
     const uint4* kr = reinterpret_cast<const uint4*>(k + (size_t)j * ldk + h * DK);
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_kernel(const T* __restrict
       float kf[8];
       unpack8<T>(kr[c], kf);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a = fmaf(qs[c * 8 + e], kf[e], a);
+      for (int e = 0; e < 8; ++e) a = fmaf(qr[c * 8 + e], kf[e], a);
     }
     if (rel_k != nullptr) {
       const int off = j - i;
@@ -147,27 +151,38 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attn_kernel(const T* __restrict
     if (probs != nullptr) probs[((size_t)h * Tq + i) * Tk + j] = pj;
   }
   __syncwarp();
-  // pass 2: P . V, output dimensions over lanes
-  float o[DK / 32];
+  // pass 2: P . V -- four output dimensions per lane (lanes 0 .. DK/4 - 1), the rows of eight keys in flight.  (One dimension
+  // triple per lane and one key per iteration made this loop a chain of Tk dependent L2 round trips: 66 us per call at
+  // 400 frames, the largest item of a chunk's prior encoder.)  Per dimension the keys are still summed in ascending order.
+  constexpr int NL = DK / 4;
+  if (lane < NL) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    const T* vbase = v + h * DK + lane * 4;
+    auto accum = [&](const uint2& r, float pj) {
+      const float2 a = Elem<T>::to_f2(r.x), b2 = Elem<T>::to_f2(r.y);
+      o[0] = fmaf(pj, a.x, o[0]); o[1] = fmaf(pj, a.y, o[1]); o[2] = fmaf(pj, b2.x, o[2]); o[3] = fmaf(pj, b2.y, o[3]);
+    };
+    int j = 0;
+    for (; j + 8 <= Tk; j += 8) {
+      uint2 r[8];
 #pragma unroll
-  for (int c = 0; c < DK / 32; ++c) o[c] = 0.f;
-  for (int j = 0; j < Tk; ++j) {
-    const float pj = sc[j];
-    const T* vr = v + (size_t)j * ldv + h * DK;
+      for (int u = 0; u < 8; ++u) r[u] = *reinterpret_cast<const uint2*>(vbase + (size_t)(j + u) * ldv);
 #pragma unroll
-    for (int c = 0; c < DK / 32; ++c) o[c] = fmaf(pj, Elem<T>::to_f(vr[c * 32 + lane]), o[c]);
-  }
-  if (rel_v != nullptr) {
-    for (int off = -WIN; off <= WIN; ++off) {
-      const int j = i + off;
-      if (j < 0 || j >= Tk) continue;
-      const float pj = sc[j];
-#pragma unroll
-      for (int c = 0; c < DK / 32; ++c) o[c] = fmaf(pj, Elem<T>::to_f(rel_v[(off + WIN) * DK + c * 32 + lane]), o[c]);
+      for (int u = 0; u < 8; ++u) accum(r[u], sc[j + u]);
     }
-  }
+    for (; j < Tk; ++j) accum(*reinterpret_cast<const uint2*>(vbase + (size_t)j * ldv), sc[j]);
+    if (rel_v != nullptr) {
+      for (int off = -WIN; off <= WIN; ++off) {
+        const int jr = i + off;
+        if (jr < 0 || jr >= Tk) continue;
+        accum(*reinterpret_cast<const uint2*>(rel_v + (off + WIN) * DK + lane * 4), sc[jr]);
+      }
+    }
+    __align__(8) T res[4];
 #pragma unroll
-  for (int c = 0; c < DK / 32; ++c) out[(size_t)i * ldo + h * DK + c * 32 + lane] = Elem<T>::from_f(o[c]);
+    for (int e = 0; e < 4; ++e) res[e] = Elem<T>::from_f(o[e]);
+    *reinterpret_cast<uint2*>(out + (size_t)i * ldo + h * DK + lane * 4) = *reinterpret_cast<const uint2*>(res);
+  }
 }
 
 // ---- MRTE: x = attn_out + s + ge (mrte_model.py:36); ge [C][Tg] in torch layout, Tg == 1 or T -------------------------
