@@ -478,7 +478,7 @@ def main():
             "config": {"workload": WORKLOAD, "l2": "256 MB flush between timed steps; 152 MB of weights (> L2) streamed per token",
                        "api": "gsv_tts.TTS.infer_phones_stream (models from TTS.load_gpt_model / load_sovits_model)",
                        "parallelism": f"{world} independent utterance streams, rank 0 reads the checkpoints, NCCL broadcast GPU to GPU at load only",
-                       "overlap": "prior encoder + vocoder of chunk c on a second stream while chunk c+1 decodes on 64 SMs",
+                       "overlap": "prior encoder + vocoder of chunk c on a second stream while chunk c+1 decodes on 64 SMs; held-back chunks decoded ahead of their yield (same clips, same order)",
                        "reference_arm_sample": f"{REF_SAMPLE_TOKENS} tokens / {REF_SAMPLE_TOKENS // CHUNK} vocoder chunks per step (per-token rate)"},
             "rtf": (ms_total / 1e3 / args.steps) / audio_s, "ttft_ms": ttft_ms,
             "roofline": roofline, "cpu_baseline": cpu_base,

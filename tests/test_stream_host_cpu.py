@@ -148,3 +148,46 @@ def test_two_launches_stay_in_flight_and_chunks_are_handed_out_behind_them():
     # EOS at step 45: five launches of 10 steps do the work, the sixth was queued speculatively and finds the sequence stopped
     assert sum(1 for k in kinds if k == "decode") == 6
     assert kinds[-2:] == ["ready", "yield"] and log[-1][2] is True
+
+
+@pytest.mark.parametrize("boost", [True, False])
+@pytest.mark.parametrize("eos_at,force", [(None, 40), (37, None), (31, None), (None, 34), (5, None), (None, 9)])
+def test_held_chunks_are_reported_early_and_only_when_they_can_still_be_yielded(boost, eos_at, force):
+    """``on_chunk_held``: called with a chunk the moment it is complete when the reference's order holds it back (never for
+    the boosted first chunk, which is yielded at once, and never for a chunk already known to be dropped because the stream
+    has stopped); the object reported is the object yielded later, or it is never yielded (the stream ended first and the
+    final yield covers it) -- and the yields themselves are those of the reference loop."""
+    chunk = 10
+    script = scripted(64, eos_at, 11)
+    log = []
+    m = make_model(script, 200, log)
+    x = torch.zeros(1, 4, dtype=torch.int64)
+    held, events = [], []
+
+    def on_held(t):
+        held.append(t)
+        events.append(("held", t.numel()))
+
+    got = []
+    for t, f in m.infer_stream(x, x, torch.zeros(1, 4, 1024), stream_chunk=chunk, boost_first_chunk=boost, force_steps=force,
+                               on_chunk_held=on_held):
+        got.append((t, f))
+        events.append(("yield", t.numel(), f))
+    want = list(reference_stream(script, 200, chunk, boost, force))
+    assert [(t.view(-1).tolist(), f) for t, f in got] == want
+    yielded_nonfinal = [t for t, f in got if not f]
+    first_boosted = 1 if (boost and yielded_nonfinal) else 0
+    # every non-final yield except the boosted first chunk was reported before, as the same object, in the same order
+    assert len(held) >= len(yielded_nonfinal) - first_boosted
+    for t, h in zip(yielded_nonfinal[first_boosted:], held):
+        assert t is h
+    # at most one reported chunk is never yielded: the one the final yield covers
+    assert len(held) - (len(yielded_nonfinal) - first_boosted) in (0, 1)
+    # a report always precedes its yield, with exactly one other yield (the previous chunk) allowed in between
+    for h in held:
+        i = events.index(("held", h.numel()))
+        later = [e for e in events[i + 1:] if e[0] == "yield" and e[1] == h.numel() and not e[2]]
+        assert len(later) <= 1
+    # a stream that has stopped on a chunk boundary does not report the chunk it is about to drop
+    if force is not None and force % chunk == 0 and eos_at is None:
+        assert all(h.numel() < force for h in held)
