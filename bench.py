@@ -551,6 +551,18 @@ def metric_blocks(tts, gpt, voc, timer, spaths, dev, dtype, pk, rank, world, dis
     out["config3"] = {"workload": "128 mixed requests (Nx U{40..120}, Ny U{75..250}, length U{50..250}) through 32 slots, V2Pro-size GPT",
                       "tokens": n3, "ms": t3 * 1e3, "tok_s": n3 / t3, "audio_s_per_s": n3 * 0.04 / t3}
 
+    # the same 128 requests handed to the slot scheduler longest predicted first (TTS.infer_features_batched(queue_order=...)):
+    # the batch drains with short requests instead of a few long ones (ideal schedule 609 decode steps instead of 732).  The
+    # predictor is max_new -- here the known target length, i.e. a perfect one; a text-length predictor would do less well.
+    try:
+        gpt.debug_seed = 5
+        t3l, toksl = sync_time(lambda: tts.infer_features_batched(xs, bs, ys, max_new=mx, queue_order="longest_first"))
+        n3l = sum(int(t.numel()) for t in toksl)
+        out["config3_longest_first"] = {"workload": "config 3's 128 requests, queue ordered longest predicted first (predictor: the known target length)",
+                                        "tokens": n3l, "ms": t3l * 1e3, "tok_s": n3l / t3l, "audio_s_per_s": n3l * 0.04 / t3l}
+    except Exception as e:      # a side measurement: never in the way of the blocks below
+        out["config3_longest_first"] = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- config 4: 32 utterances per GPU, dealt over the ranks by predicted length, continuous batch + vocoder per rank
     n4 = 32 * world
     xs, ys, bs, mx = mixed_requests(n4, 4321, dev, dtype)

@@ -183,14 +183,31 @@ class TTS:
 
     @torch.inference_mode()
     def infer_features_batched(self, phoneme_ids: Sequence, bert: Sequence, prompt_tokens: Sequence,
-                               gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0, max_new=None):
-        """Continuous-batched GPT stage of ``infer_batched`` (TTS.py:695-703): token lists in request order."""
+                               gpt_model: Optional[str] = None, top_k=15, top_p=1.0, temperature=1.0, max_new=None,
+                               queue_order: Optional[str] = None):
+        """Continuous-batched GPT stage of ``infer_batched`` (TTS.py:695-703): token lists in request order.
+        ``queue_order="longest_first"`` hands the requests to the slot scheduler longest predicted first (``max_new[i]`` where
+        given, else the phoneme count): the batch then drains with short requests, not with a few long ones holding a handful
+        of slots while the others stand empty (longest-processing-time-first; on BASELINE config 3 the ideal schedule is 609
+        decode steps instead of 732).  Results come back in request order either way; a request's noise stream is keyed by its
+        place in the queue, so its sampled tokens differ between the two orders (both are samples of the same distribution)."""
         gpt = self._pick(self.gpt_models, gpt_model, "GPT").t2s_model
-        outs, order = gpt.infer_batched(list(phoneme_ids), list(prompt_tokens), list(bert), top_k=top_k, top_p=top_p,
-                                        temperature=temperature, max_new=max_new)
-        res = [None] * len(outs)
+        n = len(phoneme_ids)
+        perm = list(range(n))
+        if queue_order == "longest_first":
+            def predicted(i):
+                if max_new is not None and int(max_new[i]) > 0:
+                    return int(max_new[i])
+                return 10 ** 9 + len(phoneme_ids[i])              # no cap given: the longer text first
+            perm.sort(key=lambda i: -predicted(i))                # stable: ties keep the caller's order
+        elif queue_order not in (None, "fifo"):
+            raise ValueError(f"queue_order must be None, 'fifo' or 'longest_first', not {queue_order!r}")
+        outs, order = gpt.infer_batched([phoneme_ids[i] for i in perm], [prompt_tokens[i] for i in perm], [bert[i] for i in perm],
+                                        top_k=top_k, top_p=top_p, temperature=temperature,
+                                        max_new=[max_new[i] for i in perm] if max_new is not None else None)
+        res = [None] * n
         for o, i in zip(outs, order.tolist()):
-            res[i] = o
+            res[perm[i]] = o
         return res
 
     def _vocode_groups(self, voc, z_p: Sequence[torch.Tensor], ge: Sequence[torch.Tensor], max_frames: int) -> List[torch.Tensor]:
